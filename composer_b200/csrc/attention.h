@@ -1,0 +1,21 @@
+// Internal (C++) interface of the attention kernels (attention.cu).
+#pragma once
+
+#include "common.cuh"
+
+namespace cb200 {
+
+// qkv: [B, T, 3E] bf16 (c_attn output; q | k | v thirds, head h at columns h*D).
+// out: [B, T, E] bf16 (heads merged).  lse: [B, H, T] fp32, log2 domain.
+int attention_fwd(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse, int B, int T, int H, int D, float scale,
+                  const DropoutParams& drop, uint32_t layer, cudaStream_t s);
+
+// delta: [B, H, T] fp32 scratch.  dq_acc: [B, T, E] fp32, must be zero on entry and is zero again on exit.
+// dqkv: [B, T, 3E] bf16 gradient of c_attn's output.
+int attention_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* out, const __nv_bfloat16* dout, const float* lse,
+                  float* delta, float* dq_acc, __nv_bfloat16* dqkv, int B, int T, int H, int D, float scale,
+                  const DropoutParams& drop, uint32_t layer, cudaStream_t s);
+
+int attention_mask_export(uint8_t* mask, int B, int T, int H, const DropoutParams& drop, uint32_t layer, cudaStream_t s);
+
+}  // namespace cb200

@@ -1,0 +1,19 @@
+// Internal (C++) interface of the decoding kernels (decode.cu).
+#pragma once
+
+#include "common.cuh"
+
+namespace cb200 {
+
+// qkv: [B, 3E] bf16 row of the new token; kcache/vcache: [B, H, t_max, D] bf16 (one layer);
+// out: [B, E] bf16; *pos_ptr = position of the new token (device memory).
+int decode_attention(const __nv_bfloat16* qkv, __nv_bfloat16* kcache, __nv_bfloat16* vcache, __nv_bfloat16* out,
+                     const int* pos_ptr, int B, int H, int D, int t_max, float scale, cudaStream_t s);
+int decode_embed(const int32_t* cur, const float* wte, const float* wpe, __nv_bfloat16* out, const int* pos_ptr, int B,
+                 int E, int vocab, cudaStream_t s);
+// pos_ptr[0] = position, pos_ptr[1] = ticket scratch (must be 0); step_ptr = output column.
+int sample_tokens(const float* logits, int ld, int V, float temperature, uint64_t seed, int seq_base, int32_t* out_ids,
+                  int out_ld, int32_t* cur, const int32_t* forced, int forced_ld, int* pos_ptr, int* step_ptr,
+                  float* u_out, int B, cudaStream_t s);
+
+}  // namespace cb200

@@ -1,0 +1,464 @@
+// HBM-bound kernels of the training path: embedding gather (+positional add,
+// dropout) and its scatter-add backward, LayerNorm forward/backward, bias
+// gradients (+dropout backward), TF-style Adam on the flat parameter arena,
+// and the bf16 shadow refresh.  All are one-pass, 128-bit vectorised, one
+// warp per token row where rows are reduced.
+#include "elementwise.h"
+
+namespace cb200 {
+
+// ---------------------------------------------------------------------------
+// Embedding: h = dropout(wte[ids] + wpe[pos0 + t])
+// Reference: SharedTokenEmbedding.call(mode='embedding') transformer.py:120-138,
+// wpe lookup :786, sum :793, dropout :794.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+embed_fwd_kernel(const int32_t* __restrict__ ids, const float* __restrict__ wte, const float* __restrict__ wpe,
+                 __nv_bfloat16* __restrict__ out, int rows, int T, int E, int pos0, int vocab, DropoutParams drop) {
+    const int warps_per_block = blockDim.x >> 5;
+    const int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    int id = ids[row];
+    id = min(max(id, 0), vocab - 1);
+    const int pos = pos0 + (row % T);
+    const float* te = wte + static_cast<size_t>(id) * E;
+    const float* pe = wpe + static_cast<size_t>(pos) * E;
+    for (int c8 = lane; c8 < E / 8; c8 += 32) {
+        const float4 a0 = __ldg(reinterpret_cast<const float4*>(te + c8 * 8));
+        const float4 a1 = __ldg(reinterpret_cast<const float4*>(te + c8 * 8 + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(pe + c8 * 8));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(pe + c8 * 8 + 4));
+        float f[8] = {a0.x + b0.x, a0.y + b0.y, a0.z + b0.z, a0.w + b0.w,
+                      a1.x + b1.x, a1.y + b1.y, a1.z + b1.z, a1.w + b1.w};
+        if (drop.threshold16 != 0) {
+            const Philox4 r = drop_bits_rowmajor(drop, SITE_EMBD, 0, row, c8);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = (drop_u16(r, e) < drop.threshold16) ? 0.f : f[e] * drop.keep_scale;
+        }
+        uint4 o;
+        o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]);
+        o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+        *reinterpret_cast<uint4*>(out + static_cast<size_t>(row) * E + c8 * 8) = o;
+    }
+}
+
+int embed_fwd(const int32_t* ids, const float* wte, const float* wpe, __nv_bfloat16* out, int B, int T, int E,
+              int pos0, int vocab, const DropoutParams& drop, cudaStream_t s) {
+    CB200_REQUIRE(E % 8 == 0, "embedding size must be a multiple of 8");
+    const int rows = B * T;
+    if (rows == 0) return 0;
+    embed_fwd_kernel<<<(rows + 7) / 8, 256, 0, s>>>(ids, wte, wpe, out, rows, T, E, pos0, vocab, drop);
+    CB200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// Backward: dWte[ids[b,t]] += g[b,t], dWpe[pos0+t] += sum_b g[b,t], where
+// g = dropout_bwd(dh).  One block per position t; a thread owns 4 columns.
+__global__ void __launch_bounds__(256)
+embed_bwd_kernel(const int32_t* __restrict__ ids, const __nv_bfloat16* __restrict__ dh, float* __restrict__ dwte,
+                 float* __restrict__ dwpe, int B, int T, int E, int pos0, int vocab, DropoutParams drop) {
+    const int t = blockIdx.x;
+    for (int c4 = threadIdx.x; c4 < E / 4; c4 += blockDim.x) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int b = 0; b < B; ++b) {
+            const int row = b * T + t;
+            const uint2 raw = *reinterpret_cast<const uint2*>(dh + static_cast<size_t>(row) * E + c4 * 4);
+            const float2 lo = unpack_bf16(raw.x), hi = unpack_bf16(raw.y);
+            float g[4] = {lo.x, lo.y, hi.x, hi.y};
+            if (drop.threshold16 != 0) {
+                const Philox4 r = drop_bits_rowmajor(drop, SITE_EMBD, 0, row, c4 >> 1);
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    g[e] = (drop_u16(r, (c4 & 1) * 4 + e) < drop.threshold16) ? 0.f : g[e] * drop.keep_scale;
+            }
+            int id = ids[row];
+            id = min(max(id, 0), vocab - 1);
+            float* dst = dwte + static_cast<size_t>(id) * E + c4 * 4;
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(g[0]), "f"(g[1]), "f"(g[2]),
+                         "f"(g[3])
+                         : "memory");
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[e] += g[e];
+        }
+        float* dp = dwpe + static_cast<size_t>(pos0 + t) * E + c4 * 4;
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dp), "f"(acc[0]), "f"(acc[1]), "f"(acc[2]),
+                     "f"(acc[3])
+                     : "memory");
+    }
+}
+
+int embed_bwd(const int32_t* ids, const __nv_bfloat16* dh, float* dwte, float* dwpe, int B, int T, int E, int pos0,
+              int vocab, const DropoutParams& drop, cudaStream_t s) {
+    if (B * T == 0) return 0;
+    const int threads = (E / 4) < 256 ? ((E / 4 + 31) / 32) * 32 : 256;
+    embed_bwd_kernel<<<T, threads, 0, s>>>(ids, dh, dwte, dwpe, B, T, E, pos0, vocab, drop);
+    CB200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// LayerNorm forward (Keras LayerNormalization(epsilon), transformer.py:551,
+// 563, 694): biased variance over the last axis, eps inside the rsqrt.
+// One warp per row; the row stays in registers between the two passes.
+// ---------------------------------------------------------------------------
+template <int VPL>  // 8-element vectors per lane: E = 256 * VPL
+__global__ void __launch_bounds__(256)
+layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, float* __restrict__ stats,
+                     int rows, int E, float eps) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    float f[VPL][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * E + (v * 32 + lane) * 8);
+        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 p = unpack_bf16(w[e]);
+            f[v][2 * e] = p.x; f[v][2 * e + 1] = p.y;
+            sum += p.x + p.y;
+        }
+    }
+    const float mean = warp_sum(sum) / E;
+    float sq = 0.f;
+#pragma unroll
+    for (int v = 0; v < VPL; ++v)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { const float d = f[v][e] - mean; sq += d * d; }
+    const float rstd = rsqrtf(warp_sum(sq) / E + eps);
+    if (lane == 0 && stats != nullptr) {
+        stats[2 * static_cast<size_t>(row)] = mean;
+        stats[2 * static_cast<size_t>(row) + 1] = rstd;
+    }
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+        const int c = (v * 32 + lane) * 8;
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c + 4));
+        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = (f[v][e] - mean) * rstd * g[e] + b[e];
+        uint4 out;
+        out.x = pack_bf16(o[0], o[1]); out.y = pack_bf16(o[2], o[3]);
+        out.z = pack_bf16(o[4], o[5]); out.w = pack_bf16(o[6], o[7]);
+        *reinterpret_cast<uint4*>(y + static_cast<size_t>(row) * E + c) = out;
+    }
+}
+
+int layernorm_fwd(const __nv_bfloat16* x, const float* gamma, const float* beta, __nv_bfloat16* y, float* stats,
+                  int rows, int E, float eps, cudaStream_t s) {
+    CB200_REQUIRE(E % 256 == 0 && E <= 2048, "LayerNorm needs the embedding size to be a multiple of 256 (<= 2048), got %d", E);
+    if (rows == 0) return 0;
+    const int grid = (rows + 7) / 8;
+    switch (E / 256) {
+        case 1: layernorm_fwd_kernel<1><<<grid, 256, 0, s>>>(x, gamma, beta, y, stats, rows, E, eps); break;
+        case 2: layernorm_fwd_kernel<2><<<grid, 256, 0, s>>>(x, gamma, beta, y, stats, rows, E, eps); break;
+        case 3: layernorm_fwd_kernel<3><<<grid, 256, 0, s>>>(x, gamma, beta, y, stats, rows, E, eps); break;
+        case 4: layernorm_fwd_kernel<4><<<grid, 256, 0, s>>>(x, gamma, beta, y, stats, rows, E, eps); break;
+        case 8: layernorm_fwd_kernel<8><<<grid, 256, 0, s>>>(x, gamma, beta, y, stats, rows, E, eps); break;
+        default: set_error("unsupported embedding size %d for LayerNorm", E); return -1;
+    }
+    CB200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// LayerNorm backward.  dy = dy_a (+ dy_b); with xhat = (x - mean) * rstd:
+//   dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma
+//   dx_out = dx (+ dres) ; dgamma += sum_rows dy * xhat ; dbeta += sum_rows dy
+// Persistent blocks: each warp walks rows with a grid stride and keeps its
+// dgamma/dbeta partials in registers; one smem reduction + atomics at the end.
+// ---------------------------------------------------------------------------
+template <int VPL>
+__global__ void __launch_bounds__(256)
+layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy_a, const __nv_bfloat16* __restrict__ dy_b,
+                     const __nv_bfloat16* __restrict__ x, const float* __restrict__ stats,
+                     const float* __restrict__ gamma, const __nv_bfloat16* __restrict__ dres,
+                     __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                     int rows, int E) {
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int warps_total = gridDim.x * (blockDim.x >> 5);
+    float gam[VPL][8], pg[VPL][8], pb[VPL][8];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+        const int c = (v * 32 + lane) * 8;
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
+        gam[v][0] = g0.x; gam[v][1] = g0.y; gam[v][2] = g0.z; gam[v][3] = g0.w;
+        gam[v][4] = g1.x; gam[v][5] = g1.y; gam[v][6] = g1.z; gam[v][7] = g1.w;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { pg[v][e] = 0.f; pb[v][e] = 0.f; }
+    }
+    for (int row = blockIdx.x * (blockDim.x >> 5) + warp; row < rows; row += warps_total) {
+        const float mean = stats[2 * static_cast<size_t>(row)], rstd = stats[2 * static_cast<size_t>(row) + 1];
+        float dyv[VPL][8], xh[VPL][8];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            const size_t off = static_cast<size_t>(row) * E + (v * 32 + lane) * 8;
+            const uint4 ra = *reinterpret_cast<const uint4*>(dy_a + off);
+            const uint4 rx = *reinterpret_cast<const uint4*>(x + off);
+            uint4 rb = make_uint4(0, 0, 0, 0);
+            if (dy_b != nullptr) rb = *reinterpret_cast<const uint4*>(dy_b + off);
+            const uint32_t wa[4] = {ra.x, ra.y, ra.z, ra.w}, wx[4] = {rx.x, rx.y, rx.z, rx.w}, wb[4] = {rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 a = unpack_bf16(wa[e]), b = unpack_bf16(wb[e]), xx = unpack_bf16(wx[e]);
+                dyv[v][2 * e] = a.x + b.x; dyv[v][2 * e + 1] = a.y + b.y;
+                xh[v][2 * e] = (xx.x - mean) * rstd; xh[v][2 * e + 1] = (xx.y - mean) * rstd;
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float g = dyv[v][e] * gam[v][e];
+                s1 += g; s2 += g * xh[v][e];
+                pg[v][e] += dyv[v][e] * xh[v][e];
+                pb[v][e] += dyv[v][e];
+            }
+        }
+        s1 = warp_sum(s1) / E;
+        s2 = warp_sum(s2) / E;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            const size_t off = static_cast<size_t>(row) * E + (v * 32 + lane) * 8;
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = rstd * (dyv[v][e] * gam[v][e] - s1 - xh[v][e] * s2);
+            if (dres != nullptr) {
+                const uint4 rr = *reinterpret_cast<const uint4*>(dres + off);
+                const uint32_t wr[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { const float2 r = unpack_bf16(wr[e]); o[2 * e] += r.x; o[2 * e + 1] += r.y; }
+            }
+            uint4 out;
+            out.x = pack_bf16(o[0], o[1]); out.y = pack_bf16(o[2], o[3]);
+            out.z = pack_bf16(o[4], o[5]); out.w = pack_bf16(o[6], o[7]);
+            *reinterpret_cast<uint4*>(dx + off) = out;
+        }
+    }
+    // cross-warp reduction of the dgamma / dbeta partials through shared memory
+    extern __shared__ float red[];   // [2][E]
+    for (int i = threadIdx.x; i < 2 * E; i += blockDim.x) red[i] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int v = 0; v < VPL; ++v)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int c = (v * 32 + lane) * 8 + e;
+            atomicAdd(&red[c], pg[v][e]);
+            atomicAdd(&red[E + c], pb[v][e]);
+        }
+    __syncthreads();
+    for (int i = threadIdx.x; i < E; i += blockDim.x) {
+        atomicAdd(&dgamma[i], red[i]);
+        atomicAdd(&dbeta[i], red[E + i]);
+    }
+}
+
+int layernorm_bwd(const __nv_bfloat16* dy_a, const __nv_bfloat16* dy_b, const __nv_bfloat16* x, const float* stats,
+                  const float* gamma, const __nv_bfloat16* dres, __nv_bfloat16* dx, float* dgamma, float* dbeta,
+                  int rows, int E, cudaStream_t s) {
+    CB200_REQUIRE(E % 256 == 0 && E <= 1024, "LayerNorm backward needs E %% 256 == 0 and E <= 1024, got %d", E);
+    if (rows == 0) return 0;
+    int grid = (rows + 7) / 8;
+    const int cap = 2 * device_sm_count_ew();
+    if (grid > cap) grid = cap;
+    const size_t smem = 2 * E * sizeof(float);
+    switch (E / 256) {
+        case 1: layernorm_bwd_kernel<1><<<grid, 256, smem, s>>>(dy_a, dy_b, x, stats, gamma, dres, dx, dgamma, dbeta, rows, E); break;
+        case 2: layernorm_bwd_kernel<2><<<grid, 256, smem, s>>>(dy_a, dy_b, x, stats, gamma, dres, dx, dgamma, dbeta, rows, E); break;
+        case 3: layernorm_bwd_kernel<3><<<grid, 256, smem, s>>>(dy_a, dy_b, x, stats, gamma, dres, dx, dgamma, dbeta, rows, E); break;
+        case 4: layernorm_bwd_kernel<4><<<grid, 256, smem, s>>>(dy_a, dy_b, x, stats, gamma, dres, dx, dgamma, dbeta, rows, E); break;
+        default: set_error("unsupported embedding size %d for LayerNorm backward", E); return -1;
+    }
+    CB200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Bias gradient (+ dropout backward):  g = dropout_bwd(dy);  dbias += colsum(g);
+// optionally writes g (the dgrad/wgrad operand) when dropout is active.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+bias_grad_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ g_out, float* __restrict__ dbias,
+                 int rows, int N, int rows_per_block, DropoutParams drop, uint32_t site, uint32_t layer) {
+    extern __shared__ float red[];   // [N]
+    for (int i = threadIdx.x; i < N; i += blockDim.x) red[i] = 0.f;
+    __syncthreads();
+    const int groups = N / 8;                      // 8-column groups per row
+    const int r0 = blockIdx.x * rows_per_block;
+    const int r1 = min(rows, r0 + rows_per_block);
+    const int total = (r1 - r0) * groups;
+    // a thread keeps the same column group when blockDim % groups == 0; otherwise fall back to smem atomics per item
+    const bool fixed_col = (blockDim.x % groups) == 0;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int my_group = threadIdx.x % groups;
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        const int row = r0 + idx / groups;
+        const int grp = idx % groups;
+        const size_t off = static_cast<size_t>(row) * N + grp * 8;
+        const uint4 raw = *reinterpret_cast<const uint4*>(dy + off);
+        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { const float2 p = unpack_bf16(w[e]); f[2 * e] = p.x; f[2 * e + 1] = p.y; }
+        if (drop.threshold16 != 0) {
+            const Philox4 r = drop_bits_rowmajor(drop, site, layer, row, grp);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = (drop_u16(r, e) < drop.threshold16) ? 0.f : f[e] * drop.keep_scale;
+            if (g_out != nullptr) {
+                uint4 o;
+                o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]);
+                o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+                *reinterpret_cast<uint4*>(g_out + off) = o;
+            }
+        }
+        if (fixed_col) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] += f[e];
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) atomicAdd(&red[grp * 8 + e], f[e]);
+        }
+    }
+    if (fixed_col) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) atomicAdd(&red[my_group * 8 + e], acc[e]);
+    }
+    __syncthreads();
+    if (dbias != nullptr)
+        for (int i = threadIdx.x; i < N; i += blockDim.x) atomicAdd(&dbias[i], red[i]);
+}
+
+int bias_grad(const __nv_bfloat16* dy, __nv_bfloat16* g_out, float* dbias, int rows, int N, const DropoutParams& drop,
+              uint32_t site, uint32_t layer, cudaStream_t s) {
+    CB200_REQUIRE(N % 8 == 0, "bias_grad needs N %% 8 == 0");
+    if (rows == 0) return 0;
+    const int target_blocks = 4 * device_sm_count_ew();
+    int rows_per_block = (rows + target_blocks - 1) / target_blocks;
+    if (rows_per_block < 8) rows_per_block = 8;
+    const int grid = (rows + rows_per_block - 1) / rows_per_block;
+    bias_grad_kernel<<<grid, 256, N * sizeof(float), s>>>(dy, g_out, dbias, rows, N, rows_per_block, drop, site, layer);
+    CB200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Adam with TF-2 Keras semantics (transformer.py:887, 921):
+//   m <- b1 m + (1-b1) g ; v <- b2 v + (1-b2) g^2 ; p <- p - lr_t * m / (sqrt(v) + eps)
+// lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t) is computed on the host in double.
+// Also refreshes the bf16 shadow (same flat layout) used by the GEMMs.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+            __nv_bfloat16* __restrict__ shadow, size_t n4, float lr_t, float b1, float b2, float eps,
+            float grad_scale) {
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        float4 pp = reinterpret_cast<float4*>(p)[i];
+        const float4 gg = reinterpret_cast<const float4*>(g)[i];
+        float4 mm = reinterpret_cast<float4*>(m)[i];
+        float4 vv = reinterpret_cast<float4*>(v)[i];
+        float* pa = reinterpret_cast<float*>(&pp);
+        const float* ga = reinterpret_cast<const float*>(&gg);
+        float* ma = reinterpret_cast<float*>(&mm);
+        float* va = reinterpret_cast<float*>(&vv);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float gr = ga[e] * grad_scale;
+            ma[e] = b1 * ma[e] + (1.0f - b1) * gr;
+            va[e] = b2 * va[e] + (1.0f - b2) * gr * gr;
+            pa[e] = pa[e] - lr_t * ma[e] / (sqrtf(va[e]) + eps);
+        }
+        reinterpret_cast<float4*>(p)[i] = pp;
+        reinterpret_cast<float4*>(m)[i] = mm;
+        reinterpret_cast<float4*>(v)[i] = vv;
+        if (shadow != nullptr) {
+            uint2 o;
+            o.x = pack_bf16(pa[0], pa[1]); o.y = pack_bf16(pa[2], pa[3]);
+            reinterpret_cast<uint2*>(shadow)[i] = o;
+        }
+    }
+}
+
+int adam_step(float* p, const float* g, float* m, float* v, __nv_bfloat16* shadow, size_t n, float lr_t, float b1,
+              float b2, float eps, float grad_scale, cudaStream_t s) {
+    CB200_REQUIRE(n % 4 == 0, "parameter arena length must be a multiple of 4");
+    if (n == 0) return 0;
+    const size_t n4 = n / 4;
+    size_t blocks = (n4 + 255) / 256;
+    const size_t cap = 8 * static_cast<size_t>(device_sm_count_ew());
+    if (blocks > cap) blocks = cap;
+    adam_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(p, g, m, v, shadow, n4, lr_t, b1, b2, eps, grad_scale);
+    CB200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// fp32 -> bf16 cast of a flat array (initial shadow fill after loading parameters).
+__global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x)
+        dst[i] = __float2bfloat16_rn(src[i]);
+}
+
+int cast_bf16(const float* src, __nv_bfloat16* dst, size_t n, cudaStream_t s) {
+    if (n == 0) return 0;
+    size_t blocks = (n + 255) / 256;
+    if (blocks > 2048) blocks = 2048;
+    cast_bf16_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(src, dst, n);
+    CB200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// Batched transpose-cast: for each job, dst[c, r] (ld = dst_ld) = bf16(src[r, c]).
+// Produces the [out, in] ("K-major B operand") shadows of the [in, out] weights.
+__global__ void __launch_bounds__(256)
+transpose_cast_kernel(const float* __restrict__ params, __nv_bfloat16* __restrict__ dst_base,
+                      const TransposeJob* __restrict__ jobs) {
+    __shared__ float tile[32][33];
+    const TransposeJob job = jobs[blockIdx.z];
+    const int tiles_c = (job.cols + 31) / 32;
+    const int tiles_r = (job.rows + 31) / 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    for (int tile_id = blockIdx.x; tile_id < tiles_c * tiles_r; tile_id += gridDim.x) {
+        const int tr = tile_id / tiles_c, tc = tile_id % tiles_c;
+        __syncthreads();
+        for (int i = ty; i < 32; i += 8) {
+            const int r = tr * 32 + i, c = tc * 32 + tx;
+            tile[i][tx] = (r < job.rows && c < job.cols) ? params[job.src_offset + static_cast<size_t>(r) * job.cols + c] : 0.f;
+        }
+        __syncthreads();
+        for (int i = ty; i < 32; i += 8) {
+            const int c = tc * 32 + i, r = tr * 32 + tx;
+            if (c < job.cols && r < job.rows)
+                dst_base[job.dst_offset + static_cast<size_t>(c) * job.dst_ld + r] = __float2bfloat16_rn(tile[tx][i]);
+        }
+    }
+}
+
+int transpose_cast(const float* params, __nv_bfloat16* dst_base, const TransposeJob* jobs_dev, int num_jobs,
+                   cudaStream_t s) {
+    if (num_jobs == 0) return 0;
+    dim3 grid(64, 1, num_jobs);
+    transpose_cast_kernel<<<grid, 256, 0, s>>>(params, dst_base, jobs_dev);
+    CB200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int device_sm_count_ew() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+}  // namespace cb200

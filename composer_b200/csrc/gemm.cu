@@ -1,0 +1,190 @@
+// Host launchers for the sm_100a GEMM family (gemm_sm100.cuh): tensor-map
+// creation (cuTensorMapEncodeTiled through the runtime's driver entry point,
+// so libcuda is not a link-time dependency) and template dispatch.
+#include "gemm.h"
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <unordered_map>
+
+#include "gemm_sm100.cuh"
+
+namespace cb200 {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+struct TmapKey {
+    const void* base;
+    uint64_t inner, outer, stride;
+    uint32_t box_inner, box_outer;
+    bool operator==(const TmapKey& o) const {
+        return base == o.base && inner == o.inner && outer == o.outer && stride == o.stride &&
+               box_inner == o.box_inner && box_outer == o.box_outer;
+    }
+};
+struct TmapKeyHash {
+    size_t operator()(const TmapKey& k) const {
+        size_t h = reinterpret_cast<size_t>(k.base);
+        h = h * 1000003u ^ k.inner; h = h * 1000003u ^ k.outer; h = h * 1000003u ^ k.stride;
+        h = h * 1000003u ^ k.box_inner; h = h * 1000003u ^ k.box_outer;
+        return h;
+    }
+};
+
+// 2-D bf16 tensor map over a row-major matrix: `inner` contiguous elements per
+// row, `outer` rows, `stride_elems` elements between rows; SWIZZLE_128B boxes.
+int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t stride_elems,
+                   uint32_t box_inner, uint32_t box_outer) {
+    static thread_local std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+    TmapKey key{base, inner, outer, stride_elems, box_inner, box_outer};
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+        *out = it->second;
+        return 0;
+    }
+    EncodeTiledFn fn = encode_fn();
+    CB200_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
+    CB200_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base address must be 16-byte aligned");
+    CB200_REQUIRE((stride_elems * 2) % 16 == 0, "TMA row stride must be a multiple of 16 bytes (got %llu elements)",
+                  (unsigned long long)stride_elems);
+    CB200_REQUIRE(box_inner * 2 == 128 && box_outer <= 256, "bad TMA box");
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {stride_elems * 2};
+    cuuint32_t box[2] = {box_inner, box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    alignas(64) CUtensorMap m;
+    CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CB200_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) inner=%llu outer=%llu stride=%llu box=%ux%u",
+                  (int)r, (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)stride_elems,
+                  box_inner, box_outer);
+    if (cache.size() > 4096) cache.clear();
+    cache.emplace(key, m);
+    *out = m;
+    return 0;
+}
+
+int device_sm_count() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+template <int BN, bool A_MN, bool B_MN, int EPI, int STAGES>
+static int launch_variant(const GemmDesc& d, cudaStream_t stream) {
+    using L = GemmSmem<BN>;
+    constexpr bool staging = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU || EPI == EPI_BIAS_DROP_RES ||
+                              EPI == EPI_MUL_DGELU);
+    constexpr int num_out = (EPI == EPI_BIAS_GELU) ? 2 : 1;
+    constexpr int b_box_rows = (BN <= 256) ? BN : BN / 2;
+    constexpr size_t smem_bytes = size_t(STAGES) * L::STAGE_BYTES + (staging ? 2 * num_out * L::STAGING_BYTES : 0) +
+                                  256 /* barriers */ + 1024 /* alignment slack */;
+    static_assert(smem_bytes <= 232448, "shared memory budget exceeded");
+
+    CB200_REQUIRE(d.M > 0 && d.N > 0 && d.K > 0, "empty GEMM (M=%d N=%d K=%d)", d.M, d.N, d.K);
+
+    CUtensorMap tmA, tmB, tmC0, tmC1;
+    int rc;
+    if (A_MN) rc = make_tmap_bf16(&tmA, d.A, d.M, d.K, d.lda, 64, 64);       // stored [K, M]
+    else      rc = make_tmap_bf16(&tmA, d.A, d.K, d.M, d.lda, 64, GEMM_BM);  // stored [M, K]
+    if (rc) return rc;
+    if (B_MN) rc = make_tmap_bf16(&tmB, d.B, d.N, d.K, d.ldb, 64, 64);       // stored [K, N]
+    else      rc = make_tmap_bf16(&tmB, d.B, d.K, d.N, d.ldb, 64, b_box_rows);  // stored [N, K]
+    if (rc) return rc;
+    if (staging) {
+        CB200_REQUIRE(d.out0 != nullptr, "GEMM epilogue needs out0");
+        rc = make_tmap_bf16(&tmC0, d.out0, d.N, d.M, d.ld_out0, 64, GEMM_BM);
+        if (rc) return rc;
+        if (num_out == 2) {
+            CB200_REQUIRE(d.out1 != nullptr, "GELU epilogue needs out1");
+            rc = make_tmap_bf16(&tmC1, d.out1, d.N, d.M, d.ld_out1, 64, GEMM_BM);
+            if (rc) return rc;
+        } else {
+            tmC1 = tmC0;
+        }
+    } else {
+        tmC0 = tmA;
+        tmC1 = tmA;
+    }
+
+    GemmArgs a;
+    memset(&a, 0, sizeof(a));
+    a.M = d.M; a.N = d.N; a.K = d.K;
+    a.num_m_tiles = (d.M + GEMM_BM - 1) / GEMM_BM;
+    a.num_n_tiles = (d.N + BN - 1) / BN;
+    a.k_blocks_total = (d.K + GEMM_BK - 1) / GEMM_BK;
+    a.k_splits = 1;
+    const int sms = device_sm_count();
+    if (EPI == EPI_ATOMIC_F32) {
+        int tiles_mn = a.num_m_tiles * a.num_n_tiles;
+        int want = sms / tiles_mn;
+        if (want < 1) want = 1;
+        if (want > a.k_blocks_total) want = a.k_blocks_total;
+        int per = (a.k_blocks_total + want - 1) / want;
+        a.k_splits = (a.k_blocks_total + per - 1) / per;   // every split owns at least one k-block
+    }
+    if (EPI == EPI_CE) CB200_REQUIRE(a.num_n_tiles == 1, "cross-entropy epilogue needs the vocabulary (%d) <= %d", d.N, BN);
+    a.bias = d.bias;
+    a.aux = d.aux; a.ld_aux = d.ld_aux;
+    a.outf = d.outf; a.ld_outf = d.ld_outf;
+    a.valid_m = d.M;
+    a.drop = d.drop; a.drop_site = d.drop_site; a.drop_layer = d.drop_layer;
+    a.labels = d.labels; a.dlogits = d.dlogits; a.ld_dlogits = d.ld_dlogits; a.grad_scale = d.grad_scale;
+    a.loss_sum = d.loss_sum; a.correct = d.correct;
+    if (EPI == EPI_BIAS_DROP_RES || EPI == EPI_MUL_DGELU) CB200_REQUIRE(d.aux != nullptr && d.ld_aux % 8 == 0, "epilogue needs aux with ld %% 8 == 0");
+    if (EPI == EPI_ATOMIC_F32) CB200_REQUIRE(d.outf != nullptr && d.ld_outf % 4 == 0 && d.N % 4 == 0, "atomic epilogue needs outf, ld %% 4 == 0");
+    if (d.bias != nullptr) CB200_REQUIRE(d.N % 4 == 0 && (reinterpret_cast<uintptr_t>(d.bias) & 15) == 0, "bias must be 16-byte aligned, N %% 4 == 0");
+
+    auto kernel = gemm_sm100_kernel<BN, A_MN, B_MN, EPI, STAGES>;
+    static bool configured = false;
+    if (!configured) {
+        CB200_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        configured = true;
+    }
+    const int total_tiles = a.num_m_tiles * a.num_n_tiles * a.k_splits;
+    const int grid = total_tiles < sms ? total_tiles : sms;
+    kernel<<<grid, GEMM_THREADS, smem_bytes, stream>>>(tmA, tmB, tmC0, tmC1, a);
+    CB200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int gemm_launch(const GemmDesc& d, cudaStream_t stream) {
+    switch (d.kind) {
+        case GEMM_BIAS:       return launch_variant<256, false, false, EPI_BIAS_BF16, 4>(d, stream);
+        case GEMM_BIAS_GELU:  return launch_variant<256, false, false, EPI_BIAS_GELU, 3>(d, stream);
+        case GEMM_BIAS_DROP_RES: return launch_variant<256, false, false, EPI_BIAS_DROP_RES, 4>(d, stream);
+        case GEMM_MUL_DGELU:  return launch_variant<256, false, false, EPI_MUL_DGELU, 4>(d, stream);
+        case GEMM_WGRAD:      return launch_variant<256, true, true, EPI_ATOMIC_F32, 4>(d, stream);
+        case GEMM_CE:
+            if (d.N <= 400) return launch_variant<400, false, false, EPI_CE, 3>(d, stream);
+            return launch_variant<512, false, false, EPI_CE, 2>(d, stream);
+        case GEMM_BIAS_BMN:   return launch_variant<256, false, true, EPI_BIAS_BF16, 4>(d, stream);
+        default: break;
+    }
+    set_error("unknown GEMM kind %d", (int)d.kind);
+    return -1;
+}
+
+}  // namespace cb200

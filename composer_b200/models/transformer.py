@@ -1,0 +1,547 @@
+'''
+The Transformer decoder of Composer, driven on a B200 through the C ABI of
+``libcomposer_b200`` (``include/composer_b200.h``).
+
+This class mirrors the reference's ``composer.models.Transformer``
+(composer/models/transformer.py:599-960): same constructor arguments, the same
+``__call__`` / ``train`` / ``compile`` / ``build`` / ``load_from_checkpoint``
+surface used by the CLI (composer/cli.py:579-589, 635-676), the same Keras
+variable names for its weights.  PyTorch only owns device memory, streams and
+the NCCL process group; every arithmetic operation is a hand-written sm_100a
+kernel.  There is no CPU path: constructing the model without a CUDA device or
+without the built library raises.
+'''
+
+import ctypes
+import json
+import logging
+import math
+import os
+import time
+from collections import OrderedDict
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from composer_b200 import ModelSaveFrequencyMode, _lib
+from composer_b200.models.base import BaseModel
+
+CHECKPOINT_INDEX = 'checkpoint.json'
+
+
+def _ptr(tensor):
+    return ctypes.c_void_p(tensor.data_ptr()) if tensor is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Transformer(BaseModel):
+    '''
+    A Transformer-decoder model that generates music as a sequence of MIDI-like
+    events (see :mod:`composer_b200.dataset.sequence`).
+
+    Constructor arguments are those of the reference (transformer.py:610-614),
+    in the same order, so that ``cli.create_model`` (cli.py:123-132) maps
+    ``transformer.model.*`` positionally.
+    '''
+
+    def __init__(self, vocab_size, embedding_size, window_size, decoder_layers_count,
+                 attention_head_count, use_relative_attention=False, initializer_mean=0,
+                 initializer_stddev=0.02, attention_dropout_rate=0.1, residual_dropout_rate=0.1,
+                 layer_normalization_epsilon=1e-5, scale=True, use_layer_normalization=True,
+                 output_hidden_states=False, output_attention_weights=False, device=None, seed=0,
+                 process_group=None):
+        if use_relative_attention:
+            # The reference's relative attention cannot run (``self.depth`` is undefined, transformer.py:281-286).
+            raise NotImplementedError('use_relative_attention is broken in the reference and not provided here.')
+        if output_hidden_states or output_attention_weights:
+            raise NotImplementedError('output_hidden_states / output_attention_weights are not on the '
+                                      'train/generate path and are not provided by the B200 build.')
+        if not torch.cuda.is_available():
+            raise RuntimeError('composer_b200.models.Transformer needs a CUDA device (B200); there is no CPU path.')
+
+        _lib.load()
+        self.vocab_size = int(vocab_size)
+        self.embedding_size = int(embedding_size)
+        self.window_size = int(window_size)
+        self.decoder_layers_count = int(decoder_layers_count)
+        self.attention_head_count = int(attention_head_count)
+        self.attention_dropout_rate = float(attention_dropout_rate)
+        self.residual_dropout_rate = float(residual_dropout_rate)
+        self.layer_normalization_epsilon = float(layer_normalization_epsilon)
+        self.scale = bool(scale)
+        self.use_layer_normalization = bool(use_layer_normalization)
+        self.initializer_mean = float(initializer_mean)
+        self.initializer_stddev = float(initializer_stddev)
+        self.seed = int(seed)
+        self.process_group = process_group
+        self.device = torch.device(device if device is not None else 'cuda:%d' % torch.cuda.current_device())
+        self.learning_rate = 1e-3
+
+        self._config = _lib.Config(self.vocab_size, self.embedding_size, self.window_size,
+                                   self.decoder_layers_count, self.attention_head_count,
+                                   self.attention_dropout_rate, self.residual_dropout_rate,
+                                   self.layer_normalization_epsilon, int(self.scale),
+                                   int(self.use_layer_normalization))
+        handle = ctypes.c_void_p()
+        _lib.call('cb200_engine_create', ctypes.byref(self._config), ctypes.byref(handle))
+        self._engine = handle
+        self._layout = self._query_layout()
+
+        with torch.cuda.device(self.device):
+            count = _lib.call('cb200_param_elems', ctypes.byref(self._config))
+            self._params = torch.zeros(count, dtype=torch.float32, device=self.device)
+            self._shadow = torch.zeros(_lib.call('cb200_shadow_elems', self._engine), dtype=torch.bfloat16,
+                                       device=self.device)
+        self._grads = self._adam_m = self._adam_v = None
+        self._workspace = None
+        self._bound = None          # (max_B, max_T, training)
+        self._adam_t = 0
+        self._global_step = 1       # tf.Variable(1), transformer.py:890
+        self._epoch = 1
+        self._loss_dev = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self._correct_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._decode_state = None
+        self.set_weights(self.initial_weights(self.seed))
+
+    def __del__(self):
+        engine = getattr(self, '_engine', None)
+        if engine:
+            try:
+                _lib.call('cb200_engine_destroy', engine)
+            except Exception:   # interpreter shutdown
+                pass
+            self._engine = None
+
+    # ------------------------------------------------------------------
+    # Variables
+    # ------------------------------------------------------------------
+    def _query_layout(self):
+        layout = OrderedDict()
+        count = _lib.call('cb200_param_tensor_count', ctypes.byref(self._config))
+        name = ctypes.create_string_buffer(128)
+        offset, rows, cols = ctypes.c_int64(), ctypes.c_int32(), ctypes.c_int32()
+        for index in range(count):
+            _lib.call('cb200_param_tensor_info', ctypes.byref(self._config), index, name, 128, ctypes.byref(offset),
+                      ctypes.byref(rows), ctypes.byref(cols))
+            layout[name.value.decode()] = (offset.value, rows.value, cols.value)
+        return layout
+
+    @property
+    def variable_names(self):
+        return list(self._layout)
+
+    def _shape_of(self, name):
+        _, rows, cols = self._layout[name]
+        if name.endswith('/gamma') or name.endswith('/beta'):
+            return (cols,)                       # Keras LayerNormalization variables are [E]
+        return (rows, cols)                      # biases are [1, out] (transformer.py:189-190)
+
+    def initial_weights(self, seed=0):
+        '''
+        Fresh variables with the reference's initializers (transformer.py:115, 188-190, 670-673):
+        truncated normal(mean, stddev) for weights and embeddings, zeros for
+        biases / beta, ones for gamma.  Returns ``{keras name: float32 array}``.
+        '''
+
+        rng = np.random.default_rng(seed)
+
+        def truncated_normal(shape):
+            out = rng.standard_normal(shape)
+            bad = np.abs(out) > 2.0
+            while bad.any():
+                out[bad] = rng.standard_normal(int(bad.sum()))
+                bad = np.abs(out) > 2.0
+            return (self.initializer_mean + self.initializer_stddev * out).astype(np.float32)
+
+        weights = OrderedDict()
+        for name in self._layout:
+            shape = self._shape_of(name)
+            if name.endswith('/gamma'):
+                weights[name] = np.ones(shape, dtype=np.float32)
+            elif name.endswith('/beta') or name.endswith('/bias'):
+                weights[name] = np.zeros(shape, dtype=np.float32)
+            else:
+                weights[name] = truncated_normal(shape)
+        return weights
+
+    def set_weights(self, weights):
+        '''Loads ``{keras name: array}`` into the fp32 arena and refreshes the bf16 shadows.'''
+
+        host = np.zeros(self._params.numel(), dtype=np.float32)
+        for name, (offset, rows, cols) in self._layout.items():
+            value = np.asarray(weights[name], dtype=np.float32)
+            if value.size != rows * cols:
+                raise ValueError('variable %s has %d elements, expected %d' % (name, value.size, rows * cols))
+            host[offset:offset + rows * cols] = value.reshape(-1)
+        self._params.copy_(torch.from_numpy(host))
+        self._refresh_shadows()
+
+    def get_weights(self):
+        '''Returns ``{keras name: float32 array}`` (a host copy of the fp32 master weights).'''
+
+        host = self._params.detach().cpu().numpy()
+        return OrderedDict((name, host[offset:offset + rows * cols].reshape(self._shape_of(name)).copy())
+                           for name, (offset, rows, cols) in self._layout.items())
+
+    def get_gradients(self):
+        host = self._grads.detach().cpu().numpy()
+        return OrderedDict((name, host[offset:offset + rows * cols].reshape(self._shape_of(name)).copy())
+                           for name, (offset, rows, cols) in self._layout.items())
+
+    def count_params(self):
+        return sum(rows * cols for _, rows, cols in self._layout.values())
+
+    @property
+    def gradient_arena(self):
+        '''The flat fp32 gradient tensor (what data-parallel training all-reduces).'''
+
+        return self._grads
+
+    def _refresh_shadows(self):
+        # The transpose job table lives in the workspace, so something must be bound; binding refreshes.
+        if self._bound is None:
+            self._bind(1, min(self.window_size, 64), training=False)
+        else:
+            with torch.cuda.device(self.device):
+                _lib.call('cb200_refresh_shadows', self._engine, _stream())
+
+    # ------------------------------------------------------------------
+    # Memory binding
+    # ------------------------------------------------------------------
+    def _bind(self, batch, sequence, training):
+        if self._bound is not None:
+            max_b, max_t, bound_training = self._bound
+            if batch * sequence <= max_b * max_t and (bound_training or not training):
+                return
+            batch_tokens = max(batch * sequence, max_b * max_t)
+            training = training or bound_training
+            sequence = max(sequence, max_t)
+            batch = (batch_tokens + sequence - 1) // sequence
+
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize(self.device)
+            if training and self._grads is None:
+                self._grads = torch.zeros_like(self._params)
+                self._adam_m = torch.zeros_like(self._params)
+                self._adam_v = torch.zeros_like(self._params)
+            need = _lib.call('cb200_workspace_bytes', self._engine, batch, sequence, int(training))
+            self._workspace = None
+            self._workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
+            _lib.call('cb200_engine_bind', self._engine, _ptr(self._params), _ptr(self._grads), _ptr(self._adam_m),
+                      _ptr(self._adam_v), _ptr(self._shadow), _ptr(self._workspace), need, batch, sequence,
+                      int(training))
+            _lib.call('cb200_refresh_shadows', self._engine, _stream())
+        self._bound = (batch, sequence, training)
+
+    def build(self, input_shape=None):
+        '''Keras-compatibility no-op (cli.py:640): variables exist from construction.'''
+
+        return self
+
+    def compile(self, learning_rate):
+        '''transformer.py:835-844 — remembers the optimizer's learning rate.'''
+
+        self.learning_rate = float(learning_rate)
+        return self
+
+    def reset_states(self):
+        self._decode_state = None
+
+    # ------------------------------------------------------------------
+    # Forward / training step
+    # ------------------------------------------------------------------
+    def _as_ids(self, array):
+        tensor = array if isinstance(array, torch.Tensor) else torch.as_tensor(np.asarray(array))
+        if tensor.dim() == 1:
+            tensor = tensor[None]
+        if tensor.dim() != 2:
+            raise ValueError('expected integer ids of shape [batch, sequence], got %r' % (tuple(tensor.shape),))
+        return tensor.to(device=self.device, dtype=torch.int32, non_blocking=True).contiguous()
+
+    def __call__(self, inputs, past=None, training=False, use_cache=True):
+        '''
+        ``Transformer.call`` (transformer.py:696-833) for integer ``inputs``
+        [batch, sequence].  Returns ``(logits, presents)``: logits is a float32
+        CUDA tensor [batch, sequence, vocab]; ``presents`` is ``None`` (the KV
+        cache lives inside :meth:`generate`, which is what the CLI loop uses).
+        '''
+
+        if past is not None:
+            raise NotImplementedError('use generate() for cached decoding')
+        ids = self._as_ids(inputs)
+        batch, sequence = ids.shape
+        self._bind(batch, sequence, training=False)
+        logits = torch.empty((batch, sequence, self.vocab_size), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.call('cb200_forward', self._engine, _ptr(ids), None, batch, sequence, 0, self.seed, 0, 0.0, None,
+                      None, _ptr(logits), _stream())
+        return logits, None
+
+    def forward_loss(self, x, y, training=False, step=0, return_logits=False):
+        '''Forward + summed loss + correct count on the device; returns (loss_sum, correct[, logits]) tensors.'''
+
+        ids, labels = self._as_ids(x), self._as_ids(y)
+        batch, sequence = ids.shape
+        self._bind(batch, sequence, training=training)
+        logits = None
+        if return_logits:
+            logits = torch.empty((batch, sequence, self.vocab_size), dtype=torch.float32, device=self.device)
+        self._loss_dev.zero_()
+        self._correct_dev.zero_()
+        with torch.cuda.device(self.device):
+            _lib.call('cb200_forward', self._engine, _ptr(ids), _ptr(labels), batch, sequence, int(training),
+                      self.seed, step, 1.0 / (batch * sequence), _ptr(self._loss_dev), _ptr(self._correct_dev),
+                      _ptr(logits), _stream())
+        self._last_ids = (ids, labels)   # keep the device buffers alive until backward has run
+        if return_logits:
+            return self._loss_dev, self._correct_dev, logits
+        return self._loss_dev, self._correct_dev
+
+    def backward(self, overlap_allreduce=True):
+        '''tape.gradient (transformer.py:920).  With a process group, all-reduces the flat gradient arena.'''
+
+        world = 1
+        group = self.process_group
+        if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            world = torch.distributed.get_world_size(group)
+        with torch.cuda.device(self.device):
+            _lib.call('cb200_zero_grads', self._engine, _stream())
+            _lib.call('cb200_backward', self._engine, -1, _stream())
+        if world > 1:
+            # Sum over ranks; the 1/world mean is folded into the Adam kernel (grad_scale).
+            torch.distributed.all_reduce(self._grads, group=group)
+        return world
+
+    def apply_gradients(self, learning_rate=None, world=1):
+        '''optimizers.Adam.apply_gradients with TF-2 Keras defaults (transformer.py:887, 921).'''
+
+        self._adam_t += 1
+        lr = self.learning_rate if learning_rate is None else learning_rate
+        with torch.cuda.device(self.device):
+            _lib.call('cb200_adam_step', self._engine, lr, 0.9, 0.999, 1e-7, self._adam_t, 1.0 / world, _stream())
+
+    def train_step(self, x, y, learning_rate=None, training=True):
+        '''
+        One iteration of the reference's hot loop (transformer.py:914-926):
+        forward, loss, gradients, Adam.  Returns device tensors
+        ``(loss_sum, correct_count)`` for this rank's batch; nothing is synchronised.
+        '''
+
+        loss, correct = self.forward_loss(x, y, training=training, step=self._adam_t)
+        world = self.backward()
+        self.apply_gradients(learning_rate, world)
+        return loss, correct
+
+    # ------------------------------------------------------------------
+    # Generation (cli.py:663-676 with the model's past= semantics)
+    # ------------------------------------------------------------------
+    def generate(self, prompt_ids, length, temperature=1.0, seed=None, sequence_index_base=0,
+                 return_uniforms=False, return_last_logits=False):
+        '''
+        Autoregressively samples ``length`` new event ids after ``prompt_ids``
+        ([batch, prompt_length], every row the same length) with a KV cache.
+        ``temperature <= 0`` selects argmax.  Raises when
+        ``prompt_length + length - 1 > window_size`` (the positional table has
+        ``window_size`` rows, transformer.py:675-679; TF-CPU raises as well).
+        Returns an int32 CUDA tensor [batch, length].
+        '''
+
+        prompt = self._as_ids(prompt_ids)
+        batch, prompt_length = prompt.shape
+        steps = prompt_length - 1 + length
+        if steps > self.window_size:
+            raise ValueError('prompt_length + length - 1 = %d exceeds window_size = %d: position embeddings exist '
+                             'only for window_size positions' % (steps, self.window_size))
+        if self._bound is None:
+            self._bind(1, min(self.window_size, 64), training=False)
+        seed = self.seed if seed is None else int(seed)
+        with torch.cuda.device(self.device):
+            t_max = (steps + 63) // 64 * 64
+            key = (batch, t_max)
+            if self._decode_state is None or self._decode_state[0] != key:
+                cache = torch.empty(_lib.call('cb200_kv_cache_elems', self._engine, batch, t_max),
+                                    dtype=torch.bfloat16, device=self.device)
+                need = _lib.call('cb200_decode_workspace_bytes', self._engine, batch)
+                workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
+                self._decode_state = (key, cache, workspace)
+            _, cache, workspace = self._decode_state
+            out = torch.empty((batch, length), dtype=torch.int32, device=self.device)
+            uniforms = torch.empty((batch, steps), dtype=torch.float32, device=self.device) if return_uniforms else None
+            last = torch.empty((batch, self.vocab_size), dtype=torch.float32, device=self.device) \
+                if return_last_logits else None
+            _lib.call('cb200_generate', self._engine, _ptr(cache), t_max, _ptr(workspace), workspace.numel(),
+                      _ptr(prompt), batch, prompt_length, length, float(temperature), seed, int(sequence_index_base),
+                      _ptr(out), _ptr(uniforms), _ptr(last), _stream())
+        extras = [t for t in (uniforms, last) if t is not None]
+        return (out, *extras) if extras else out
+
+    # ------------------------------------------------------------------
+    # Checkpoints (own format; TF object-graph checkpoints need TensorFlow)
+    # ------------------------------------------------------------------
+    def save_checkpoint(self, logdir, max_checkpoints=1):
+        '''
+        Writes ``ckpt-<step>.npz`` (variables under their Keras names, Adam
+        slots, step / epoch counters) and rotates old files like
+        ``tf.train.CheckpointManager(max_to_keep)`` (transformer.py:891).
+        '''
+
+        logdir = Path(logdir)
+        logdir.mkdir(parents=True, exist_ok=True)
+        arrays = {'variables/' + k: v for k, v in self.get_weights().items()}
+        if self._adam_m is not None:
+            arrays['optimizer/m'] = self._adam_m.detach().cpu().numpy()
+            arrays['optimizer/v'] = self._adam_v.detach().cpu().numpy()
+        arrays['optimizer/iterations'] = np.asarray(self._adam_t, dtype=np.int64)
+        arrays['step'] = np.asarray(self._global_step, dtype=np.int64)
+        arrays['epoch'] = np.asarray(self._epoch, dtype=np.int64)
+        index_path = logdir / CHECKPOINT_INDEX
+        index = {'all': [], 'latest': None}
+        if index_path.exists():
+            index = json.loads(index_path.read_text())
+        number = (max([int(Path(p).stem.split('-')[-1]) for p in index['all']] + [0])) + 1
+        path = logdir / ('ckpt-%d.npz' % number)
+        np.savez(path, **arrays)
+        index['all'].append(path.name)
+        index['latest'] = path.name
+        while max_checkpoints and len(index['all']) > max_checkpoints:
+            stale = logdir / index['all'].pop(0)
+            if stale.exists():
+                stale.unlink()
+        index_path.write_text(json.dumps(index))
+        return str(path)
+
+    @staticmethod
+    def latest_checkpoint(restoredir):
+        index_path = Path(restoredir) / CHECKPOINT_INDEX
+        if not index_path.exists():
+            return None
+        latest = json.loads(index_path.read_text()).get('latest')
+        return str(Path(restoredir) / latest) if latest else None
+
+    def _restore(self, path, with_optimizer):
+        data = np.load(path)
+        self.set_weights({name: data['variables/' + name] for name in self._layout})
+        self._global_step = int(data['step'])
+        self._epoch = int(data['epoch'])
+        if with_optimizer and 'optimizer/m' in data.files:
+            self._bind(1, min(self.window_size, 64), training=True)
+            self._adam_m.copy_(torch.from_numpy(data['optimizer/m']))
+            self._adam_v.copy_(torch.from_numpy(data['optimizer/v']))
+            self._adam_t = int(data['optimizer/iterations'])
+
+    def load_from_checkpoint(self, restoredir):
+        '''BaseModel.load_from_checkpoint (models/__init__.py:66-90): weights only, errors exit(1).'''
+
+        try:
+            path = self.latest_checkpoint(restoredir)
+            if path is None:
+                raise FileNotFoundError('no checkpoint in %s' % restoredir)
+            self._restore(path, with_optimizer=False)
+            logging.info('{} model restored from \'{}\' (epoch {}, global step {}).'.format(
+                self.__class__.__name__, path, self._epoch, self._global_step))
+        except Exception:
+            logging.exception('Failed to restore {} model from \'{}\'.'.format(self.__class__.__name__, restoredir))
+            raise SystemExit(1)
+
+    # ------------------------------------------------------------------
+    # Training loop (transformer.py:846-960)
+    # ------------------------------------------------------------------
+    def train(self, dataset, input_shape, logdir, restoredir=None, epochs=None,
+              learning_rate=1e-3, save_frequency_mode=ModelSaveFrequencyMode.EPOCH,
+              save_frequency=1, max_checkpoints=1, show_progress_bar=True, max_steps=None, log_every=10):
+        '''
+        Fits the model to ``dataset`` (any re-iterable of ``(x, y)`` integer
+        batches [batch, window]) with the reference's loop structure: Adam,
+        mean sparse-categorical cross-entropy, per-step ``loss`` / ``accuracy``
+        scalars, ``epoch_loss`` / ``epoch_accuracy`` per epoch, checkpoints every
+        ``save_frequency`` steps or epochs.  Like the reference, ``epochs=N``
+        stops when the 1-based epoch counter reaches N (transformer.py:890, 907).
+
+        Differences, all host-side: metrics are read back every ``log_every``
+        steps (the reference formats them every step, a device sync), and
+        ``max_steps`` (extension) bounds the run for benchmarks and tests.
+        '''
+
+        from tqdm import tqdm
+
+        logdir = Path(restoredir) if restoredir is not None else Path(logdir)
+        self.compile(learning_rate)
+        if restoredir is not None:
+            try:
+                path = self.latest_checkpoint(logdir)
+                self._restore(path, with_optimizer=True)
+                logging.info('Model restored from \'{}\'.'.format(path))
+            except Exception:
+                logging.error('Failed to restore model from \'{}\'.'.format(restoredir))
+                raise SystemExit(1)
+
+        rank = torch.distributed.get_rank() if torch.distributed.is_initialized() else 0
+        writer = None
+        if rank == 0:
+            try:
+                from torch.utils.tensorboard import SummaryWriter
+                writer = SummaryWriter(str(logdir / 'train'))
+            except Exception:   # tensorboard missing: scalars go to the log only
+                logging.warning('tensorboard is not available; scalars are only logged.')
+
+        save_frequency_mode = ModelSaveFrequencyMode(save_frequency_mode)
+        steps_per_epoch = None
+        steps_done = 0
+        history = []
+        while epochs is None or self._epoch < epochs:
+            current_epoch = self._epoch
+            logging.info('Epoch {}'.format(current_epoch if epochs is None else '{}/{}'.format(current_epoch, epochs)))
+            epoch_loss = torch.zeros(1, dtype=torch.float64, device=self.device)
+            epoch_correct = torch.zeros(1, dtype=torch.float64, device=self.device)
+            epoch_tokens = 0
+            epoch_batches = 0
+            with tqdm(total=steps_per_epoch, disable=not (show_progress_bar and rank == 0)) as progress_bar:
+                for x, y in dataset:
+                    loss_sum, correct = self.train_step(x, y, learning_rate)
+                    tokens = int(np.prod(np.shape(x)))
+                    epoch_loss += loss_sum.double() / tokens
+                    epoch_correct += correct.double()
+                    epoch_tokens += tokens
+                    epoch_batches += 1
+                    global_step = self._global_step
+                    if global_step % log_every == 0 or log_every == 1:
+                        loss_value = float(loss_sum) / tokens          # host sync, every log_every steps
+                        accuracy = float(correct) / tokens
+                        history.append((global_step, loss_value, accuracy))
+                        if writer is not None:
+                            writer.add_scalar('loss', loss_value, global_step)
+                            writer.add_scalar('accuracy', accuracy, global_step)
+                        progress_bar.set_description('- loss: {:.4f} - accuracy: {:.4f}'.format(loss_value, accuracy))
+                    if save_frequency_mode == ModelSaveFrequencyMode.GLOBAL_STEP and \
+                            global_step % save_frequency == 0 and rank == 0:
+                        save_path = self.save_checkpoint(logdir, max_checkpoints)
+                        progress_bar.write('Saved checkpoint for step {} at {}.'.format(global_step, save_path))
+                    self._global_step += 1
+                    steps_done += 1
+                    progress_bar.update(1)
+                    if max_steps is not None and steps_done >= max_steps:
+                        break
+
+                if epoch_batches and writer is not None:
+                    writer.add_scalar('epoch_loss', float(epoch_loss) / epoch_batches, current_epoch)
+                    writer.add_scalar('epoch_accuracy', float(epoch_correct) / max(epoch_tokens, 1), current_epoch)
+                if save_frequency_mode == ModelSaveFrequencyMode.EPOCH and current_epoch % save_frequency == 0 \
+                        and rank == 0:
+                    save_path = self.save_checkpoint(logdir, max_checkpoints)
+                    progress_bar.write('Saved checkpoint for epoch {} at {}.'.format(current_epoch, save_path))
+                if steps_per_epoch is None:
+                    steps_per_epoch = progress_bar.n
+                self._epoch += 1
+            if max_steps is not None and steps_done >= max_steps:
+                break
+            if epoch_batches == 0:
+                logging.warning('The dataset yielded no batches; stopping.')
+                break
+
+        if writer is not None:
+            writer.close()
+        return history
