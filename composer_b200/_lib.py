@@ -37,6 +37,7 @@ class NativeError(RuntimeError):
 _SIGNATURES = {
     'cb200_last_error': (ctypes.c_char_p, []),
     'cb200_abi_version': (c_int, []),
+    'cb200_launch_count': (ctypes.c_longlong, []),
     'cb200_param_elems': (c_i64, [ctypes.POINTER(Config)]),
     'cb200_param_tensor_count': (c_int, [ctypes.POINTER(Config)]),
     'cb200_param_tensor_info': (c_int, [ctypes.POINTER(Config), c_int, ctypes.c_char_p, c_int,

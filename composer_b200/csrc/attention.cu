@@ -581,6 +581,7 @@ int attention_fwd(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse, int 
         default: set_error("attention head size %d is not supported (16, 32 or 64)", D); return -1;
     }
     CB200_CUDA_OK(cudaGetLastError());
+    note_launch(1);
     return 0;
 }
 
@@ -598,6 +599,7 @@ static int launch_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* dout, const
     dim3 grid((T + BC - 1) / BC, H, B);
     kernel<<<grid, ATT_THREADS, smem, s>>>(qkv, dout, lse, delta, dq_acc, dqkv, T, H, scale, scale * kLog2e, drop, layer);
     CB200_CUDA_OK(cudaGetLastError());
+    note_launch(1);
     return 0;
 }
 
@@ -625,11 +627,13 @@ int attention_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* out, const __nv
     }
     if (rc) return rc;
     CB200_CUDA_OK(cudaGetLastError());
+    note_launch(1);
     size_t n4 = static_cast<size_t>(rows) * (E / 4);
     size_t blocks = (n4 + 255) / 256;
     if (blocks > 4096) blocks = 4096;
     attn_dq_store_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(dq_acc, dqkv, rows, E);
     CB200_CUDA_OK(cudaGetLastError());
+    note_launch(1);
     return 0;
 }
 
@@ -651,6 +655,7 @@ int attention_mask_export(uint8_t* mask, int B, int T, int H, const DropoutParam
     dim3 grid(T, B * H);
     attn_mask_export_kernel<<<grid, 128, 0, s>>>(mask, T, H, drop, layer);
     CB200_CUDA_OK(cudaGetLastError());
+    note_launch(1);
     return 0;
 }
 

@@ -17,6 +17,8 @@ namespace cb200 {
 // Host-side error plumbing (thread-local message returned by cb200_last_error)
 // ---------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
+// Counts kernel launches issued by this library (reported by bench.py as gpu_launches).
+void note_launch(long long n = 1);
 
 #define CB200_CUDA_OK(expr)                                                        \
     do {                                                                           \

@@ -143,6 +143,7 @@ int decode_attention(const __nv_bfloat16* qkv, __nv_bfloat16* kcache, __nv_bfloa
         default: set_error("attention head size %d is not supported (16, 32 or 64)", D); return -1;
     }
     CB200_CUDA_OK(cudaGetLastError());
+    note_launch(1);
     return 0;
 }
 
@@ -172,6 +173,7 @@ int decode_embed(const int32_t* cur, const float* wte, const float* wpe, __nv_bf
     if (B == 0) return 0;
     decode_embed_kernel<<<(B + 7) / 8, 256, 0, s>>>(cur, wte, wpe, out, pos_ptr, B, E, vocab);
     CB200_CUDA_OK(cudaGetLastError());
+    note_launch(1);
     return 0;
 }
 
@@ -280,6 +282,7 @@ int sample_tokens(const float* logits, int ld, int V, float temperature, uint64_
                                               static_cast<uint32_t>(seed >> 32), seq_base, out_ids, out_ld, cur, forced,
                                               forced_ld, pos_ptr, step_ptr, u_out, B);
     CB200_CUDA_OK(cudaGetLastError());
+    note_launch(1);
     return 0;
 }
 

@@ -50,6 +50,7 @@ int embed_fwd(const int32_t* ids, const float* wte, const float* wpe, __nv_bfloa
     if (rows == 0) return 0;
     embed_fwd_kernel<<<(rows + 7) / 8, 256, 0, s>>>(ids, wte, wpe, out, rows, T, E, pos0, vocab, drop);
     CB200_CUDA_OK(cudaGetLastError());
+    note_launch(1);
     return 0;
 }
 
@@ -94,6 +95,7 @@ int embed_bwd(const int32_t* ids, const __nv_bfloat16* dh, float* dwte, float* d
     const int threads = (E / 4) < 256 ? ((E / 4 + 31) / 32) * 32 : 256;
     embed_bwd_kernel<<<T, threads, 0, s>>>(ids, dh, dwte, dwpe, B, T, E, pos0, vocab, drop);
     CB200_CUDA_OK(cudaGetLastError());
+    note_launch(1);
     return 0;
 }
 
@@ -165,6 +167,7 @@ int layernorm_fwd(const __nv_bfloat16* x, const float* gamma, const float* beta,
         default: set_error("unsupported embedding size %d for LayerNorm", E); return -1;
     }
     CB200_CUDA_OK(cudaGetLastError());
+    note_launch(1);
     return 0;
 }
 
@@ -277,6 +280,7 @@ int layernorm_bwd(const __nv_bfloat16* dy_a, const __nv_bfloat16* dy_b, const __
         default: set_error("unsupported embedding size %d for LayerNorm backward", E); return -1;
     }
     CB200_CUDA_OK(cudaGetLastError());
+    note_launch(1);
     return 0;
 }
 
@@ -345,6 +349,7 @@ int bias_grad(const __nv_bfloat16* dy, __nv_bfloat16* g_out, float* dbias, int r
     const int grid = (rows + rows_per_block - 1) / rows_per_block;
     bias_grad_kernel<<<grid, 256, N * sizeof(float), s>>>(dy, g_out, dbias, rows, N, rows_per_block, drop, site, layer);
     CB200_CUDA_OK(cudaGetLastError());
+    note_launch(1);
     return 0;
 }
 
@@ -396,6 +401,7 @@ int adam_step(float* p, const float* g, float* m, float* v, __nv_bfloat16* shado
     if (blocks > cap) blocks = cap;
     adam_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(p, g, m, v, shadow, n4, lr_t, b1, b2, eps, grad_scale);
     CB200_CUDA_OK(cudaGetLastError());
+    note_launch(1);
     return 0;
 }
 
@@ -412,6 +418,7 @@ int cast_bf16(const float* src, __nv_bfloat16* dst, size_t n, cudaStream_t s) {
     if (blocks > 2048) blocks = 2048;
     cast_bf16_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(src, dst, n);
     CB200_CUDA_OK(cudaGetLastError());
+    note_launch(1);
     return 0;
 }
 
@@ -447,6 +454,7 @@ int transpose_cast(const float* params, __nv_bfloat16* dst_base, const Transpose
     dim3 grid(64, 1, num_jobs);
     transpose_cast_kernel<<<grid, 256, 0, s>>>(params, dst_base, jobs_dev);
     CB200_CUDA_OK(cudaGetLastError());
+    note_launch(1);
     return 0;
 }
 

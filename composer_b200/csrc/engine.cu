@@ -2,6 +2,7 @@
 // kernels into Transformer.call / loss / tape.gradient / Adam / cached decoding.
 // Everything is enqueued on the caller's stream; see include/composer_b200.h
 // for the contract and the reference lines each entry point replaces.
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -18,6 +19,9 @@
 namespace cb200 {
 
 static thread_local char g_error[1024] = "";
+
+static std::atomic<long long> g_launches{0};
+void note_launch(long long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -124,6 +128,7 @@ struct Engine {
     int B = 0, T = 0;
     DropoutParams drop_res{}, drop_attn{};
     bool have_forward = false;
+    cudaStream_t decode_stream = nullptr;
 };
 
 static DropoutParams make_dropout(float rate, uint64_t seed, uint32_t step, bool enabled) {
@@ -340,6 +345,7 @@ static int add3(const bf16* a, const bf16* b, const bf16* c, bf16* out, size_t n
     if (blocks > 4096) blocks = 4096;
     add3_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(a, b, c, out, n8);
     CB200_CUDA_OK(cudaGetLastError());
+    note_launch(1);
     return 0;
 }
 
@@ -553,15 +559,10 @@ static int decode_step(Engine& e, DecodeBuffers& d, bf16* cache, int t_max, int 
                          d.forced, steps, d.state, d.state + 2, d.uniforms, B, s);
 }
 
-static int generate(Engine& e, bf16* cache, int t_max, uint8_t* ws, int64_t ws_bytes, const int32_t* prompt, int B,
-                    int P, int n_new, float temperature, uint64_t seed, int64_t seq_base, int32_t* out_ids,
-                    float* uniforms_out, float* step_logits, cudaStream_t s) {
-    CB200_REQUIRE(e.params != nullptr, "engine is not bound");
-    CB200_REQUIRE(B >= 1 && P >= 1 && n_new >= 1, "generate needs B, prompt_len, n_new >= 1");
+static int generate_on(Engine& e, bf16* cache, int t_max, uint8_t* ws, int64_t ws_bytes, const int32_t* prompt, int B,
+                       int P, int n_new, float temperature, uint64_t seed, int64_t seq_base, int32_t* out_ids,
+                       float* uniforms_out, float* step_logits, cudaStream_t s) {
     const int steps = P - 1 + n_new;
-    // positions 0 .. steps-1 are embedded; wpe has window_size rows (transformer.py:675-679, 770)
-    CB200_REQUIRE(steps <= e.W, "prompt_len + length - 1 = %d positions exceed window_size %d", steps, e.W);
-    CB200_REQUIRE(steps <= t_max, "KV cache too small: %d positions, t_max %d", steps, t_max);
     DecodeBuffers d;
     const int64_t need = carve_decode(e, nullptr, B, steps, d);
     CB200_REQUIRE(ws_bytes >= need, "decode workspace too small: %lld < %lld", (long long)ws_bytes, (long long)need);
@@ -569,6 +570,7 @@ static int generate(Engine& e, bf16* cache, int t_max, uint8_t* ws, int64_t ws_b
     const int n_init = B * steps > 8 ? B * steps : 8;
     decode_init_kernel<<<(n_init + 255) / 256, 256, 0, s>>>(prompt, B, P, steps, d.cur, d.forced, d.state);
     CB200_CUDA_OK(cudaGetLastError());
+    note_launch(1);
     int rc;
     // step 0 runs eagerly (also configures kernel attributes outside of capture); the rest replays a graph
     if ((rc = decode_step(e, d, cache, t_max, B, steps, temperature, seed, seq_base, s))) return rc;
@@ -576,7 +578,10 @@ static int generate(Engine& e, bf16* cache, int t_max, uint8_t* ws, int64_t ws_b
         cudaGraph_t graph = nullptr;
         cudaGraphExec_t exec = nullptr;
         CB200_CUDA_OK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        const long long before = g_launches.load();
         rc = decode_step(e, d, cache, t_max, B, steps, temperature, seed, seq_base, s);
+        const long long per_step = g_launches.load() - before;
+        note_launch(per_step * (steps - 2));   // the captured step itself is replayed steps-1 times
         cudaError_t ce = cudaStreamEndCapture(s, &graph);
         if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
         CB200_CUDA_OK(ce);
@@ -589,9 +594,10 @@ static int generate(Engine& e, bf16* cache, int t_max, uint8_t* ws, int64_t ws_b
                 return -2;
             }
         }
-        CB200_CUDA_OK(cudaStreamSynchronize(s));
+        cudaError_t se = cudaStreamSynchronize(s);
         cudaGraphExecDestroy(exec);
         cudaGraphDestroy(graph);
+        CB200_CUDA_OK(se);
     }
     CB200_CUDA_OK(cudaMemcpy2DAsync(out_ids, n_new * sizeof(int32_t), d.all_ids + (P - 1), steps * sizeof(int32_t),
                                     n_new * sizeof(int32_t), B, cudaMemcpyDeviceToDevice, s));
@@ -601,6 +607,25 @@ static int generate(Engine& e, bf16* cache, int t_max, uint8_t* ws, int64_t ws_b
         CB200_CUDA_OK(cudaMemcpyAsync(step_logits, d.logits, sizeof(float) * B * e.V, cudaMemcpyDeviceToDevice, s));
     CB200_CUDA_OK(cudaStreamSynchronize(s));
     return 0;
+}
+
+// The step graph is captured on a private stream (the caller's may be the legacy
+// default stream, which cannot be captured); the caller's stream is drained first
+// and the private stream is drained before returning, so ordering is preserved.
+static int generate(Engine& e, bf16* cache, int t_max, uint8_t* ws, int64_t ws_bytes, const int32_t* prompt, int B,
+                    int P, int n_new, float temperature, uint64_t seed, int64_t seq_base, int32_t* out_ids,
+                    float* uniforms_out, float* step_logits, cudaStream_t user_stream) {
+    CB200_REQUIRE(e.params != nullptr, "engine is not bound");
+    CB200_REQUIRE(B >= 1 && P >= 1 && n_new >= 1, "generate needs B, prompt_len, n_new >= 1");
+    const int steps = P - 1 + n_new;
+    // positions 0 .. steps-1 are embedded; wpe has window_size rows (transformer.py:675-679, 770)
+    CB200_REQUIRE(steps <= e.W, "prompt_len + length - 1 = %d positions exceed window_size %d", steps, e.W);
+    CB200_REQUIRE(steps <= t_max, "KV cache too small: %d positions, t_max %d", steps, t_max);
+    CB200_CUDA_OK(cudaStreamSynchronize(user_stream));
+    if (e.decode_stream == nullptr)
+        CB200_CUDA_OK(cudaStreamCreateWithFlags(&e.decode_stream, cudaStreamNonBlocking));
+    return generate_on(e, cache, t_max, ws, ws_bytes, prompt, B, P, n_new, temperature, seed, seq_base, out_ids,
+                       uniforms_out, step_logits, e.decode_stream);
 }
 
 }  // namespace cb200
@@ -614,6 +639,7 @@ extern "C" {
 
 const char* cb200_last_error(void) { return g_error; }
 int cb200_abi_version(void) { return 1; }
+long long cb200_launch_count(void) { return g_launches.load(); }
 
 int64_t cb200_param_elems(const cb200_config* cfg) {
     ParamLayout l;
@@ -666,7 +692,9 @@ int cb200_engine_create(const cb200_config* cfg, void** engine) {
 }
 
 int cb200_engine_destroy(void* engine) {
-    delete static_cast<Engine*>(engine);
+    Engine* e = static_cast<Engine*>(engine);
+    if (e && e->decode_stream) cudaStreamDestroy(e->decode_stream);
+    delete e;
     return 0;
 }
 
@@ -862,6 +890,7 @@ int cb200_rowmajor_dropout_mask(uint8_t* mask, int rows, int cols, float dropout
     rowmajor_mask_kernel<<<1024, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         mask, rows, cols, make_dropout(dropout_rate, seed, step, dropout_rate > 0.f), site, layer);
     CB200_CUDA_OK(cudaGetLastError());
+    note_launch(1);
     return 0;
 }
 

@@ -24,7 +24,7 @@ from pathlib import Path
 import numpy as np
 import torch
 
-from composer_b200 import ModelSaveFrequencyMode, _lib
+from composer_b200 import ModelSaveFrequencyMode, _lib, parallel
 from composer_b200.models.base import BaseModel
 
 CHECKPOINT_INDEX = 'checkpoint.json'
@@ -301,19 +301,35 @@ class Transformer(BaseModel):
             return self._loss_dev, self._correct_dev, logits
         return self._loss_dev, self._correct_dev
 
+    def _gradient_buckets(self):
+        return parallel.gradient_buckets(self._layout, self.decoder_layers_count)
+
     def backward(self, overlap_allreduce=True):
-        '''tape.gradient (transformer.py:920).  With a process group, all-reduces the flat gradient arena.'''
+        '''
+        tape.gradient (transformer.py:920).  With more than one rank the flat
+        gradient arena is summed over ranks with NCCL; each bucket (one decoder
+        block) is all-reduced asynchronously as soon as its backward stage has
+        been enqueued, so the collective overlaps the remaining backward work.
+        Returns the world size (the 1/world mean is folded into Adam).
+        '''
 
         world = 1
         group = self.process_group
-        if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
             world = torch.distributed.get_world_size(group)
         with torch.cuda.device(self.device):
             _lib.call('cb200_zero_grads', self._engine, _stream())
-            _lib.call('cb200_backward', self._engine, -1, _stream())
-        if world > 1:
-            # Sum over ranks; the 1/world mean is folded into the Adam kernel (grad_scale).
-            torch.distributed.all_reduce(self._grads, group=group)
+            if world == 1:
+                _lib.call('cb200_backward', self._engine, -1, _stream())
+                return world
+            if not overlap_allreduce:
+                _lib.call('cb200_backward', self._engine, -1, _stream())
+                torch.distributed.all_reduce(self._grads, group=group)
+                return world
+            # bucket i is complete once backward stage i has been enqueued (stage 0 = ln_f; the last = embeddings)
+            parallel.allreduce_buckets(
+                self._grads, self._gradient_buckets(), group,
+                after_bucket=lambda stage: _lib.call('cb200_backward', self._engine, stage, _stream()))
         return world
 
     def apply_gradients(self, learning_rate=None, world=1):

@@ -47,6 +47,8 @@ typedef struct cb200_config {
 
 const char* cb200_last_error(void);
 int cb200_abi_version(void);
+/* Number of kernels this library has launched in this process (graph replays included). */
+long long cb200_launch_count(void);
 
 /* ---- parameter arena ------------------------------------------------------
  * All trainable variables live in one flat fp32 arena in Keras creation order

@@ -274,7 +274,7 @@ def check_adam(n=100000):
     mr = b1 * m0 + (1 - b1) * gg
     vr = b2 * v0 + (1 - b2) * gg * gg
     pr = p0 - lr_t * mr / (vr.sqrt() + eps)
-    return _finish([_stats('adam p', p, pr, 1e-6), _stats('adam m', m, mr, 1e-6), _stats('adam v', v, vr, 1e-6),
+    return _finish([_stats('adam p', p, pr, 1e-5), _stats('adam m', m, mr, 1e-5), _stats('adam v', v, vr, 1e-5),
                     _stats('adam shadow', shadow, pr, 1e-2)])
 
 
