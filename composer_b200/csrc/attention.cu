@@ -75,22 +75,10 @@ __device__ __forceinline__ void load_tile_async(uint32_t smem_base, const __nv_b
     }
 }
 
-// Keep-multiplier bits for the 8 accumulator n-tiles of a 16 x 64 score block
-// (rows i_lo = base + g and i_hi = i_lo + 8): bit (2*t + e) of lo/hi is set when
-// element (row, col 8*t + 2*tig + e) is kept.
-__device__ __forceinline__ void attn_keep_bits(const DropoutParams& drop, uint32_t layer, uint32_t bh, uint32_t i_lo,
-                                               uint32_t jb, uint32_t tig, uint32_t& lo, uint32_t& hi) {
-    lo = 0; hi = 0;
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-        const Philox4 r0 = drop_bits_attn(drop, layer, bh, i_lo, jb, tig, half);
-        const Philox4 r1 = drop_bits_attn(drop, layer, bh, i_lo + 8, jb, tig, half);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            lo |= (drop_u16(r0, e) >= drop.threshold16 ? 1u : 0u) << (half * 8 + e);
-            hi |= (drop_u16(r1, e) >= drop.threshold16 ? 1u : 0u) << (half * 8 + e);
-        }
-    }
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
 }
 
 constexpr int ATT_BR = 64;   // query rows per CTA (4 warps x 16)
@@ -103,7 +91,7 @@ constexpr int ATT_THREADS = 128;
 template <int D>
 __global__ void __launch_bounds__(ATT_THREADS)
 attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, float* __restrict__ lse,
-                int T, int H, float scale_log2, DropoutParams drop, uint32_t layer) {
+                int T, int H, float scale_log2, AttnDropKey drop) {
     constexpr int KS = D / 16;     // k-steps of the QK^T product
     constexpr int NT_O = D / 8;    // n-tiles of the output
     __shared__ __align__(128) uint8_t sQ[ATT_BR * D * 2];
@@ -188,8 +176,8 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
         float bm_lo = -INFINITY, bm_hi = -INFINITY;
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
-            bm_lo = fmaxf(bm_lo, fmaxf(s[t][0], s[t][1]));
-            bm_hi = fmaxf(bm_hi, fmaxf(s[t][2], s[t][3]));
+            bm_lo = fmax3(bm_lo, s[t][0], s[t][1]);
+            bm_hi = fmax3(bm_hi, s[t][2], s[t][3]);
         }
         bm_lo = fmaxf(bm_lo, __shfl_xor_sync(0xffffffffu, bm_lo, 1));
         bm_lo = fmaxf(bm_lo, __shfl_xor_sync(0xffffffffu, bm_lo, 2));
@@ -216,15 +204,14 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
             o[t][0] *= corr_lo; o[t][1] *= corr_lo; o[t][2] *= corr_hi; o[t][3] *= corr_hi;
         }
         // ---- dropout on the probabilities (the row sums above stay undropped) ----
-        if (drop.threshold16 != 0) {
-            uint32_t keep_lo, keep_hi;
-            attn_keep_bits(drop, layer, b * H + h, q0 + warp * 16 + g, j, tig, keep_lo, keep_hi);
+        if (drop.threshold32 != 0) {
+            uint32_t x = attn_stream_seed(drop, b * H + h, (q0 >> 4) + warp, j, lane);
 #pragma unroll
             for (int t = 0; t < 8; ++t) {
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    if (!((keep_lo >> (2 * t + e)) & 1u)) s[t][e] = 0.f;
-                    if (!((keep_hi >> (2 * t + e)) & 1u)) s[t][2 + e] = 0.f;
+                for (int e = 0; e < 4; ++e) {
+                    x = x * ATTN_LCG_A + ATTN_LCG_C;
+                    if (x < drop.threshold32) s[t][e] = 0.f;
                 }
             }
         }
@@ -255,7 +242,7 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
     l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
     l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1);
     l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 2);
-    const float ks_scale = (drop.threshold16 != 0) ? drop.keep_scale : 1.0f;
+    const float ks_scale = (drop.threshold32 != 0) ? drop.keep_scale : 1.0f;
     const float inv_lo = ks_scale / l_lo, inv_hi = ks_scale / l_hi;
     const int i_lo = q0 + warp * 16 + g, i_hi = i_lo + 8;
     __nv_bfloat16* ob = out + static_cast<size_t>(b) * T * E + h * D;
@@ -310,17 +297,20 @@ attn_bwd_delta_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat1
 // 64-row query block, so dQ rows are complete inside a warp (added to the fp32
 // dq buffer with vector reductions) while the warp's partial dK / dV stay in
 // registers for the whole walk and are combined across the 4 warps at the end.
-// P and dS are needed transposed (dV += P^T dO, dK += dS^T Q): movmatrix on
-// the packed bf16 accumulator tiles.
+// The key block is processed in 32-key halves (fewer live registers); a half
+// that lies entirely above the warp's rows is skipped, one that straddles the
+// diagonal takes the masked path.  P and dS are needed transposed (dV += P^T dO,
+// dK += dS^T Q): movmatrix on the packed bf16 accumulator tiles.
+// With dropout (keep mask M, keep scale ks): dV = ks * (M.P)^T dO,
+// dS = ks * P.(M.dP - delta/ks); the ks factors are applied once at the end.
 // ---------------------------------------------------------------------------
-template <int D, int BC>
-__global__ void __launch_bounds__(ATT_THREADS)
+template <int D, int BC, bool DROP>
+__global__ void __launch_bounds__(ATT_THREADS, (D == 16) ? 4 : 1)
 attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
                 const float* __restrict__ lse, const float* __restrict__ delta, float* __restrict__ dq_acc,
-                __nv_bfloat16* __restrict__ dqkv, int T, int H, float scale, float scale_log2, DropoutParams drop,
-                uint32_t layer) {
+                __nv_bfloat16* __restrict__ dqkv, int T, int H, float scale, float scale_log2, AttnDropKey drop) {
     constexpr int KS = D / 16;
-    constexpr int NT_C = BC / 8;    // n-tiles across the key block
+    constexpr int HALVES = BC / 32;
     constexpr int MT = BC / 16;     // m-tiles of dK / dV
     constexpr int NT_D = D / 8;
     constexpr int TILE_Q = ATT_BR * D * 2;
@@ -343,6 +333,8 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
     const int k0 = kb * BC;
     const int nqb = (T + ATT_BR - 1) / ATT_BR;
     const int qb_first = k0 / ATT_BR;
+    const float ks_scale = DROP ? drop.keep_scale : 1.0f;
+    const float inv_ks = 1.0f / ks_scale;
 
     const __nv_bfloat16* base = qkv + static_cast<size_t>(b) * T * ld;
     const __nv_bfloat16* gq = base + h * D;
@@ -359,7 +351,7 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
             const int r = qb * ATT_BR + tid;
             // rows past the end get lse = +inf so that their probabilities are exactly 0
             sLse[buf * ATT_BR + tid] = (r < T) ? glse[r] : INFINITY;
-            sDelta[buf * ATT_BR + tid] = (r < T) ? gdelta[r] : 0.f;
+            sDelta[buf * ATT_BR + tid] = (r < T) ? gdelta[r] * inv_ks : 0.f;
         }
     };
 
@@ -389,131 +381,130 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
 
         const uint32_t qbase = smem_u32(sQ + buf * TILE_Q), dobase = smem_u32(sdO + buf * TILE_Q);
         const uint32_t kbase = smem_u32(sK), vbase = smem_u32(sV);
-        uint32_t qf[KS][4], dof[KS][4];
-#pragma unroll
-        for (int ks = 0; ks < KS; ++ks) {
-            const int r = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-            const int c = ks * 2 + (lane >> 4);
-            ldmatrix_x4(qf[ks], qbase + tile_off<D>(r, c));
-            ldmatrix_x4(dof[ks], dobase + tile_off<D>(r, c));
-        }
-        // ---- S = Q K^T and dP = dO V^T ------------------------------------
-        float s[NT_C][4], dp[NT_C][4];
-#pragma unroll
-        for (int t = 0; t < NT_C; ++t) {
-            s[t][0] = s[t][1] = s[t][2] = s[t][3] = 0.f;
-            dp[t][0] = dp[t][1] = dp[t][2] = dp[t][3] = 0.f;
-        }
-#pragma unroll
-        for (int ks = 0; ks < KS; ++ks) {
-#pragma unroll
-            for (int tp = 0; tp < NT_C / 2; ++tp) {
-                uint32_t kf[4], vf[4];
-                const int key = tp * 16 + ((lane >> 4) << 3) + (lane & 7);
-                const int c = ks * 2 + ((lane >> 3) & 1);
-                ldmatrix_x4(kf, kbase + tile_off<D>(key, c));
-                ldmatrix_x4(vf, vbase + tile_off<D>(key, c));
-                mma_bf16_16816(s[2 * tp], qf[ks], kf[0], kf[1]);
-                mma_bf16_16816(s[2 * tp + 1], qf[ks], kf[2], kf[3]);
-                mma_bf16_16816(dp[2 * tp], dof[ks], vf[0], vf[1]);
-                mma_bf16_16816(dp[2 * tp + 1], dof[ks], vf[2], vf[3]);
-            }
-        }
-        // ---- P = exp2(S*c - lse), causal mask, dropout, dS = P * (dP - delta) ----
+        const int row_min = qb * ATT_BR + warp * 16;     // this warp's first query row
         const int r_lo = warp * 16 + g, r_hi = r_lo + 8;
-        const float lse_lo = sLse[buf * ATT_BR + r_lo], lse_hi = sLse[buf * ATT_BR + r_hi];
-        const float dl_lo = sDelta[buf * ATT_BR + r_lo], dl_hi = sDelta[buf * ATT_BR + r_hi];
         const int i_lo = qb * ATT_BR + r_lo, i_hi = i_lo + 8;
-        const bool diagonal = (qb * ATT_BR) < (k0 + BC);   // some key of this block may exceed some query row
-        uint32_t keep_lo = 0xFFFFFFFFu, keep_hi = 0xFFFFFFFFu;
-        const bool dropping = drop.threshold16 != 0;
-        if (dropping) {
-            if (BC == 64) {
-                attn_keep_bits(drop, layer, b * H + h, i_lo, k0 / 64, tig, keep_lo, keep_hi);
-            } else {   // BC == 32: one half of a 64-wide dropout block
-                const uint32_t half = (k0 % 64) / 32;
-                const Philox4 x0 = drop_bits_attn(drop, layer, b * H + h, i_lo, k0 / 64, tig, half);
-                const Philox4 x1 = drop_bits_attn(drop, layer, b * H + h, i_hi, k0 / 64, tig, half);
-                keep_lo = 0; keep_hi = 0;
+
+        if (k0 <= row_min + 15 && row_min < T) {          // otherwise every key of the block is masked for this warp
+            uint32_t qf[KS][4], dof[KS][4];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    keep_lo |= (drop_u16(x0, e) >= drop.threshold16 ? 1u : 0u) << e;
-                    keep_hi |= (drop_u16(x1, e) >= drop.threshold16 ? 1u : 0u) << e;
-                }
+            for (int ks = 0; ks < KS; ++ks) {
+                const int r = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+                const int c = ks * 2 + (lane >> 4);
+                ldmatrix_x4(qf[ks], qbase + tile_off<D>(r, c));
+                ldmatrix_x4(dof[ks], dobase + tile_off<D>(r, c));
             }
-        }
-        const float ks_scale = dropping ? drop.keep_scale : 1.0f;
-        // p (possibly dropped, for dV) and ds, packed to bf16 and transposed 8x8-block-wise
-        uint32_t pT[2][NT_C], dsT[2][NT_C];   // [query half][key n-tile]
-        uint32_t dsA[NT_C][2];                // untransposed dS for dQ: [n-tile][lo/hi rows]
-#pragma unroll
-        for (int t = 0; t < NT_C; ++t) {
-            float p[4], ds[4], pd[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int col = k0 + t * 8 + 2 * tig + (e & 1);
-                const int row = (e < 2) ? i_lo : i_hi;
-                const float l = (e < 2) ? lse_lo : lse_hi;
-                float pv = fast_exp2(fmaf(s[t][e], scale_log2, -l));
-                if (diagonal && col > row) pv = 0.f;
-                const bool kept = (((e < 2) ? keep_lo : keep_hi) >> (2 * t + (e & 1))) & 1u;
-                const float dpv = kept ? dp[t][e] * ks_scale : 0.f;
-                p[e] = pv;
-                pd[e] = kept ? pv * ks_scale : 0.f;
-                ds[e] = pv * (dpv - ((e < 2) ? dl_lo : dl_hi));
-            }
-            const uint32_t p_lo = pack_bf16(pd[0], pd[1]), p_hi = pack_bf16(pd[2], pd[3]);
-            const uint32_t d_lo = pack_bf16(ds[0], ds[1]), d_hi = pack_bf16(ds[2], ds[3]);
-            dsA[t][0] = d_lo; dsA[t][1] = d_hi;
-            pT[0][t] = movmatrix_trans(p_lo); pT[1][t] = movmatrix_trans(p_hi);
-            dsT[0][t] = movmatrix_trans(d_lo); dsT[1][t] = movmatrix_trans(d_hi);
-        }
-        // ---- dQ (16 x D) = dS (16 x BC) K (BC x D), complete for these rows over this key block ----
-        {
+            const float lse_lo = sLse[buf * ATT_BR + r_lo], lse_hi = sLse[buf * ATT_BR + r_hi];
+            const float dl_lo = sDelta[buf * ATT_BR + r_lo], dl_hi = sDelta[buf * ATT_BR + r_hi];
             float dq[NT_D][4];
 #pragma unroll
             for (int t = 0; t < NT_D; ++t) { dq[t][0] = dq[t][1] = dq[t][2] = dq[t][3] = 0.f; }
+
 #pragma unroll
-            for (int ks = 0; ks < BC / 16; ++ks) {
-                const uint32_t a[4] = {dsA[2 * ks][0], dsA[2 * ks][1], dsA[2 * ks + 1][0], dsA[2 * ks + 1][1]};
+            for (int hf = 0; hf < HALVES; ++hf) {
+                const int kh0 = k0 + hf * 32;                 // first key of this half
+                if (kh0 > row_min + 15) continue;             // entirely above the diagonal for this warp
+                const bool partial = (kh0 + 31) > row_min;    // straddles the diagonal
+                // ---- S = Q K^T and dP = dO V^T for 32 keys ------------------
+                float s[4][4], dp[4][4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    s[t][0] = s[t][1] = s[t][2] = s[t][3] = 0.f;
+                    dp[t][0] = dp[t][1] = dp[t][2] = dp[t][3] = 0.f;
+                }
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+                    for (int tp = 0; tp < 2; ++tp) {
+                        uint32_t kf[4], vf[4];
+                        const int key = hf * 32 + tp * 16 + ((lane >> 4) << 3) + (lane & 7);
+                        const int c = ks * 2 + ((lane >> 3) & 1);
+                        ldmatrix_x4(kf, kbase + tile_off<D>(key, c));
+                        ldmatrix_x4(vf, vbase + tile_off<D>(key, c));
+                        mma_bf16_16816(s[2 * tp], qf[ks], kf[0], kf[1]);
+                        mma_bf16_16816(s[2 * tp + 1], qf[ks], kf[2], kf[3]);
+                        mma_bf16_16816(dp[2 * tp], dof[ks], vf[0], vf[1]);
+                        mma_bf16_16816(dp[2 * tp + 1], dof[ks], vf[2], vf[3]);
+                    }
+                }
+                // ---- P = exp2(S*c - lse) ; dS' = P * (M.dP - delta/ks) -------
+                uint32_t x = 0;
+                if (DROP) {
+                    x = attn_stream_seed(drop, b * H + h, row_min >> 4, kh0 >> 6, lane);
+                    if (kh0 & 32) x = x * lcg_mul_pow(16) + lcg_add_pow(16);   // second half of the 64-key block
+                }
+                uint32_t pT[2][4], dsT[2][4];   // [query half][key n-tile], transposed 8x8 blocks
+                uint32_t dsA[4][2];             // untransposed dS' for dQ
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    float p[4], ds[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float pv = fast_exp2(fmaf(s[t][e], scale_log2, (e < 2) ? -lse_lo : -lse_hi));
+                        if (partial) {
+                            const int col = kh0 + t * 8 + 2 * tig + (e & 1);
+                            if (col > ((e < 2) ? i_lo : i_hi)) pv = 0.f;
+                        }
+                        float dpv = dp[t][e];
+                        float pd = pv;
+                        if (DROP) {
+                            x = x * ATTN_LCG_A + ATTN_LCG_C;
+                            if (x < drop.threshold32) { dpv = 0.f; pd = 0.f; }
+                        }
+                        p[e] = pd;
+                        ds[e] = pv * (dpv - ((e < 2) ? dl_lo : dl_hi));
+                    }
+                    const uint32_t p_lo = pack_bf16(p[0], p[1]), p_hi = pack_bf16(p[2], p[3]);
+                    const uint32_t d_lo = pack_bf16(ds[0], ds[1]), d_hi = pack_bf16(ds[2], ds[3]);
+                    dsA[t][0] = d_lo; dsA[t][1] = d_hi;
+                    pT[0][t] = movmatrix_trans(p_lo); pT[1][t] = movmatrix_trans(p_hi);
+                    dsT[0][t] = movmatrix_trans(d_lo); dsT[1][t] = movmatrix_trans(d_hi);
+                }
+                // ---- dQ += dS' K   (k = this half's 32 keys) -----------------
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {
+                    const uint32_t a[4] = {dsA[2 * ks][0], dsA[2 * ks][1], dsA[2 * ks + 1][0], dsA[2 * ks + 1][1]};
+#pragma unroll
+                    for (int np = 0; np < NT_D / 2; ++np) {
+                        uint32_t kf[4];
+                        const int key = hf * 32 + ks * 16 + (((lane >> 3) & 1) << 3) + (lane & 7);
+                        const int c = np * 2 + (lane >> 4);
+                        ldmatrix_x4_trans(kf, kbase + tile_off<D>(key, c));
+                        mma_bf16_16816(dq[2 * np], a, kf[0], kf[1]);
+                        mma_bf16_16816(dq[2 * np + 1], a, kf[2], kf[3]);
+                    }
+                }
+                // ---- dV += P^T dO ; dK += dS'^T Q   (M = keys, K = this warp's 16 query rows) ----
 #pragma unroll
                 for (int np = 0; np < NT_D / 2; ++np) {
-                    uint32_t kf[4];
-                    const int key = ks * 16 + (((lane >> 3) & 1) << 3) + (lane & 7);
+                    uint32_t dob[4], qb4[4];
+                    const int r = warp * 16 + (((lane >> 3) & 1) << 3) + (lane & 7);
                     const int c = np * 2 + (lane >> 4);
-                    ldmatrix_x4_trans(kf, kbase + tile_off<D>(key, c));
-                    mma_bf16_16816(dq[2 * np], a, kf[0], kf[1]);
-                    mma_bf16_16816(dq[2 * np + 1], a, kf[2], kf[3]);
+                    ldmatrix_x4_trans(dob, dobase + tile_off<D>(r, c));
+                    ldmatrix_x4_trans(qb4, qbase + tile_off<D>(r, c));
+#pragma unroll
+                    for (int m = 0; m < 2; ++m) {
+                        const uint32_t pa[4] = {pT[0][2 * m], pT[0][2 * m + 1], pT[1][2 * m], pT[1][2 * m + 1]};
+                        const uint32_t da[4] = {dsT[0][2 * m], dsT[0][2 * m + 1], dsT[1][2 * m], dsT[1][2 * m + 1]};
+                        mma_bf16_16816(dv[hf * 2 + m][2 * np], pa, dob[0], dob[1]);
+                        mma_bf16_16816(dv[hf * 2 + m][2 * np + 1], pa, dob[2], dob[3]);
+                        mma_bf16_16816(dk[hf * 2 + m][2 * np], da, qb4[0], qb4[1]);
+                        mma_bf16_16816(dk[hf * 2 + m][2 * np + 1], da, qb4[2], qb4[3]);
+                    }
                 }
             }
+            // ---- dQ rows of this warp are complete for this key block ----------
+            const float dq_scale = scale * ks_scale;
             float* dqb = dq_acc + static_cast<size_t>(b) * T * E + h * D;
 #pragma unroll
             for (int t = 0; t < NT_D; ++t) {
                 const int col = t * 8 + 2 * tig;
                 if (i_lo < T)
                     asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(dqb + static_cast<size_t>(i_lo) * E + col),
-                                 "f"(dq[t][0] * scale), "f"(dq[t][1] * scale) : "memory");
+                                 "f"(dq[t][0] * dq_scale), "f"(dq[t][1] * dq_scale) : "memory");
                 if (i_hi < T)
                     asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(dqb + static_cast<size_t>(i_hi) * E + col),
-                                 "f"(dq[t][2] * scale), "f"(dq[t][3] * scale) : "memory");
-            }
-        }
-        // ---- dV += P^T dO ; dK += dS^T Q   (M = keys, K = this warp's 16 query rows) ----
-#pragma unroll
-        for (int np = 0; np < NT_D / 2; ++np) {
-            uint32_t dob[4], qb4[4];
-            const int r = warp * 16 + (((lane >> 3) & 1) << 3) + (lane & 7);
-            const int c = np * 2 + (lane >> 4);
-            ldmatrix_x4_trans(dob, dobase + tile_off<D>(r, c));
-            ldmatrix_x4_trans(qb4, qbase + tile_off<D>(r, c));
-#pragma unroll
-            for (int m = 0; m < MT; ++m) {
-                const uint32_t pa[4] = {pT[0][2 * m], pT[0][2 * m + 1], pT[1][2 * m], pT[1][2 * m + 1]};
-                const uint32_t da[4] = {dsT[0][2 * m], dsT[0][2 * m + 1], dsT[1][2 * m], dsT[1][2 * m + 1]};
-                mma_bf16_16816(dv[m][2 * np], pa, dob[0], dob[1]);
-                mma_bf16_16816(dv[m][2 * np + 1], pa, dob[2], dob[3]);
-                mma_bf16_16816(dk[m][2 * np], da, qb4[0], qb4[1]);
-                mma_bf16_16816(dk[m][2 * np + 1], da, qb4[2], qb4[3]);
+                                 "f"(dq[t][2] * dq_scale), "f"(dq[t][3] * dq_scale) : "memory");
             }
         }
         __syncthreads();
@@ -534,15 +525,16 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
                 atomicAdd(&sRed[BC * D + key * D + col], dv[m][t][e]);
             }
     __syncthreads();
+    const float dk_scale = scale * ks_scale;
     __nv_bfloat16* dkb = dqkv + static_cast<size_t>(b) * T * ld + E + h * D;
     __nv_bfloat16* dvb = dqkv + static_cast<size_t>(b) * T * ld + 2 * E + h * D;
     for (int i = tid; i < BC * D / 2; i += ATT_THREADS) {
         const int key = (2 * i) / D, col = (2 * i) % D;
         if (k0 + key < T) {
             *reinterpret_cast<uint32_t*>(dkb + static_cast<size_t>(k0 + key) * ld + col) =
-                pack_bf16(sRed[key * D + col] * scale, sRed[key * D + col + 1] * scale);
+                pack_bf16(sRed[key * D + col] * dk_scale, sRed[key * D + col + 1] * dk_scale);
             *reinterpret_cast<uint32_t*>(dvb + static_cast<size_t>(k0 + key) * ld + col) =
-                pack_bf16(sRed[BC * D + key * D + col], sRed[BC * D + key * D + col + 1]);
+                pack_bf16(sRed[BC * D + key * D + col] * ks_scale, sRed[BC * D + key * D + col + 1] * ks_scale);
         }
     }
 }
@@ -572,12 +564,14 @@ static const float kLog2e = 1.4426950408889634f;
 int attention_fwd(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse, int B, int T, int H, int D, float scale,
                   const DropoutParams& drop, uint32_t layer, cudaStream_t s) {
     if (B * T == 0) return 0;
+    CB200_REQUIRE(T < (1 << 17), "sequences of 2^17 tokens or more are not supported by the attention dropout stream");
     dim3 grid((T + ATT_BR - 1) / ATT_BR, H, B);
     const float c = scale * kLog2e;
+    const AttnDropKey key = make_attn_drop_key(drop, layer);
     switch (D) {
-        case 16: attn_fwd_kernel<16><<<grid, ATT_THREADS, 0, s>>>(qkv, out, lse, T, H, c, drop, layer); break;
-        case 32: attn_fwd_kernel<32><<<grid, ATT_THREADS, 0, s>>>(qkv, out, lse, T, H, c, drop, layer); break;
-        case 64: attn_fwd_kernel<64><<<grid, ATT_THREADS, 0, s>>>(qkv, out, lse, T, H, c, drop, layer); break;
+        case 16: attn_fwd_kernel<16><<<grid, ATT_THREADS, 0, s>>>(qkv, out, lse, T, H, c, key); break;
+        case 32: attn_fwd_kernel<32><<<grid, ATT_THREADS, 0, s>>>(qkv, out, lse, T, H, c, key); break;
+        case 64: attn_fwd_kernel<64><<<grid, ATT_THREADS, 0, s>>>(qkv, out, lse, T, H, c, key); break;
         default: set_error("attention head size %d is not supported (16, 32 or 64)", D); return -1;
     }
     CB200_CUDA_OK(cudaGetLastError());
@@ -585,22 +579,30 @@ int attention_fwd(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse, int 
     return 0;
 }
 
-template <int D, int BC>
+template <int D, int BC, bool DROP>
 static int launch_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* dout, const float* lse, const float* delta,
-                      float* dq_acc, __nv_bfloat16* dqkv, int B, int T, int H, float scale, const DropoutParams& drop,
-                      uint32_t layer, cudaStream_t s) {
+                      float* dq_acc, __nv_bfloat16* dqkv, int B, int T, int H, float scale, const AttnDropKey& key,
+                      cudaStream_t s) {
     constexpr size_t smem = 2 * BC * D * 2 + 4 * ATT_BR * D * 2 + 4 * ATT_BR * sizeof(float) + 2 * BC * D * sizeof(float);
-    auto kernel = attn_bwd_kernel<D, BC>;
+    auto kernel = attn_bwd_kernel<D, BC, DROP>;
     static bool configured = false;
     if (!configured) {
         CB200_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     dim3 grid((T + BC - 1) / BC, H, B);
-    kernel<<<grid, ATT_THREADS, smem, s>>>(qkv, dout, lse, delta, dq_acc, dqkv, T, H, scale, scale * kLog2e, drop, layer);
+    kernel<<<grid, ATT_THREADS, smem, s>>>(qkv, dout, lse, delta, dq_acc, dqkv, T, H, scale, scale * kLog2e, key);
     CB200_CUDA_OK(cudaGetLastError());
     note_launch(1);
     return 0;
+}
+
+template <int D, int BC>
+static int launch_bwd_drop(bool dropping, const __nv_bfloat16* qkv, const __nv_bfloat16* dout, const float* lse,
+                           const float* delta, float* dq_acc, __nv_bfloat16* dqkv, int B, int T, int H, float scale,
+                           const AttnDropKey& key, cudaStream_t s) {
+    return dropping ? launch_bwd<D, BC, true>(qkv, dout, lse, delta, dq_acc, dqkv, B, T, H, scale, key, s)
+                    : launch_bwd<D, BC, false>(qkv, dout, lse, delta, dq_acc, dqkv, B, T, H, scale, key, s);
 }
 
 int attention_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* out, const __nv_bfloat16* dout, const float* lse,
@@ -609,19 +611,21 @@ int attention_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* out, const __nv
     if (B * T == 0) return 0;
     const int rows = B * T;
     const int E = H * D;
+    const AttnDropKey key = make_attn_drop_key(drop, layer);
+    const bool dropping = key.threshold32 != 0;
     int rc = 0;
     switch (D) {
         case 16:
             attn_bwd_delta_kernel<16><<<(rows + 7) / 8, 256, 0, s>>>(dout, out, delta, rows, T, H);
-            rc = launch_bwd<16, 64>(qkv, dout, lse, delta, dq_acc, dqkv, B, T, H, scale, drop, layer, s);
+            rc = launch_bwd_drop<16, 64>(dropping, qkv, dout, lse, delta, dq_acc, dqkv, B, T, H, scale, key, s);
             break;
         case 32:
             attn_bwd_delta_kernel<32><<<(rows + 7) / 8, 256, 0, s>>>(dout, out, delta, rows, T, H);
-            rc = launch_bwd<32, 32>(qkv, dout, lse, delta, dq_acc, dqkv, B, T, H, scale, drop, layer, s);
+            rc = launch_bwd_drop<32, 32>(dropping, qkv, dout, lse, delta, dq_acc, dqkv, B, T, H, scale, key, s);
             break;
         case 64:
             attn_bwd_delta_kernel<64><<<(rows + 7) / 8, 256, 0, s>>>(dout, out, delta, rows, T, H);
-            rc = launch_bwd<64, 32>(qkv, dout, lse, delta, dq_acc, dqkv, B, T, H, scale, drop, layer, s);
+            rc = launch_bwd_drop<64, 32>(dropping, qkv, dout, lse, delta, dq_acc, dqkv, B, T, H, scale, key, s);
             break;
         default: set_error("attention head size %d is not supported (16, 32 or 64)", D); return -1;
     }
@@ -638,22 +642,29 @@ int attention_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* out, const __nv
 }
 
 // Debug/parity helper: materialise the attention-probability keep mask
-// ([B, H, T, T] bytes, 1 = kept) that the kernels above apply.
-__global__ void attn_mask_export_kernel(uint8_t* __restrict__ mask, int T, int H, DropoutParams drop, uint32_t layer) {
+// ([B, H, T, T] bytes, 1 = kept) that the kernels above apply.  One thread per
+// (16-row group, 64-key block, lane) replays that lane's LCG stream.
+__global__ void attn_mask_export_kernel(uint8_t* __restrict__ mask, int T, int H, AttnDropKey drop) {
     const int bh = blockIdx.y;
-    const int i = blockIdx.x;
-    for (int j = threadIdx.x; j < T; j += blockDim.x) {
-        const int jb = j / 64, within = j % 64;
-        const int t = within / 8, tig = (within % 8) / 2, e = within % 2;
-        const Philox4 r = drop_bits_attn(drop, layer, bh, i, jb, tig, t / 4);
-        const uint32_t u = drop_u16(r, (t % 4) * 2 + e);
-        mask[(static_cast<size_t>(bh) * T + i) * T + j] = (drop.threshold16 == 0 || u >= drop.threshold16) ? 1 : 0;
+    const int n16 = (T + 15) / 16, n64 = (T + 63) / 64;
+    const int total = n16 * n64 * 32;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int lane = idx & 31, jb = (idx >> 5) % n64, i16 = (idx >> 5) / n64;
+        const int g = lane >> 2, tig = lane & 3;
+        uint32_t x = attn_stream_seed(drop, bh, i16, jb, lane);
+        for (int t = 0; t < 8; ++t)
+            for (int e = 0; e < 4; ++e) {
+                x = x * ATTN_LCG_A + ATTN_LCG_C;
+                const int i = i16 * 16 + g + 8 * (e >> 1), j = jb * 64 + 8 * t + 2 * tig + (e & 1);
+                if (i < T && j < T)
+                    mask[(static_cast<size_t>(bh) * T + i) * T + j] = (drop.threshold32 == 0 || x >= drop.threshold32) ? 1 : 0;
+            }
     }
 }
 
 int attention_mask_export(uint8_t* mask, int B, int T, int H, const DropoutParams& drop, uint32_t layer, cudaStream_t s) {
-    dim3 grid(T, B * H);
-    attn_mask_export_kernel<<<grid, 128, 0, s>>>(mask, T, H, drop, layer);
+    dim3 grid(64, B * H);
+    attn_mask_export_kernel<<<grid, 256, 0, s>>>(mask, T, H, make_attn_drop_key(drop, layer));
     CB200_CUDA_OK(cudaGetLastError());
     note_launch(1);
     return 0;

@@ -95,20 +95,22 @@ __device__ __forceinline__ float fast_tanh(float x) {
     return y;
 }
 
-// GELU, tanh form (reference: composer/models/transformer.py:35-40).
+// GELU, tanh form (reference: composer/models/transformer.py:35-40), with the hardware tanh
+// (MUFU.TANH, relative error ~2^-11: below the bf16 rounding of the stored result).
 __device__ __forceinline__ float gelu_tanh(float x) {
     const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-    float inner = k0 * (x + k1 * x * x * x);
-    return 0.5f * x * (1.0f + tanhf(inner));
+    const float t = fast_tanh(k0 * x * fmaf(k1, x * x, 1.0f));
+    const float hx = 0.5f * x;
+    return fmaf(hx, t, hx);
 }
 
 // d/dx of the tanh-form GELU.
 __device__ __forceinline__ float gelu_tanh_grad(float x) {
     const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-    float x2 = x * x;
-    float t = tanhf(k0 * (x + k1 * x * x2));
-    float dt = (1.0f - t * t) * k0 * (1.0f + 3.0f * k1 * x2);
-    return 0.5f * (1.0f + t) + 0.5f * x * dt;
+    const float x2 = x * x;
+    const float t = fast_tanh(k0 * x * fmaf(k1, x2, 1.0f));
+    const float dt = (1.0f - t * t) * k0 * fmaf(3.0f * k1, x2, 1.0f);
+    return fmaf(0.5f * x, dt, fmaf(0.5f, t, 0.5f));
 }
 
 // ---------------------------------------------------------------------------
@@ -142,6 +144,7 @@ struct DropoutParams {
     uint32_t step;               // global step (so masks differ every step)
     uint32_t threshold16;        // drop when 16-bit draw < threshold16 ; 0 = dropout off
     float keep_scale;            // 1 / (1 - rate)
+    float rate;                  // the configured rate (0 when off)
 };
 
 __host__ __device__ __forceinline__ uint32_t drop_key1(const DropoutParams& p, uint32_t site, uint32_t layer) {
@@ -155,14 +158,58 @@ __host__ __device__ __forceinline__ Philox4 drop_bits_rowmajor(const DropoutPara
     return philox4x32_10(row, col8, 0x0D0Du, site, p.seed_lo, drop_key1(p, site, layer));
 }
 
-// Attention-probability dropout.  One call covers, for query row i of
-// (batch b, head h), the 8 key columns {64*jb + 8*t + 2*tig + e : t in
-// 4*half..4*half+3, e in 0..1}: exactly what one thread of the m16n8k16
-// accumulator layout owns in half of a 64-wide key block.
-__host__ __device__ __forceinline__ Philox4 drop_bits_attn(const DropoutParams& p, uint32_t layer, uint32_t bh,
-                                                           uint32_t i, uint32_t jb, uint32_t tig, uint32_t half) {
-    return philox4x32_10(i, (jb << 3) | (tig << 1) | half, bh, SITE_ATTN_W, p.seed_lo,
-                         drop_key1(p, SITE_ATTN_W, layer));
+// Attention-probability dropout.  The T x T keep mask is defined per 16 x 64 block (16 query rows
+// starting at 16*i16, 64 keys starting at 64*jb) of one (batch, head) pair `bh`.  In the m16n8k16
+// accumulator layout such a block is owned by 32 lanes; lane = 4*g + tig owns the 32 elements
+//     idx = 4*t + e,  t = 0..7, e = 0..3  ->  (row 16*i16 + g + 8*(e >> 1), key 64*jb + 8*t + 2*tig + (e & 1)).
+// Their keep decisions come from one LCG stream: x_0 = attn_stream_seed(...), x_{n+1} = A x_n + C, element
+// idx is kept iff x_{idx+1} >= threshold32.  The stream seed is a Philox-keyed hash of the block coordinates
+// (the key is drawn once per launch from Philox4x32-10 of (seed, step, layer)), so forward, backward and the
+// mask export regenerate identical masks with ~3 instructions per element instead of a Philox call per 8.
+struct AttnDropKey {
+    uint32_t k0, k1;
+    uint32_t threshold32;   // drop when x < threshold32 ; 0 = dropout off
+    float keep_scale;
+};
+
+constexpr uint32_t ATTN_LCG_A = 747796405u, ATTN_LCG_C = 2891336453u;
+
+__host__ __device__ constexpr uint32_t lcg_mul_pow(int n) {
+    uint32_t a = 1;
+    for (int i = 0; i < n; ++i) a *= ATTN_LCG_A;
+    return a;
+}
+__host__ __device__ constexpr uint32_t lcg_add_pow(int n) {
+    uint32_t c = 0;
+    for (int i = 0; i < n; ++i) c = c * ATTN_LCG_A + ATTN_LCG_C;
+    return c;
+}
+
+__host__ __device__ __forceinline__ uint32_t fmix32(uint32_t h) {
+    h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+    return h;
+}
+
+__host__ __device__ __forceinline__ uint32_t attn_stream_seed(const AttnDropKey& key, uint32_t bh, uint32_t i16,
+                                                              uint32_t jb, uint32_t lane) {
+    const uint32_t lo = (i16 << 16) ^ (jb << 5) ^ lane;   // injective for T < 2^17
+    uint32_t h = fmix32(lo ^ key.k0);
+    return fmix32(h + bh * 0x9E3779B9u + key.k1);
+}
+
+__host__ __device__ __forceinline__ AttnDropKey make_attn_drop_key(const DropoutParams& p, uint32_t layer) {
+    AttnDropKey k;
+    const Philox4 r = philox4x32_10(layer, p.step, SITE_ATTN_W, 0x17u, p.seed_lo, p.seed_hi);
+    k.k0 = r.x; k.k1 = r.y;
+    if (p.threshold16 == 0) {
+        k.threshold32 = 0; k.keep_scale = 1.f;
+    } else {
+        double t = static_cast<double>(p.rate) * 4294967296.0;
+        if (t > 4294967295.0) t = 4294967295.0;
+        k.threshold32 = static_cast<uint32_t>(t);
+        k.keep_scale = p.keep_scale;
+    }
+    return k;
 }
 
 __host__ __device__ __forceinline__ uint32_t drop_u16(const Philox4& r, int e) {

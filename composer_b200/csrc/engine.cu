@@ -139,11 +139,13 @@ static DropoutParams make_dropout(float rate, uint64_t seed, uint32_t step, bool
     if (!enabled || rate <= 0.f) {
         p.threshold16 = 0;
         p.keep_scale = 1.f;
+        p.rate = 0.f;
     } else {
         double t = static_cast<double>(rate) * 65536.0 + 0.5;
         if (t > 65535.0) t = 65535.0;
         p.threshold16 = static_cast<uint32_t>(t);
         p.keep_scale = 1.0f / (1.0f - rate);   // Keras Dropout: kept values scaled by 1 / (1 - rate)
+        p.rate = rate;
     }
     return p;
 }

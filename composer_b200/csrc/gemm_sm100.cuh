@@ -10,8 +10,10 @@
 // them in HBM).  Tiles are 128 (M) x BN (N) x 64 (K), SWIZZLE_128B.
 //
 // Roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane),
-// warp 2 = TMEM allocator, warps 4-7 = epilogue (thread t of the epilogue owns
-// accumulator row t, i.e. TMEM lane t).
+// warp 2 = TMEM allocator, warps 4-11 = epilogue: warp w reads TMEM lane quadrant
+// w % 4 (thread = accumulator row) and takes the 32-column half (w - 4) / 4 of
+// every 64-column slab (the cross-entropy epilogue needs whole rows per thread
+// and uses warps 4-7 only).
 //
 // Reference call sites replaced (composer/models/transformer.py): Conv1D.call
 // :194-209 (c_attn :416, attn c_proj :443, c_fc/c_proj :504-505), the tied
@@ -24,7 +26,7 @@ namespace cb200 {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 384;   // 4 control warps + 8 epilogue warps
 
 enum GemmEpilogue : int {
     EPI_BIAS_BF16 = 0,      // out0 = bf16(acc + bias)
@@ -66,7 +68,7 @@ struct GemmSmem {
     static constexpr int STAGING_BYTES = GEMM_BM * 128;                 // one 64-column bf16 slab
 };
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // Byte offset of 16-byte chunk `chunk` (0..7) of row `row` inside a
 // SWIZZLE_128B tile whose rows are 128 bytes (what TMA expects to store from).
@@ -89,6 +91,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     constexpr bool USES_STAGING = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU || EPI == EPI_BIAS_DROP_RES ||
                                    EPI == EPI_MUL_DGELU);
     constexpr int NUM_OUT = (EPI == EPI_BIAS_GELU) ? 2 : 1;
+    constexpr int EPI_WARPS = (EPI == EPI_CE) ? 4 : 8;
     static_assert(BN % 16 == 0 && BN <= 512, "bad BN");
     static_assert(!(B_MN && BN > 256), "MN-major B with BN > 256 not supported");
 
@@ -122,7 +125,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         for (int s = 0; s < ACC_STAGES; ++s) {
             mbar_init(&tmem_full[s], 1);
-            mbar_init(&tmem_empty[s], 128);
+            mbar_init(&tmem_empty[s], EPI_WARPS * 32);
         }
         mbar_fence_init();
     }
@@ -218,9 +221,10 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp >= 4 && warp < 4 + EPI_WARPS) {
         // ===================== Epilogue =====================
         const int quad = warp & 3;                   // TMEM lane quadrant this warp may read
+        const int half = (warp - 4) >> 2;            // which 32 columns of each 64-column slab
         const int row_in_tile = quad * 32 + lane;
         const int epi_tid = threadIdx.x - 128;
         int acc = 0;
@@ -250,8 +254,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     // the TMA store that last read this buffer pair must have drained
                     if (epi_tid == 0) tma_store_wait_read<NUM_OUT>();
                     epi_bar_sync();
-#pragma unroll
-                    for (int half = 0; half < 2; ++half) {
+                    {
                         uint32_t v[32];
                         tmem_ld32(t_row + slab * 64 + half * 32, v);
                         tmem_ld_wait();
@@ -336,7 +339,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             } else if constexpr (EPI == EPI_ATOMIC_F32) {
                 if (has_work) {
 #pragma unroll 1
-                    for (int c = 0; c < BN; c += 32) {
+                    for (int c = half * 32; c < BN; c += 64) {
                         if (n0 + c >= args.N) break;
                         uint32_t v[32];
                         tmem_ld32(t_row + c, v);
