@@ -162,27 +162,24 @@ __host__ __device__ __forceinline__ Philox4 drop_bits_rowmajor(const DropoutPara
 // starting at 16*i16, 64 keys starting at 64*jb) of one (batch, head) pair `bh`.  In the m16n8k16
 // accumulator layout such a block is owned by 32 lanes; lane = 4*g + tig owns the 32 elements
 //     idx = 4*t + e,  t = 0..7, e = 0..3  ->  (row 16*i16 + g + 8*(e >> 1), key 64*jb + 8*t + 2*tig + (e & 1)).
-// Their keep decisions come from one LCG stream: x_0 = attn_stream_seed(...), x_{n+1} = A x_n + C, element
-// idx is kept iff x_{idx+1} >= threshold32.  The stream seed is a Philox-keyed hash of the block coordinates
-// (the key is drawn once per launch from Philox4x32-10 of (seed, step, layer)), so forward, backward and the
-// mask export regenerate identical masks with ~3 instructions per element instead of a Philox call per 8.
+// Their keep decisions come from one multiplicative congruential stream modulo 2^32:
+//     x_0 = attn_stream_seed(...) (odd),  x_{n+1} = A x_n,  element idx is kept iff x_{idx+1} >= threshold32
+// (the comparison is dominated by the high bits, the good ones of a power-of-two MCG).  The seed is a
+// Philox-keyed bijective hash of the block coordinates: the key is drawn once per launch from
+// Philox4x32-10 of (seed, step, layer), so forward, backward and the mask export regenerate identical
+// masks at 3 instructions per element (IMAD, ISETP, FSEL) instead of a Philox call per 8 elements.
 struct AttnDropKey {
     uint32_t k0, k1;
     uint32_t threshold32;   // drop when x < threshold32 ; 0 = dropout off
     float keep_scale;
 };
 
-constexpr uint32_t ATTN_LCG_A = 747796405u, ATTN_LCG_C = 2891336453u;
+constexpr uint32_t ATTN_MCG_A = 0x93D765DDu;   // Steele & Vigna (2021), good 32-bit MCG multiplier
 
-__host__ __device__ constexpr uint32_t lcg_mul_pow(int n) {
+__host__ __device__ constexpr uint32_t mcg_mul_pow(int n) {
     uint32_t a = 1;
-    for (int i = 0; i < n; ++i) a *= ATTN_LCG_A;
+    for (int i = 0; i < n; ++i) a *= ATTN_MCG_A;
     return a;
-}
-__host__ __device__ constexpr uint32_t lcg_add_pow(int n) {
-    uint32_t c = 0;
-    for (int i = 0; i < n; ++i) c = c * ATTN_LCG_A + ATTN_LCG_C;
-    return c;
 }
 
 __host__ __device__ __forceinline__ uint32_t fmix32(uint32_t h) {
@@ -190,11 +187,14 @@ __host__ __device__ __forceinline__ uint32_t fmix32(uint32_t h) {
     return h;
 }
 
-__host__ __device__ __forceinline__ uint32_t attn_stream_seed(const AttnDropKey& key, uint32_t bh, uint32_t i16,
-                                                              uint32_t jb, uint32_t lane) {
-    const uint32_t lo = (i16 << 16) ^ (jb << 5) ^ lane;   // injective for T < 2^17
-    uint32_t h = fmix32(lo ^ key.k0);
-    return fmix32(h + bh * 0x9E3779B9u + key.k1);
+// Per-(batch*head, lane) part of the seed; computed once per thread.
+__host__ __device__ __forceinline__ uint32_t attn_stream_base(const AttnDropKey& key, uint32_t bh, uint32_t lane) {
+    return fmix32(fmix32(bh ^ key.k0) + lane * 0x9E3779B9u + key.k1);
+}
+
+// (i16 < 2^13, jb < 2^11: injective for T <= 2^17); fmix32 is a bijection, so distinct blocks get distinct seeds.
+__host__ __device__ __forceinline__ uint32_t attn_stream_seed(uint32_t base, uint32_t i16, uint32_t jb) {
+    return fmix32(base ^ ((i16 << 11) | jb)) | 1u;
 }
 
 __host__ __device__ __forceinline__ AttnDropKey make_attn_drop_key(const DropoutParams& p, uint32_t layer) {
