@@ -352,6 +352,35 @@ class Transformer(BaseModel):
         self.apply_gradients(learning_rate, world)
         return loss, correct
 
+    def evaluate(self, dataset, verbose=0):
+        '''
+        Mean loss and accuracy over ``dataset`` without dropout (what the reference's
+        ``evaluate`` command asks of Keras, cli.py:606-615).  Returns ``(loss, accuracy)``.
+        '''
+
+        loss_total = torch.zeros(1, dtype=torch.float64, device=self.device)
+        correct_total = torch.zeros(1, dtype=torch.float64, device=self.device)
+        tokens = 0
+        for x, y in dataset:
+            loss_sum, correct = self.forward_loss(x, y, training=False)
+            loss_total += loss_sum.double()
+            correct_total += correct.double()
+            tokens += int(np.prod(np.shape(x)))
+        if tokens == 0:
+            return float('nan'), float('nan')
+        return float(loss_total) / tokens, float(correct_total) / tokens
+
+    def summary_lines(self):
+        '''Variable table in Keras order (the reference's ``summary`` command prints ``model.summary()``).'''
+
+        lines = ['Model: "transformer"', '%-40s %-16s %12s' % ('Variable', 'Shape', 'Param #'), '=' * 70]
+        for name in self._layout:
+            shape = self._shape_of(name)
+            lines.append('%-40s %-16s %12d' % (name, str(tuple(shape)), int(np.prod(shape))))
+        lines.append('=' * 70)
+        lines.append('Total params: {:,}'.format(self.count_params()))
+        return lines
+
     # ------------------------------------------------------------------
     # Generation (cli.py:663-676 with the model's past= semantics)
     # ------------------------------------------------------------------
