@@ -77,6 +77,8 @@ _SIGNATURES = {
     'cb200_attention_dropout_mask': (c_int, [c_ptr, c_int, c_int, c_int, c_f32, c_u64, c_u32, c_u32, c_ptr]),
     'cb200_rowmajor_dropout_mask': (c_int, [c_ptr, c_int, c_int, c_f32, c_u64, c_u32, c_u32, c_u32, c_ptr]),
     'cb200_adam': (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_ptr]),
+    'cb200_decode_linear': (c_int, [c_int, c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_int, c_int, c_int, c_int,
+                                    c_ptr]),
     'cb200_decode_attention': (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_f32, c_ptr]),
 }
 

@@ -7,6 +7,7 @@
 // place.  Sampling replaces cli.py:670-673 (logits / temperature,
 // tf.random.categorical, last position).
 #include "decode.h"
+#include "mma_sync.cuh"
 
 namespace cb200 {
 
@@ -64,34 +65,49 @@ decode_attn_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restr
     const int n_keys = pos + 1;
     const __nv_bfloat16* kb = kcache + head_base;
     const __nv_bfloat16* vb = vcache + head_base;
-    for (int key0 = warp * KPW; key0 < n_keys; key0 += 4 * KPW) {
-        const int key = key0 + lane / CH;
-        const bool valid = key < n_keys;
-        uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
-        if (valid) {
-            // the row appended above was written through the normal path: read it coherently
-            if (key == pos) {
-                kv = *reinterpret_cast<const uint4*>(kb + static_cast<size_t>(key) * D + part * 8);
-                vv = *reinterpret_cast<const uint4*>(vb + static_cast<size_t>(key) * D + part * 8);
-            } else {
-                kv = ld_nc_v4(kb + static_cast<size_t>(key) * D + part * 8);
-                vv = ld_nc_v4(vb + static_cast<size_t>(key) * D + part * 8);
+    constexpr int UNROLL = 4;            // key groups in flight per warp: 2 * UNROLL 16-byte loads per lane
+    for (int key0 = warp * KPW; key0 < n_keys; key0 += 4 * KPW * UNROLL) {
+        uint4 kv[UNROLL], vv[UNROLL];
+        bool valid[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const int key = key0 + u * 4 * KPW + lane / CH;
+            valid[u] = key < n_keys;
+            kv[u] = make_uint4(0, 0, 0, 0); vv[u] = make_uint4(0, 0, 0, 0);
+            if (valid[u]) {
+                // the row appended above was written through the normal path: read it coherently
+                if (key == pos) {
+                    kv[u] = *reinterpret_cast<const uint4*>(kb + static_cast<size_t>(key) * D + part * 8);
+                    vv[u] = *reinterpret_cast<const uint4*>(vb + static_cast<size_t>(key) * D + part * 8);
+                } else {
+                    kv[u] = ld_nc_v4(kb + static_cast<size_t>(key) * D + part * 8);
+                    vv[u] = ld_nc_v4(vb + static_cast<size_t>(key) * D + part * 8);
+                }
             }
         }
-        float s = dot8(kv, q);
+        float sc[UNROLL];
+        float mn = m;
 #pragma unroll
-        for (int o = 1; o < CH; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        s = valid ? s * scale_log2 : -INFINITY;
-        const float mn = fmaxf(m, s);
+        for (int u = 0; u < UNROLL; ++u) {
+            float s = dot8(kv[u], q);
+#pragma unroll
+            for (int o = 1; o < CH; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            sc[u] = valid[u] ? s * scale_log2 : -INFINITY;
+            mn = fmaxf(mn, sc[u]);
+        }
         if (mn != -INFINITY) {
             const float corr = fast_exp2(m - mn);
-            const float p = fast_exp2(s - mn);
-            l = l * corr + p;
-            const float2 v0 = unpack_bf16(vv.x), v1 = unpack_bf16(vv.y), v2 = unpack_bf16(vv.z), v3 = unpack_bf16(vv.w);
-            acc[0] = acc[0] * corr + p * v0.x; acc[1] = acc[1] * corr + p * v0.y;
-            acc[2] = acc[2] * corr + p * v1.x; acc[3] = acc[3] * corr + p * v1.y;
-            acc[4] = acc[4] * corr + p * v2.x; acc[5] = acc[5] * corr + p * v2.y;
-            acc[6] = acc[6] * corr + p * v3.x; acc[7] = acc[7] * corr + p * v3.y;
+            l *= corr;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] *= corr;
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const float p = fast_exp2(sc[u] - mn);
+                l += p;
+                const float2 v0 = unpack_bf16(vv[u].x), v1 = unpack_bf16(vv[u].y), v2 = unpack_bf16(vv[u].z), v3 = unpack_bf16(vv[u].w);
+                acc[0] += p * v0.x; acc[1] += p * v0.y; acc[2] += p * v1.x; acc[3] += p * v1.y;
+                acc[4] += p * v2.x; acc[5] += p * v2.y; acc[6] += p * v3.x; acc[7] += p * v3.y;
+            }
             m = mn;
         }
     }
@@ -177,13 +193,86 @@ int decode_embed(const int32_t* cur, const float* wte, const float* wpe, __nv_bf
     return 0;
 }
 
-// Fused temperature scale + softmax + multinomial draw (one warp per sequence).
-// u ~ U[0,1) from Philox4x32-10 keyed by (seed, global sequence index, step), so
-// the tokens do not depend on how sequences are sharded over GPUs.  The draw is
-// the inverse CDF in vocabulary order.  temperature <= 0 selects argmax (first
-// maximum).  When `forced` is non-null and forced[b*forced_ld + step] >= 0 that
-// id is emitted instead (prompt teacher-forcing).  The last warp to finish
-// advances the position counter for the next graph replay.
+// Temperature scale + softmax + multinomial draw for one sequence, executed by one warp on a row of
+// logits `z` (global or shared memory).  u ~ U[0,1) from Philox4x32-10 keyed by (seed, global sequence
+// index, step), so the tokens do not depend on how sequences are sharded over GPUs.  The draw is the
+// inverse CDF in vocabulary order.  greedy selects argmax (first maximum).
+__device__ __forceinline__ int sample_row(const float* z, int V, float inv_temperature, int greedy, uint32_t seed_lo,
+                                          uint32_t seed_hi, uint32_t seq_index, uint32_t step, int lane, float* u_used) {
+    float vmax = -INFINITY;
+    int amax = 0x7fffffff;
+    for (int c = lane; c < V; c += 32) {
+        const float v = z[c];
+        if (v > vmax) { vmax = v; amax = c; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float v2 = __shfl_xor_sync(0xffffffffu, vmax, o);
+        const int a2 = __shfl_xor_sync(0xffffffffu, amax, o);
+        if (v2 > vmax || (v2 == vmax && a2 < amax)) { vmax = v2; amax = a2; }
+    }
+    int chosen = amax;
+    float u = 0.f;
+    if (!greedy) {
+        const float kLog2e = 1.4426950408889634f;
+        const float c = inv_temperature * kLog2e;
+        // lane owns the contiguous slice [lo, hi) so that the CDF is in vocabulary order
+        const int per = (V + 31) / 32;
+        const int lo = lane * per, hi = min(V, lo + per);
+        float mass = 0.f;
+        for (int i = lo; i < hi; ++i) mass += exp2f((z[i] - vmax) * c);
+        float prefix = mass;   // inclusive scan over lanes
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float t = __shfl_up_sync(0xffffffffu, prefix, o);
+            if (lane >= o) prefix += t;
+        }
+        const float total = __shfl_sync(0xffffffffu, prefix, 31);
+        const Philox4 r = philox4x32_10(step, seq_index, 0x5A17u, 0u, seed_lo, seed_hi);
+        u = (r.x >> 8) * (1.0f / 16777216.0f);          // 24-bit uniform in [0, 1)
+        const float target = u * total;
+        // the lane whose slice [prefix - mass, prefix) contains the target resolves the id
+        const float before = prefix - mass;
+        const bool mine = (target >= before && target < prefix) || (lane == 31 && target >= prefix);
+        int pick = -1;
+        if (mine) {
+            float run = before;
+            pick = max(hi - 1, lo);
+            for (int i = lo; i < hi; ++i) {
+                run += exp2f((z[i] - vmax) * c);
+                if (target < run) { pick = i; break; }
+            }
+            if (pick >= V) pick = V - 1;
+        }
+        // lowest lane that claims wins (slices are disjoint; this only breaks float ties)
+        const uint32_t ballot = __ballot_sync(0xffffffffu, pick >= 0);
+        const int src = ballot ? (__ffs(ballot) - 1) : 0;
+        chosen = __shfl_sync(0xffffffffu, pick, src);
+        if (chosen < 0) chosen = amax;
+    }
+    *u_used = u;
+    return chosen;
+}
+
+// Advances the device-side position / step counters once per launch (last block to finish).
+__device__ __forceinline__ void advance_counters(int* pos_ptr, int* step_ptr, int step) {
+    __shared__ int block_done;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int ticket = atomicAdd(reinterpret_cast<unsigned int*>(pos_ptr + 1), 1u);
+        block_done = (ticket == gridDim.x * gridDim.y - 1);
+    }
+    __syncthreads();
+    if (block_done && threadIdx.x == 0) {
+        pos_ptr[1] = 0;          // reset the ticket
+        *pos_ptr = *pos_ptr + 1;
+        *step_ptr = step + 1;
+    }
+}
+
+// Sampling from materialised logits (one warp per sequence).  When `forced` is non-null and
+// forced[b*forced_ld + step] >= 0 that id is emitted instead (prompt teacher-forcing).
 __global__ void __launch_bounds__(128)
 sample_kernel(const float* __restrict__ logits, int ld, int V, float inv_temperature, int greedy, uint32_t seed_lo,
               uint32_t seed_hi, int seq_base, int32_t* __restrict__ out_ids, int out_ld, int32_t* __restrict__ cur,
@@ -193,59 +282,9 @@ sample_kernel(const float* __restrict__ logits, int ld, int V, float inv_tempera
     const int b = blockIdx.x * (blockDim.x >> 5) + warp;
     const int step = *step_ptr;
     if (b < B) {
-        const float* z = logits + static_cast<size_t>(b) * ld;
-        float vmax = -INFINITY;
-        int amax = 0x7fffffff;
-        for (int c = lane; c < V; c += 32) {
-            const float v = z[c];
-            if (v > vmax) { vmax = v; amax = c; }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float v2 = __shfl_xor_sync(0xffffffffu, vmax, o);
-            const int a2 = __shfl_xor_sync(0xffffffffu, amax, o);
-            if (v2 > vmax || (v2 == vmax && a2 < amax)) { vmax = v2; amax = a2; }
-        }
-        int chosen = amax;
-        float u = 0.f;
-        if (!greedy) {
-            const float kLog2e = 1.4426950408889634f;
-            const float c = inv_temperature * kLog2e;
-            // pass 1: total mass; lane owns the contiguous slice [lo, hi) so that the CDF is in vocabulary order
-            const int per = (V + 31) / 32;
-            const int lo = lane * per, hi = min(V, lo + per);
-            float mass = 0.f;
-            for (int i = lo; i < hi; ++i) mass += exp2f((z[i] - vmax) * c);
-            float prefix = mass;   // inclusive scan over lanes
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const float t = __shfl_up_sync(0xffffffffu, prefix, o);
-                if (lane >= o) prefix += t;
-            }
-            const float total = __shfl_sync(0xffffffffu, prefix, 31);
-            const Philox4 r = philox4x32_10(static_cast<uint32_t>(step), static_cast<uint32_t>(seq_base + b), 0x5A17u, 0u,
-                                            seed_lo, seed_hi);
-            u = (r.x >> 8) * (1.0f / 16777216.0f);          // 24-bit uniform in [0, 1)
-            const float target = u * total;
-            // the lane whose slice [prefix - mass, prefix) contains the target resolves the id
-            const float before = prefix - mass;
-            const bool mine = (target >= before && target < prefix) || (lane == 31 && target >= prefix);
-            int pick = -1;
-            if (mine) {
-                float run = before;
-                pick = max(hi - 1, lo);
-                for (int i = lo; i < hi; ++i) {
-                    run += exp2f((z[i] - vmax) * c);
-                    if (target < run) { pick = i; break; }
-                }
-                if (pick >= V) pick = V - 1;
-            }
-            // lowest lane that claims wins (slices are disjoint; this only breaks float ties)
-            const uint32_t ballot = __ballot_sync(0xffffffffu, pick >= 0);
-            const int src = ballot ? (__ffs(ballot) - 1) : 0;
-            chosen = __shfl_sync(0xffffffffu, pick, src);
-            if (chosen < 0) chosen = amax;
-        }
+        float u;
+        int chosen = sample_row(logits + static_cast<size_t>(b) * ld, V, inv_temperature, greedy, seed_lo, seed_hi,
+                                static_cast<uint32_t>(seq_base + b), static_cast<uint32_t>(step), lane, &u);
         if (forced != nullptr) {
             const int f = forced[static_cast<size_t>(b) * forced_ld + step];
             if (f >= 0) chosen = f;
@@ -256,20 +295,109 @@ sample_kernel(const float* __restrict__ logits, int ld, int V, float inv_tempera
             if (u_out != nullptr) u_out[static_cast<size_t>(b) * out_ld + step] = u;
         }
     }
-    // advance the device-side counters once per launch
-    __shared__ int block_done;
+    advance_counters(pos_ptr, step_ptr, step);
+}
+
+// ln_f + tied logits + sampling for one decode step, one CTA (4 warps) per sequence: the final hidden
+// row is normalised in shared memory, every warp takes vocabulary rows v = warp, warp + 4, ... (a lane
+// reads 16 contiguous bytes of wte[v], so a warp load covers 512 contiguous bytes), the 390 logits stay
+// in shared memory and warp 0 draws the token.  Replaces LayerNorm + logits GEMM + sampler launches.
+// Reference: transformer.py:811, :818 (tied logits) and cli.py:670-673.
+template <int VPL>   // 8-element vectors per lane over E: E = 256 * VPL
+__global__ void __launch_bounds__(128)
+logits_sample_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, float eps, const __nv_bfloat16* __restrict__ wte, int V,
+                     float inv_temperature, int greedy, uint32_t seed_lo, uint32_t seed_hi, int seq_base,
+                     int32_t* __restrict__ out_ids, int out_ld, int32_t* __restrict__ cur,
+                     const int32_t* __restrict__ forced, int forced_ld, int* __restrict__ pos_ptr,
+                     int* __restrict__ step_ptr, float* __restrict__ u_out, float* __restrict__ logits_out) {
+    constexpr int E = 256 * VPL;
+    __shared__ float sh[E];
+    __shared__ float sz[512];
+    __shared__ float sred[8];
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int step = *step_ptr;
+    // ---- ln_f over the row (each thread 2 * VPL elements) ----
+    float v[2 * VPL];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 2 * VPL; ++i) {
+        v[i] = __bfloat162float(x[static_cast<size_t>(b) * E + i * 128 + tid]);
+        sum += v[i];
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) sred[warp] = sum;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        const unsigned int ticket = atomicAdd(reinterpret_cast<unsigned int*>(pos_ptr + 1), 1u);
-        block_done = (ticket == gridDim.x - 1);
+    const float mean = (sred[0] + sred[1] + sred[2] + sred[3]) / E;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < 2 * VPL; ++i) { const float d = v[i] - mean; sq += d * d; }
+    sq = warp_sum(sq);
+    if (lane == 0) sred[4 + warp] = sq;
+    __syncthreads();
+    const float rstd = rsqrtf((sred[4] + sred[5] + sred[6] + sred[7]) / E + eps);
+#pragma unroll
+    for (int i = 0; i < 2 * VPL; ++i) {
+        const int c = i * 128 + tid;
+        // the training path rounds ln_f's output to bf16 before the logits GEMM; do the same
+        sh[c] = __bfloat162float(__float2bfloat16_rn((v[i] - mean) * rstd * gamma[c] + beta[c]));
     }
     __syncthreads();
-    if (block_done && threadIdx.x == 0) {
-        pos_ptr[1] = 0;          // reset the ticket
-        *pos_ptr = *pos_ptr + 1;
-        *step_ptr = step + 1;
+    // ---- logits: warp per vocabulary row ----
+    float hreg[VPL][8];
+#pragma unroll
+    for (int k = 0; k < VPL; ++k)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) hreg[k][e] = sh[(k * 32 + lane) * 8 + e];
+    for (int row = warp; row < V; row += 4) {
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+            const uint4 w = __ldg(reinterpret_cast<const uint4*>(wte + static_cast<size_t>(row) * E + (k * 32 + lane) * 8));
+            acc += dot8(w, hreg[k]);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) sz[row] = acc;
     }
+    __syncthreads();
+    if (logits_out != nullptr)
+        for (int c = tid; c < V; c += 128) logits_out[static_cast<size_t>(b) * V + c] = sz[c];
+    if (warp == 0) {
+        float u;
+        int chosen = sample_row(sz, V, inv_temperature, greedy, seed_lo, seed_hi, static_cast<uint32_t>(seq_base + b),
+                                static_cast<uint32_t>(step), lane, &u);
+        if (forced != nullptr) {
+            const int f = forced[static_cast<size_t>(b) * forced_ld + step];
+            if (f >= 0) chosen = f;
+        }
+        if (lane == 0) {
+            out_ids[static_cast<size_t>(b) * out_ld + step] = chosen;
+            cur[b] = chosen;
+            if (u_out != nullptr) u_out[static_cast<size_t>(b) * out_ld + step] = u;
+        }
+    }
+    advance_counters(pos_ptr, step_ptr, step);
+}
+
+int logits_sample(const __nv_bfloat16* x, const float* gamma, const float* beta, float eps, const __nv_bfloat16* wte,
+                  int E, int V, float temperature, uint64_t seed, int seq_base, int32_t* out_ids, int out_ld,
+                  int32_t* cur, const int32_t* forced, int forced_ld, int* pos_ptr, int* step_ptr, float* u_out,
+                  float* logits_out, int B, cudaStream_t s) {
+    if (B == 0) return 0;
+    CB200_REQUIRE(V <= 512 && E % 256 == 0 && E <= 1024, "logits_sample supports vocab <= 512 and E in {256, 512, 768, 1024}");
+    const int greedy = temperature <= 0.f ? 1 : 0;
+    const float inv_t = greedy ? 1.f : 1.0f / temperature;
+    const uint32_t lo = static_cast<uint32_t>(seed), hi = static_cast<uint32_t>(seed >> 32);
+    switch (E / 256) {
+        case 1: logits_sample_kernel<1><<<B, 128, 0, s>>>(x, gamma, beta, eps, wte, V, inv_t, greedy, lo, hi, seq_base, out_ids, out_ld, cur, forced, forced_ld, pos_ptr, step_ptr, u_out, logits_out); break;
+        case 2: logits_sample_kernel<2><<<B, 128, 0, s>>>(x, gamma, beta, eps, wte, V, inv_t, greedy, lo, hi, seq_base, out_ids, out_ld, cur, forced, forced_ld, pos_ptr, step_ptr, u_out, logits_out); break;
+        case 3: logits_sample_kernel<3><<<B, 128, 0, s>>>(x, gamma, beta, eps, wte, V, inv_t, greedy, lo, hi, seq_base, out_ids, out_ld, cur, forced, forced_ld, pos_ptr, step_ptr, u_out, logits_out); break;
+        default: logits_sample_kernel<4><<<B, 128, 0, s>>>(x, gamma, beta, eps, wte, V, inv_t, greedy, lo, hi, seq_base, out_ids, out_ld, cur, forced, forced_ld, pos_ptr, step_ptr, u_out, logits_out); break;
+    }
+    CB200_CUDA_OK(cudaGetLastError());
+    note_launch(1);
+    return 0;
 }
 
 int sample_tokens(const float* logits, int ld, int V, float temperature, uint64_t seed, int seq_base, int32_t* out_ids,
@@ -284,6 +412,148 @@ int sample_tokens(const float* logits, int ld, int V, float temperature, uint64_
     CB200_CUDA_OK(cudaGetLastError());
     note_launch(1);
     return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Skinny linear layer for decoding: Y[B, N] = X[B, K] W + b with B <= a few
+// hundred rows.  The persistent tcgen05 GEMM tiles 128 x 256 outputs per CTA,
+// which leaves 2-8 CTAs busy at these sizes; here a CTA owns 128 rows x NB (16
+// or 32) output columns, so a layer spreads over N/NB x ceil(B/128) CTAs (48-64
+// for c_attn / c_fc), streams K in 64-wide chunks through a 3-stage cp.async
+// pipeline and uses mma.sync (weights are L2-resident: the step is latency-,
+// not FLOP-bound).  W is the [N, K] ("out, in") bf16 shadow.
+// Epilogues: 0 bias, 1 bias + gelu, 2 bias + residual.
+// ---------------------------------------------------------------------------
+constexpr int DL_THREADS = 256;
+constexpr int DL_STAGES = 3;
+
+__device__ __forceinline__ uint32_t dl_tile_off(int row, int chunk) {   // rows of 64 bf16 = 128 bytes, 8 chunks
+    return static_cast<uint32_t>(row * 128 + ((chunk ^ (row & 7)) << 4));
+}
+
+template <int NB, int EPI>
+__global__ void __launch_bounds__(DL_THREADS)
+decode_linear_kernel(const __nv_bfloat16* __restrict__ X, int ldx, const __nv_bfloat16* __restrict__ Wt,
+                     const float* __restrict__ bias, const __nv_bfloat16* __restrict__ res, int ldres,
+                     __nv_bfloat16* __restrict__ Y, int ldy, int B, int N, int K) {
+    constexpr int X_BYTES = 128 * 128;          // 128 rows x 64 k
+    constexpr int W_BYTES = NB * 128;
+    constexpr int STAGE = X_BYTES + W_BYTES;
+    extern __shared__ __align__(128) uint8_t dl_smem[];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int g = lane >> 2, tig = lane & 3;
+    const int n0 = blockIdx.x * NB, r0 = blockIdx.y * 128;
+    const int kchunks = K / 64;
+
+    auto issue = [&](int kc, int stage) {
+        const uint32_t sx = smem_u32(dl_smem + stage * STAGE), sw = sx + X_BYTES;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {           // 128 rows x 8 chunks / 256 threads
+            const int idx = tid + c * DL_THREADS;
+            const int r = idx >> 3, ch = idx & 7;
+            const bool ok = (r0 + r) < B;
+            cp_async_16(sx + dl_tile_off(r, ch), X + static_cast<size_t>(ok ? r0 + r : 0) * ldx + kc * 64 + ch * 8, ok);
+        }
+        if (tid < NB * 8) {
+            const int r = tid >> 3, ch = tid & 7;
+            const bool ok = (n0 + r) < N;
+            cp_async_16(sw + dl_tile_off(r, ch), Wt + static_cast<size_t>(ok ? n0 + r : 0) * K + kc * 64 + ch * 8, ok);
+        }
+    };
+
+    float acc[NB / 8][4];
+#pragma unroll
+    for (int t = 0; t < NB / 8; ++t) { acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f; }
+
+#pragma unroll
+    for (int s = 0; s < DL_STAGES - 1; ++s) {
+        if (s < kchunks) issue(s, s);
+        cp_async_commit();
+    }
+    const int a_row = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, a_chunk = lane >> 4;
+    const int b_row = ((lane >> 4) << 3) + (lane & 7), b_chunk = (lane >> 3) & 1;
+    for (int kc = 0; kc < kchunks; ++kc) {
+        cp_async_wait<DL_STAGES - 2>();
+        __syncthreads();
+        if (kc + DL_STAGES - 1 < kchunks) issue(kc + DL_STAGES - 1, (kc + DL_STAGES - 1) % DL_STAGES);
+        cp_async_commit();
+        const uint32_t sx = smem_u32(dl_smem + (kc % DL_STAGES) * STAGE), sw = sx + X_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            uint32_t af[4];
+            ldmatrix_x4(af, sx + dl_tile_off(a_row, ks * 2 + a_chunk));
+#pragma unroll
+            for (int tp = 0; tp < NB / 16; ++tp) {
+                uint32_t bf[4];
+                ldmatrix_x4(bf, sw + dl_tile_off(tp * 16 + b_row, ks * 2 + b_chunk));
+                mma_bf16_16816(acc[2 * tp], af, bf[0], bf[1]);
+                mma_bf16_16816(acc[2 * tp + 1], af, bf[2], bf[3]);
+            }
+        }
+    }
+    // ---- epilogue ----
+    const int row_lo = r0 + warp * 16 + g, row_hi = row_lo + 8;
+#pragma unroll
+    for (int t = 0; t < NB / 8; ++t) {
+        const int col = n0 + t * 8 + 2 * tig;
+        if (col >= N) continue;
+        const float b0 = bias ? bias[col] : 0.f, b1 = bias ? bias[col + 1] : 0.f;
+        float v[4] = {acc[t][0] + b0, acc[t][1] + b1, acc[t][2] + b0, acc[t][3] + b1};
+        if (EPI == 1) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] = gelu_tanh(v[e]);
+        }
+        if (EPI == 2) {
+            if (row_lo < B) {
+                const float2 r = unpack_bf16(*reinterpret_cast<const uint32_t*>(res + static_cast<size_t>(row_lo) * ldres + col));
+                v[0] += r.x; v[1] += r.y;
+            }
+            if (row_hi < B) {
+                const float2 r = unpack_bf16(*reinterpret_cast<const uint32_t*>(res + static_cast<size_t>(row_hi) * ldres + col));
+                v[2] += r.x; v[3] += r.y;
+            }
+        }
+        if (row_lo < B) *reinterpret_cast<uint32_t*>(Y + static_cast<size_t>(row_lo) * ldy + col) = pack_bf16(v[0], v[1]);
+        if (row_hi < B) *reinterpret_cast<uint32_t*>(Y + static_cast<size_t>(row_hi) * ldy + col) = pack_bf16(v[2], v[3]);
+    }
+}
+
+template <int NB, int EPI>
+static int launch_decode_linear(const __nv_bfloat16* X, int ldx, const __nv_bfloat16* Wt, const float* bias,
+                                const __nv_bfloat16* res, int ldres, __nv_bfloat16* Y, int ldy, int B, int N, int K,
+                                cudaStream_t s) {
+    constexpr size_t smem = DL_STAGES * (128 * 128 + NB * 128);
+    auto kernel = decode_linear_kernel<NB, EPI>;
+    static bool configured = false;
+    if (!configured) {
+        CB200_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    dim3 grid((N + NB - 1) / NB, (B + 127) / 128);
+    kernel<<<grid, DL_THREADS, smem, s>>>(X, ldx, Wt, bias, res, ldres, Y, ldy, B, N, K);
+    CB200_CUDA_OK(cudaGetLastError());
+    note_launch(1);
+    return 0;
+}
+
+int decode_linear(int epilogue, const __nv_bfloat16* X, int ldx, const __nv_bfloat16* Wt, const float* bias,
+                  const __nv_bfloat16* res, int ldres, __nv_bfloat16* Y, int ldy, int B, int N, int K, cudaStream_t s) {
+    if (B == 0) return 0;
+    CB200_REQUIRE(K % 64 == 0 && N % 8 == 0, "decode_linear needs K %% 64 == 0 and N %% 8 == 0");
+    CB200_REQUIRE(epilogue != 2 || res != nullptr, "residual epilogue needs a residual");
+    const bool narrow = N <= 512;    // spread small layers over more CTAs
+    switch (epilogue) {
+        case 0: return narrow ? launch_decode_linear<16, 0>(X, ldx, Wt, bias, res, ldres, Y, ldy, B, N, K, s)
+                              : launch_decode_linear<32, 0>(X, ldx, Wt, bias, res, ldres, Y, ldy, B, N, K, s);
+        case 1: return narrow ? launch_decode_linear<16, 1>(X, ldx, Wt, bias, res, ldres, Y, ldy, B, N, K, s)
+                              : launch_decode_linear<32, 1>(X, ldx, Wt, bias, res, ldres, Y, ldy, B, N, K, s);
+        case 2: return narrow ? launch_decode_linear<16, 2>(X, ldx, Wt, bias, res, ldres, Y, ldy, B, N, K, s)
+                              : launch_decode_linear<32, 2>(X, ldx, Wt, bias, res, ldres, Y, ldy, B, N, K, s);
+        default: break;
+    }
+    set_error("unknown decode_linear epilogue %d", epilogue);
+    return -1;
 }
 
 }  // namespace cb200

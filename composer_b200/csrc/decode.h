@@ -16,4 +16,13 @@ int sample_tokens(const float* logits, int ld, int V, float temperature, uint64_
                   int out_ld, int32_t* cur, const int32_t* forced, int forced_ld, int* pos_ptr, int* step_ptr,
                   float* u_out, int B, cudaStream_t s);
 
+// ln_f + tied logits + sampling fused (one CTA per sequence); logits_out (fp32 [B, V]) may be null.
+int logits_sample(const __nv_bfloat16* x, const float* gamma, const float* beta, float eps, const __nv_bfloat16* wte,
+                  int E, int V, float temperature, uint64_t seed, int seq_base, int32_t* out_ids, int out_ld,
+                  int32_t* cur, const int32_t* forced, int forced_ld, int* pos_ptr, int* step_ptr, float* u_out,
+                  float* logits_out, int B, cudaStream_t s);
+// Y[B, N] = X[B, K] Wt^T + bias ; epilogue 0 bias, 1 bias + gelu, 2 bias + residual.  Wt is [N, K] bf16.
+int decode_linear(int epilogue, const __nv_bfloat16* X, int ldx, const __nv_bfloat16* Wt, const float* bias,
+                  const __nv_bfloat16* res, int ldres, __nv_bfloat16* Y, int ldy, int B, int N, int K, cudaStream_t s);
+
 }  // namespace cb200

@@ -508,7 +508,6 @@ static int decode_step(Engine& e, DecodeBuffers& d, bf16* cache, int t_max, int 
     const float* P = e.params;
     const bf16* S = e.shadow;
     const float att_scale = e.cfg.scale_attention ? 1.0f / sqrtf(static_cast<float>(e.D)) : 1.0f;
-    DropoutParams off = make_dropout(0.f, 0, 0, false);
     const int64_t layer_stride = 2ll * B * e.H * t_max * e.D;
     int rc;
     if ((rc = decode_embed(d.cur, P + e.lay.wte, P + e.lay.wpe, d.x, d.state, B, E, e.V, s))) return rc;
@@ -521,44 +520,26 @@ static int decode_step(Engine& e, DecodeBuffers& d, bf16* cache, int t_max, int 
             if ((rc = layernorm_fwd(x_in, P + o.ln1_g, P + o.ln1_b, d.x1, d.stats, B, E, e.cfg.layer_normalization_epsilon, s))) return rc;
             x1 = d.x1;
         }
-        {
-            GemmDesc g = gemm_desc(GEMM_BIAS, B, 3 * E, E, x1, E, S + e.shT_attn[l], E);
-            g.bias = P + o.attn_b; g.out0 = d.qkv; g.ld_out0 = 3 * E;
-            if ((rc = gemm_launch(g, s))) return rc;
-        }
+        // c_attn, in-place cache append + attention, c_proj + residual
+        if ((rc = decode_linear(0, x1, E, S + e.shT_attn[l], P + o.attn_b, nullptr, 0, d.qkv, 3 * E, B, 3 * E, E, s))) return rc;
         bf16* kc = cache + l * layer_stride;
         bf16* vc = kc + layer_stride / 2;
         if ((rc = decode_attention(d.qkv, kc, vc, d.att, d.state, B, e.H, e.D, t_max, att_scale, s))) return rc;
-        {
-            GemmDesc g = gemm_desc(GEMM_BIAS_DROP_RES, B, E, E, d.att, E, S + e.shT_proj[l], E);
-            g.bias = P + o.proj_b; g.out0 = d.x2; g.ld_out0 = E; g.aux = x1; g.ld_aux = E; g.drop = off;
-            if ((rc = gemm_launch(g, s))) return rc;
-        }
+        if ((rc = decode_linear(2, d.att, E, S + e.shT_proj[l], P + o.proj_b, x1, E, d.x2, E, B, E, E, s))) return rc;
         const bf16* mln = d.x2;
         if (e.cfg.use_layer_normalization) {
             if ((rc = layernorm_fwd(d.x2, P + o.ln2_g, P + o.ln2_b, d.mln, d.stats, B, E, e.cfg.layer_normalization_epsilon, s))) return rc;
             mln = d.mln;
         }
-        {
-            GemmDesc g = gemm_desc(GEMM_BIAS_GELU, B, F, E, mln, E, S + e.shT_fc[l], E);
-            g.bias = P + o.fc_b; g.out0 = d.u; g.ld_out0 = F; g.out1 = d.gl; g.ld_out1 = F;
-            if ((rc = gemm_launch(g, s))) return rc;
-        }
-        {
-            GemmDesc g = gemm_desc(GEMM_BIAS_DROP_RES, B, E, F, d.gl, F, S + e.shT_proj2[l], F);
-            g.bias = P + o.proj2_b; g.out0 = x_out; g.ld_out0 = E; g.aux = d.x2; g.ld_aux = E; g.drop = off;
-            if ((rc = gemm_launch(g, s))) return rc;
-        }
+        // c_fc + gelu, mlp c_proj + residual
+        if ((rc = decode_linear(1, mln, E, S + e.shT_fc[l], P + o.fc_b, nullptr, 0, d.gl, F, B, F, E, s))) return rc;
+        if ((rc = decode_linear(2, d.gl, F, S + e.shT_proj2[l], P + o.proj2_b, d.x2, E, x_out, E, B, E, F, s))) return rc;
         bf16* t = x_in; x_in = x_out; x_out = t;
     }
-    if ((rc = layernorm_fwd(x_in, P + e.lay.lnf_g, P + e.lay.lnf_b, d.x1, d.stats, B, E, e.cfg.layer_normalization_epsilon, s))) return rc;
-    {
-        GemmDesc g = gemm_desc(GEMM_CE, B, e.V, E, d.x1, E, S + e.lay.wte, E);
-        g.outf = d.logits; g.ld_outf = e.V;
-        if ((rc = gemm_launch(g, s))) return rc;
-    }
-    return sample_tokens(d.logits, e.V, e.V, temperature, seed, static_cast<int>(seq_base), d.all_ids, steps, d.cur,
-                         d.forced, steps, d.state, d.state + 2, d.uniforms, B, s);
+    // ln_f + tied logits + sampling in one kernel
+    return logits_sample(x_in, P + e.lay.lnf_g, P + e.lay.lnf_b, e.cfg.layer_normalization_epsilon, S + e.lay.wte, E, e.V,
+                         temperature, seed, static_cast<int>(seq_base), d.all_ids, steps, d.cur, d.forced, steps,
+                         d.state, d.state + 2, d.uniforms, d.logits, B, s);
 }
 
 static int generate_on(Engine& e, bf16* cache, int t_max, uint8_t* ws, int64_t ws_bytes, const int32_t* prompt, int B,
@@ -906,6 +887,13 @@ int cb200_decode_attention(const void* qkv, void* kcache, void* vcache, void* ou
                            int D, int t_max, float scale, void* stream) {
     return decode_attention(static_cast<const bf16*>(qkv), static_cast<bf16*>(kcache), static_cast<bf16*>(vcache),
                             static_cast<bf16*>(out), pos, B, H, D, t_max, scale, static_cast<cudaStream_t>(stream));
+}
+
+int cb200_decode_linear(int epilogue, const void* X, int ldx, const void* Wt, const float* bias, const void* res,
+                        int ldres, void* Y, int ldy, int B, int N, int K, void* stream) {
+    return decode_linear(epilogue, static_cast<const bf16*>(X), ldx, static_cast<const bf16*>(Wt), bias,
+                         static_cast<const bf16*>(res), ldres, static_cast<bf16*>(Y), ldy, B, N, K,
+                         static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -158,6 +158,11 @@ int cb200_adam(float* p, const float* g, float* m, float* v, void* shadow, int64
 int cb200_decode_attention(const void* qkv, void* kcache, void* vcache, void* out, const int32_t* pos, int B, int H,
                            int D, int t_max, float scale, void* stream);
 
+/* Skinny linear layer of the decode step: Y[B, N] = X[B, K] Wt^T + bias, Wt stored [N, K] (bf16).
+ * epilogue: 0 bias, 1 bias + gelu, 2 bias + residual (res [B, ldres]). */
+int cb200_decode_linear(int epilogue, const void* X, int ldx, const void* Wt, const float* bias, const void* res,
+                        int ldres, void* Y, int ldy, int B, int N, int K, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

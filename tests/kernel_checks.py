@@ -363,6 +363,22 @@ def check_decode_attention(B=3, H=16, D=16, t_max=96, pos=70):
                     _stats('decode v append', vc2.reshape(-1, D), vr.reshape(-1, D), 0.0, scale=1.0)])
 
 
+def check_decode_linear(B=37, N=768, K=256, epilogue=0, seed=81):
+    x = _randn(B, K, seed=seed)
+    w = _randn(N, K, scale=0.05, seed=seed + 1)          # stored [N, K]
+    bias = _randn(N, dtype=torch.float32, seed=seed + 2)
+    res = _randn(B, N, seed=seed + 3)
+    y = torch.full((B, N), float('nan'), dtype=torch.bfloat16, device=DEV)
+    _lib.call('cb200_decode_linear', epilogue, ptr(x), K, ptr(w), ptr(bias), ptr(res), N, ptr(y), N, B, N, K, stream())
+    torch.cuda.synchronize()
+    ref = x.float() @ w.float().t() + bias
+    if epilogue == 1:
+        ref = 0.5 * ref * (1 + torch.tanh(math.sqrt(2 / math.pi) * (ref + 0.044715 * ref ** 3)))
+    if epilogue == 2:
+        ref = ref + res.float()
+    return _finish(_stats('decode_linear B%d N%d K%d epi%d' % (B, N, K, epilogue), y, ref, 1e-2))
+
+
 GROUPS = {
     'gemm_basic': [lambda: check_gemm_bias(128, 256, 64), lambda: check_gemm_bias(256, 768, 256),
                    lambda: check_gemm_bias(300, 768, 256), lambda: check_gemm_bias(4096, 256, 1024),
@@ -383,6 +399,9 @@ GROUPS = {
     'attention_bwd': [lambda: check_attention(1, 64, 2, 16), lambda: check_attention(2, 200, 16, 16),
                       lambda: check_attention(1, 256, 4, 64), lambda: check_attention(1, 192, 4, 32),
                       lambda: check_attention(2, 200, 16, 16, rate=0.1)],
+    'decode_linear': [check_decode_linear, lambda: check_decode_linear(256, 1024, 256, 1),
+                      lambda: check_decode_linear(130, 256, 1024, 2), lambda: check_decode_linear(1, 256, 256, 2),
+                      lambda: check_decode_linear(32, 3072, 1024, 0)],
     'decode': [check_decode_attention, lambda: check_decode_attention(2, 4, 64, 300, 299),
                lambda: check_decode_attention(2, 16, 16, 64, 0)],
 }
