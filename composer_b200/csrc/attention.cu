@@ -320,8 +320,8 @@ attn_bwd_delta_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat1
 // With dropout (keep mask M, keep scale ks): dV = ks * (M.P)^T dO,
 // dS = ks * P.(M.dP - delta/ks); the ks factors are applied once at the end.
 // ---------------------------------------------------------------------------
-template <int D, int BC, int MW, bool DROP>
-__global__ void __launch_bounds__(ATT_THREADS, (D == 16) ? 3 : 1)
+template <int D, int BC, int MW, bool DROP, int MINB>
+__global__ void __launch_bounds__(ATT_THREADS, MINB)
 attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
                 const float* __restrict__ lse, const float* __restrict__ delta, float* __restrict__ dq_acc,
                 __nv_bfloat16* __restrict__ dqkv, int T, int H, float scale, float scale_log2, AttnDropKey drop) {
@@ -628,13 +628,13 @@ int attention_fwd(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse, int 
     return 0;
 }
 
-template <int D, int BC, int MW, bool DROP>
+template <int D, int BC, int MW, bool DROP, int MINB>
 static int launch_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* dout, const float* lse, const float* delta,
                       float* dq_acc, __nv_bfloat16* dqkv, int B, int T, int H, float scale, const AttnDropKey& key,
                       cudaStream_t s) {
     constexpr int BR = 64 * MW;
     constexpr size_t smem = 2 * BC * D * 2 + 4 * BR * D * 2 + 4 * BR * sizeof(float) + 2 * BC * D * sizeof(float);
-    auto kernel = attn_bwd_kernel<D, BC, MW, DROP>;
+    auto kernel = attn_bwd_kernel<D, BC, MW, DROP, MINB>;
     static bool configured = false;
     if (!configured) {
         CB200_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -647,12 +647,12 @@ static int launch_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* dout, const
     return 0;
 }
 
-template <int D, int BC, int MW>
+template <int D, int BC, int MW, int MINB>
 static int launch_bwd_drop(bool dropping, const __nv_bfloat16* qkv, const __nv_bfloat16* dout, const float* lse,
                            const float* delta, float* dq_acc, __nv_bfloat16* dqkv, int B, int T, int H, float scale,
                            const AttnDropKey& key, cudaStream_t s) {
-    return dropping ? launch_bwd<D, BC, MW, true>(qkv, dout, lse, delta, dq_acc, dqkv, B, T, H, scale, key, s)
-                    : launch_bwd<D, BC, MW, false>(qkv, dout, lse, delta, dq_acc, dqkv, B, T, H, scale, key, s);
+    return dropping ? launch_bwd<D, BC, MW, true, MINB>(qkv, dout, lse, delta, dq_acc, dqkv, B, T, H, scale, key, s)
+                    : launch_bwd<D, BC, MW, false, MINB>(qkv, dout, lse, delta, dq_acc, dqkv, B, T, H, scale, key, s);
 }
 
 int attention_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* out, const __nv_bfloat16* dout, const float* lse,
@@ -667,15 +667,15 @@ int attention_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* out, const __nv
     switch (D) {
         case 16:
             attn_bwd_delta_kernel<16><<<(rows + 7) / 8, 256, 0, s>>>(dout, out, delta, rows, T, H);
-            rc = launch_bwd_drop<16, 64, 2>(dropping, qkv, dout, lse, delta, dq_acc, dqkv, B, T, H, scale, key, s);
+            rc = launch_bwd_drop<16, 64, 2, 4>(dropping, qkv, dout, lse, delta, dq_acc, dqkv, B, T, H, scale, key, s);
             break;
         case 32:
             attn_bwd_delta_kernel<32><<<(rows + 7) / 8, 256, 0, s>>>(dout, out, delta, rows, T, H);
-            rc = launch_bwd_drop<32, 32, 1>(dropping, qkv, dout, lse, delta, dq_acc, dqkv, B, T, H, scale, key, s);
+            rc = launch_bwd_drop<32, 32, 1, 1>(dropping, qkv, dout, lse, delta, dq_acc, dqkv, B, T, H, scale, key, s);
             break;
         case 64:
             attn_bwd_delta_kernel<64><<<(rows + 7) / 8, 256, 0, s>>>(dout, out, delta, rows, T, H);
-            rc = launch_bwd_drop<64, 32, 1>(dropping, qkv, dout, lse, delta, dq_acc, dqkv, B, T, H, scale, key, s);
+            rc = launch_bwd_drop<64, 32, 1, 1>(dropping, qkv, dout, lse, delta, dq_acc, dqkv, B, T, H, scale, key, s);
             break;
         default: set_error("attention head size %d is not supported (16, 32 or 64)", D); return -1;
     }

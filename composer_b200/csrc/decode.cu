@@ -350,15 +350,24 @@ logits_sample_kernel(const __nv_bfloat16* __restrict__ x, const float* __restric
     for (int k = 0; k < VPL; ++k)
 #pragma unroll
         for (int e = 0; e < 8; ++e) hreg[k][e] = sh[(k * 32 + lane) * 8 + e];
-    for (int row = warp; row < V; row += 4) {
-        float acc = 0.f;
+    constexpr int RU = 4;     // vocabulary rows in flight per warp (the loop is L2-latency bound otherwise)
+    for (int row0 = warp; row0 < V; row0 += 4 * RU) {
+        uint4 w[RU][VPL];
 #pragma unroll
-        for (int k = 0; k < VPL; ++k) {
-            const uint4 w = __ldg(reinterpret_cast<const uint4*>(wte + static_cast<size_t>(row) * E + (k * 32 + lane) * 8));
-            acc += dot8(w, hreg[k]);
+        for (int r = 0; r < RU; ++r) {
+            const int row = min(row0 + 4 * r, V - 1);
+#pragma unroll
+            for (int k = 0; k < VPL; ++k)
+                w[r][k] = __ldg(reinterpret_cast<const uint4*>(wte + static_cast<size_t>(row) * E + (k * 32 + lane) * 8));
         }
-        acc = warp_sum(acc);
-        if (lane == 0) sz[row] = acc;
+#pragma unroll
+        for (int r = 0; r < RU; ++r) {
+            float acc = 0.f;
+#pragma unroll
+            for (int k = 0; k < VPL; ++k) acc += dot8(w[r][k], hreg[k]);
+            acc = warp_sum(acc);
+            if (lane == 0 && row0 + 4 * r < V) sz[row0 + 4 * r] = acc;
+        }
     }
     __syncthreads();
     if (logits_out != nullptr)
