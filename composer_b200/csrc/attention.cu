@@ -600,6 +600,9 @@ attn_dq_store_kernel(float* __restrict__ dq_acc, __nv_bfloat16* __restrict__ dqk
 // ---------------------------------------------------------------------------
 // Host launchers
 // ---------------------------------------------------------------------------
+static int g_attention_bwd_impl = 0;
+void attention_set_bwd_impl(int impl) { g_attention_bwd_impl = impl; }
+
 static const float kLog2e = 1.4426950408889634f;
 
 template <int D, int MW>
@@ -664,20 +667,21 @@ int attention_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* out, const __nv
     const AttnDropKey key = make_attn_drop_key(drop, layer);
     const bool dropping = key.threshold32 != 0;
     int rc = 0;
+    const bool use_tc = g_attention_bwd_impl == 0;   // 0: tcgen05 / TMEM (default), 1: warp-level mma.sync
     switch (D) {
-        case 16:
-            attn_bwd_delta_kernel<16><<<(rows + 7) / 8, 256, 0, s>>>(dout, out, delta, rows, T, H);
-            rc = launch_bwd_drop<16, 64, 2, 4>(dropping, qkv, dout, lse, delta, dq_acc, dqkv, B, T, H, scale, key, s);
-            break;
-        case 32:
-            attn_bwd_delta_kernel<32><<<(rows + 7) / 8, 256, 0, s>>>(dout, out, delta, rows, T, H);
-            rc = launch_bwd_drop<32, 32, 1, 1>(dropping, qkv, dout, lse, delta, dq_acc, dqkv, B, T, H, scale, key, s);
-            break;
-        case 64:
-            attn_bwd_delta_kernel<64><<<(rows + 7) / 8, 256, 0, s>>>(dout, out, delta, rows, T, H);
-            rc = launch_bwd_drop<64, 32, 1, 1>(dropping, qkv, dout, lse, delta, dq_acc, dqkv, B, T, H, scale, key, s);
-            break;
+        case 16: attn_bwd_delta_kernel<16><<<(rows + 7) / 8, 256, 0, s>>>(dout, out, delta, rows, T, H); break;
+        case 32: attn_bwd_delta_kernel<32><<<(rows + 7) / 8, 256, 0, s>>>(dout, out, delta, rows, T, H); break;
+        case 64: attn_bwd_delta_kernel<64><<<(rows + 7) / 8, 256, 0, s>>>(dout, out, delta, rows, T, H); break;
         default: set_error("attention head size %d is not supported (16, 32 or 64)", D); return -1;
+    }
+    if (use_tc) {
+        rc = attention_bwd_tc_main(qkv, dout, lse, delta, dq_acc, dqkv, B, T, H, D, scale, key, s);
+    } else if (D == 16) {
+        rc = launch_bwd_drop<16, 64, 2, 4>(dropping, qkv, dout, lse, delta, dq_acc, dqkv, B, T, H, scale, key, s);
+    } else if (D == 32) {
+        rc = launch_bwd_drop<32, 32, 1, 1>(dropping, qkv, dout, lse, delta, dq_acc, dqkv, B, T, H, scale, key, s);
+    } else {
+        rc = launch_bwd_drop<64, 32, 1, 1>(dropping, qkv, dout, lse, delta, dq_acc, dqkv, B, T, H, scale, key, s);
     }
     if (rc) return rc;
     CB200_CUDA_OK(cudaGetLastError());

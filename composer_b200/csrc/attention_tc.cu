@@ -1,0 +1,396 @@
+// Attention backward on the 5th-generation tensor cores (tcgen05 / TMEM).
+//
+// One CTA owns 128 keys of one (batch, head) and walks the 128-row query tiles
+// at or below the diagonal.  Per tile:
+//   S  = Q K^T, dP = dO V^T          tcgen05.mma, M 128 x N 128, accumulators in TMEM
+//   softmax warps (thread = query row, 32 columns each): P = exp2(S c - lse),
+//     causal mask, dropout, dS' = P (M.dP - delta/ks) -> bf16 -> swizzled smem
+//   dV += P^T dO, dK += dS'^T Q      the same smem tile read through an MN-major
+//   dQ  = dS' K                       descriptor (transposed) and a K-major one
+// so no score element is ever transposed or re-loaded by a CUDA core: compared
+// with the mma.sync kernel (attention.cu) the movmatrix / ldmatrix / HMMA issue
+// slots disappear and the element work is the only thing the SM issues.
+// dK, dV accumulate in TMEM over the whole walk; dQ tiles are drained from TMEM
+// by the thread that owns the row and reduced into the fp32 dq buffer.
+//
+// Q, K, V, dO tiles are rows of d_h bf16 (32 / 64 / 128 bytes) loaded by TMA
+// with the swizzle whose span is one row, consumed K-major (S, dP) and MN-major
+// (dV, dK, dQ right operands).  Reference semantics: see attention.cu.
+#include "attention.h"
+#include "gemm.h"
+
+#include <type_traits>
+
+namespace cb200 {
+
+constexpr int TCB_SM_WARPS = 16;                       // softmax warps: 4 row bands x 4 column quarters
+constexpr int TCB_THREADS = (TCB_SM_WARPS + 2) * 32;   // + control warp + TMEM allocator warp
+constexpr int TCB_CPT = 128 / (TCB_SM_WARPS / 4);      // key columns per softmax thread (64)
+constexpr int TCB_TILE = 128;                          // query rows per tile = keys per CTA
+
+template <int D>
+struct TcbCfg {
+    static constexpr int RB = 2 * D;                       // bytes per row of a Q/K/V/dO tile
+    static constexpr int TILE = TCB_TILE * RB;             // 4 / 8 / 16 KB
+    static constexpr int PBYTES = 2 * TCB_TILE * 128;      // P or dS': [2 column halves][128 rows][128 B]
+    static constexpr int NBUF_Q = (D <= 32) ? 3 : 2;       // Q / dO tile ring
+    static constexpr int NBUF_P = (D <= 32) ? 2 : 1;       // P / dS' buffers
+    static constexpr size_t SMEM = 2 * TILE + 2 * NBUF_Q * TILE + 2 * NBUF_P * PBYTES + 256 + 1024;
+};
+
+// Software pipeline (tile index it):
+//   control thread:  S/dP(it+1) is issued as soon as the softmax warps have pulled S/dP(it) out of TMEM
+//                    (bar_sdp_free), i.e. it runs under the softmax arithmetic of tile it; dV/dK/dQ(it) follow
+//                    when P/dS'(it) are in shared memory (bar_p_full).
+//   softmax warps:   wait S/dP(it) -> tcgen05.ld -> release TMEM -> arithmetic -> smem -> bar_p_full;
+//                    dQ(it-1) is drained at the top of iteration it, when its MMAs have long finished.
+template <int D, bool DROP>
+__global__ void __launch_bounds__(TCB_THREADS, 1)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+                   const float* __restrict__ lse, const float* __restrict__ delta, float* __restrict__ dq_acc,
+                   __nv_bfloat16* __restrict__ dqkv, int T, int H, float scale, float scale_log2, AttnDropKey drop) {
+    using C = TcbCfg<D>;
+    constexpr int RB = C::RB, TILE = C::TILE, PBYTES = C::PBYTES, NBUF_Q = C::NBUF_Q, NBUF_P = C::NBUF_P;
+    constexpr uint32_t LT = umma_layout_for_row_bytes(RB); // swizzle mode of the Q/K/V/dO tiles
+    constexpr uint32_t COL_S = 0, COL_DP = 128, COL_DQ = 256, COL_DK = 256 + D, COL_DV = 256 + 2 * D;
+    static_assert(COL_DV + D <= 512, "TMEM budget");
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sK = smem;
+    uint8_t* sV = sK + TILE;
+    uint8_t* sQ = sV + TILE;                  // [NBUF_Q][TILE]
+    uint8_t* sdO = sQ + NBUF_Q * TILE;        // [NBUF_Q][TILE]
+    uint8_t* sP = sdO + NBUF_Q * TILE;        // [NBUF_P][PBYTES]
+    uint8_t* sdS = sP + NBUF_P * PBYTES;      // [NBUF_P][PBYTES]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + NBUF_P * PBYTES);
+    uint64_t* bar_kv = bars;                  // K, V landed
+    uint64_t* bar_load = bars + 1;            // [3] Q, dO tile landed
+    uint64_t* bar_s_full = bars + 4;          // S, dP complete in TMEM
+    uint64_t* bar_sdp_free = bars + 5;        // S, dP pulled into registers by every softmax thread
+    uint64_t* bar_p_full = bars + 6;          // P, dS' written to smem
+    uint64_t* bar_dq_full = bars + 7;         // dV, dK, dQ MMAs of the tile complete
+    uint64_t* bar_dq_free = bars + 8;         // dQ drained from TMEM
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+    const int E = H * D;
+    const int kb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int k0 = kb * TCB_TILE;
+    const int nq = (T + TCB_TILE - 1) / TCB_TILE;
+    const int ntiles = nq - kb;                            // query tiles kb .. nq-1
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+
+    if (warp == TCB_SM_WARPS && lane == 0) {
+        tma_prefetch_desc(&tm_qkv);
+        tma_prefetch_desc(&tm_do);
+        mbar_init(bar_kv, 1);
+        for (int i = 0; i < 3; ++i) mbar_init(&bar_load[i], 1);
+        mbar_init(bar_s_full, 1);
+        mbar_init(bar_sdp_free, TCB_SM_WARPS * 32);
+        mbar_init(bar_p_full, TCB_SM_WARPS * 32);
+        mbar_init(bar_dq_full, 1);
+        mbar_init(bar_dq_free, 128);
+        mbar_fence_init();
+    }
+    if (warp == TCB_SM_WARPS + 1) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const int row_base = b * T;                            // first row of this sequence in the [B*T, ...] tensors
+
+    if (warp == TCB_SM_WARPS) {
+        // ===================== control warp: TMA producer + MMA issuer =====================
+        if (elect_one()) {
+            constexpr uint32_t IDESC_S = umma_idesc_bf16(128, 128, 0, 0);     // Q K^T, dO V^T
+            constexpr uint32_t IDESC_T = umma_idesc_bf16(128, D, 1, 1);       // P^T dO, dS^T Q
+            constexpr uint32_t IDESC_Q = umma_idesc_bf16(128, D, 0, 1);       // dS K
+            const uint32_t aK = smem_u32(sK), aV = smem_u32(sV);
+            auto load_tile = [&](int t) {
+                const int buf = t % NBUF_Q;
+                const int y = row_base + (kb + t) * TCB_TILE;
+                mbar_expect_tx(&bar_load[buf], 2 * TILE);
+                tma_load_2d(sQ + buf * TILE, &tm_qkv, &bar_load[buf], h * D, y);
+                tma_load_2d(sdO + buf * TILE, &tm_do, &bar_load[buf], h * D, y);
+            };
+            auto issue_s_dp = [&](int t) {
+                const int buf = t % NBUF_Q;
+                mbar_wait(&bar_load[buf], (t / NBUF_Q) & 1);
+                tc_fence_after();
+                const uint32_t aQ = smem_u32(sQ + buf * TILE), aO = smem_u32(sdO + buf * TILE);
+                // K-major operands, d_h/16 k-steps of 32 bytes inside the swizzle row
+#pragma unroll
+                for (int ks = 0; ks < D / 16; ++ks)
+                    umma_bf16(tmem + COL_S, umma_smem_desc(aQ + ks * 32, 16, 8 * RB, LT),
+                              umma_smem_desc(aK + ks * 32, 16, 8 * RB, LT), IDESC_S, ks > 0 ? 1u : 0u);
+#pragma unroll
+                for (int ks = 0; ks < D / 16; ++ks)
+                    umma_bf16(tmem + COL_DP, umma_smem_desc(aO + ks * 32, 16, 8 * RB, LT),
+                              umma_smem_desc(aV + ks * 32, 16, 8 * RB, LT), IDESC_S, ks > 0 ? 1u : 0u);
+                umma_commit(bar_s_full);
+            };
+            mbar_expect_tx(bar_kv, 2 * TILE);
+            tma_load_2d(sK, &tm_qkv, bar_kv, E + h * D, row_base + k0);
+            tma_load_2d(sV, &tm_qkv, bar_kv, 2 * E + h * D, row_base + k0);
+            load_tile(0);
+            if (NBUF_Q == 3 && ntiles > 1) load_tile(1);
+            mbar_wait(bar_kv, 0);
+            issue_s_dp(0);
+            for (int it = 0; it < ntiles; ++it) {
+                // the ring slot of tile it + NBUF_Q - 1 was last read by the MMAs of tile it - 1
+                if (it >= 1) mbar_wait(bar_dq_full, (it - 1) & 1);
+                if (it + NBUF_Q - 1 < ntiles) load_tile(it + NBUF_Q - 1);
+                if (it + 1 < ntiles) {
+                    mbar_wait(bar_sdp_free, it & 1);       // S/dP(it) are in registers: TMEM columns reusable
+                    tc_fence_after();
+                    issue_s_dp(it + 1);
+                }
+                mbar_wait(bar_p_full, it & 1);
+                tc_fence_after();
+                if (it >= 1) {
+                    mbar_wait(bar_dq_free, (it - 1) & 1);  // previous dQ tile drained
+                    tc_fence_after();
+                }
+                const int buf = it % NBUF_Q;
+                const uint32_t aQ = smem_u32(sQ + buf * TILE), aO = smem_u32(sdO + buf * TILE);
+                const uint32_t aP = smem_u32(sP + (it % NBUF_P) * PBYTES), aS = smem_u32(sdS + (it % NBUF_P) * PBYTES);
+                // dV += P^T dO, dK += dS'^T Q : A = smem tile read MN-major (M = keys), K = 128 query rows
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks)
+                    umma_bf16(tmem + COL_DV, umma_smem_desc(aP + ks * 2048, 16384, 1024, 2u),
+                              umma_smem_desc(aO + ks * 16 * RB, 128 * RB, 8 * RB, LT), IDESC_T, (it > 0 || ks > 0) ? 1u : 0u);
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks)
+                    umma_bf16(tmem + COL_DK, umma_smem_desc(aS + ks * 2048, 16384, 1024, 2u),
+                              umma_smem_desc(aQ + ks * 16 * RB, 128 * RB, 8 * RB, LT), IDESC_T, (it > 0 || ks > 0) ? 1u : 0u);
+                // dQ = dS' K : A K-major (two 64-key halves of 16 KB), B = K tile MN-major
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks)
+                    umma_bf16(tmem + COL_DQ, umma_smem_desc(aS + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024, 2u),
+                              umma_smem_desc(aK + ks * 16 * RB, 128 * RB, 8 * RB, LT), IDESC_Q, ks > 0 ? 1u : 0u);
+                umma_commit(bar_dq_full);
+            }
+        }
+    } else if (warp < TCB_SM_WARPS) {
+        // ===================== softmax warps =====================
+        const int quad = warp & 3;                    // TMEM lane quadrant = 32-row band of the tile
+        const int cq = warp >> 2;                     // which TCB_CPT-column slice of the 128 keys
+        const int r = quad * 32 + lane;               // row inside the tile
+        const uint32_t t_lane = tmem + (static_cast<uint32_t>(quad * 32) << 16);
+        const float ks_scale = DROP ? drop.keep_scale : 1.0f;
+        const float inv_ks = 1.0f / ks_scale;
+        const float* glse = lse + (static_cast<size_t>(b) * H + h) * T;
+        const float* gdelta = delta + (static_cast<size_t>(b) * H + h) * T;
+        float* dqb = dq_acc + static_cast<size_t>(b) * T * E + h * D;
+        // dropout: this thread's row meets 4 lanes' streams (tig = 0..3) of the m16n8k16 ownership map
+        uint32_t base4[4] = {0, 0, 0, 0};
+        const int g = r & 7, hi = (r >> 3) & 1;
+        if (DROP) {
+#pragma unroll
+            for (int tig = 0; tig < 4; ++tig) base4[tig] = attn_stream_base(drop, b * H + h, 4 * g + tig);
+        }
+        const float dq_scale = scale * ks_scale;
+
+        auto drain_dq = [&](int t) {                  // tile t's dQ rows of this band -> fp32 buffer
+            const int row_g = (kb + t) * TCB_TILE + r;
+            mbar_wait(bar_dq_full, t & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int c0 = 0; c0 < D; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(t_lane + COL_DQ + c0, v);
+                tmem_ld_wait();
+                if (row_g < T) {
+                    float* dst = dqb + static_cast<size_t>(row_g) * E + c0;
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4)
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j),
+                                     "f"(__uint_as_float(v[j]) * dq_scale), "f"(__uint_as_float(v[j + 1]) * dq_scale),
+                                     "f"(__uint_as_float(v[j + 2]) * dq_scale), "f"(__uint_as_float(v[j + 3]) * dq_scale)
+                                     : "memory");
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(bar_dq_free);
+        };
+
+        // per-row softmax statistics are fetched one tile ahead (a global-memory latency per tile otherwise)
+        float lse_next = (kb * TCB_TILE + r < T) ? glse[kb * TCB_TILE + r] : INFINITY;   // +inf => P = 0 past the end
+        float dl_next = (kb * TCB_TILE + r < T) ? gdelta[kb * TCB_TILE + r] * inv_ks : 0.f;
+        for (int it = 0; it < ntiles; ++it) {
+            const int row_g = (kb + it) * TCB_TILE + r;            // global query row
+            const float lse_r = lse_next, dl_r = dl_next;
+            {
+                const int row_n = row_g + TCB_TILE;
+                const bool ok = (it + 1 < ntiles) && row_n < T;
+                lse_next = ok ? glse[row_n] : INFINITY;
+                dl_next = ok ? gdelta[row_n] * inv_ks : 0.f;
+            }
+            if (cq == 0 && it >= 1) drain_dq(it - 1);
+            mbar_wait(bar_s_full, it & 1);
+            tc_fence_after();
+            const bool diagonal = (it == 0);
+            uint8_t* bp = sP + (it % NBUF_P) * PBYTES;
+            uint8_t* bs = sdS + (it % NBUF_P) * PBYTES;
+            uint32_t xs[4] = {0, 0, 0, 0};
+            // 16 columns at a time keep the live register set small
+#pragma unroll
+            for (int ch = 0; ch < TCB_CPT / 16; ++ch) {
+                const int col0 = cq * TCB_CPT + ch * 16;           // first key column of this chunk (inside the tile)
+                const bool last = (ch == TCB_CPT / 16 - 1);
+                uint32_t pk[8], dk_[8];                            // packed bf16 pairs of P (dropped) and dS'
+                if (diagonal && col0 > quad * 32 + 31) {
+                    // every key of this chunk is above every row of this band
+                    if (last) {
+                        tc_fence_before();
+                        mbar_arrive(bar_sdp_free);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { pk[i] = 0u; dk_[i] = 0u; }
+                } else {
+                    uint32_t sv[16], dv_[16];
+                    tmem_ld16(t_lane + COL_S + col0, sv);
+                    tmem_ld16(t_lane + COL_DP + col0, dv_);
+                    tmem_ld_wait();
+                    if (last) {
+                        tc_fence_before();
+                        mbar_arrive(bar_sdp_free);                 // the next tile's S/dP may overwrite TMEM now
+                    }
+                    const bool partial = diagonal && (col0 + 15 > quad * 32);
+                    if (DROP && (ch == 0 || (col0 & 63) == 0)) {
+                        // (re)seed at the thread's first chunk and at every new 64-key dropout block.  The stream is
+                        // parked two positions before element idx = 4*t + 2*hi (t = first 8-key group of the chunk),
+                        // so that every pair below advances by A^3 then A.
+                        const uint32_t park = ((col0 & 32) ? mcg_mul_pow(16) : 1u) * (hi ? 1u : mcg_inv_pow(2));
+#pragma unroll
+                        for (int tig = 0; tig < 4; ++tig)
+                            xs[tig] = attn_stream_seed(base4[tig], static_cast<uint32_t>(row_g) >> 4,
+                                                       static_cast<uint32_t>((k0 + col0) >> 6)) * park;
+                    }
+                    // two copies of the element loop: only chunks that straddle the diagonal pay for the mask
+                    auto elements = [&](auto masked) {
+#pragma unroll
+                        for (int t2 = 0; t2 < 2; ++t2) {
+#pragma unroll
+                            for (int tig = 0; tig < 4; ++tig) {
+                                float pd[2], ds[2];
+#pragma unroll
+                                for (int e = 0; e < 2; ++e) {
+                                    const int c = 8 * t2 + 2 * tig + e;              // column inside this chunk
+                                    float pv = fast_exp2(fmaf(__uint_as_float(sv[c]), scale_log2, -lse_r));
+                                    if (decltype(masked)::value && (col0 + c > r)) pv = 0.f;
+                                    float dpv = __uint_as_float(dv_[c]);
+                                    pd[e] = pv;
+                                    if (DROP) {
+                                        xs[tig] *= (e == 0) ? mcg_mul_pow(3) : ATTN_MCG_A;
+                                        const bool dropped = xs[tig] < drop.threshold32;
+                                        dpv = dropped ? 0.f : dpv;
+                                        pd[e] = dropped ? 0.f : pd[e];
+                                    }
+                                    ds[e] = pv * (dpv - dl_r);
+                                }
+                                pk[4 * t2 + tig] = pack_bf16(pd[0], pd[1]);
+                                dk_[4 * t2 + tig] = pack_bf16(ds[0], ds[1]);
+                            }
+                        }
+                    };
+                    if (partial) elements(std::true_type{});
+                    else         elements(std::false_type{});
+                }
+                if (ch == 0 && NBUF_P == 1 && it >= 1) mbar_wait(bar_dq_full, (it - 1) & 1);   // single buffer: tile it-1's MMAs must be done
+                // two 16-byte chunks of this row per tensor; chunk index XOR (row & 7) = SWIZZLE_128B
+                const uint32_t half_off = static_cast<uint32_t>((col0 >> 6) * 16384 + r * 128);
+#pragma unroll
+                for (int c2 = 0; c2 < 2; ++c2) {
+                    const uint32_t off = half_off + (((((col0 & 63) >> 3) + c2) ^ (r & 7)) << 4);
+                    *reinterpret_cast<uint4*>(bp + off) = make_uint4(pk[4 * c2], pk[4 * c2 + 1], pk[4 * c2 + 2], pk[4 * c2 + 3]);
+                    *reinterpret_cast<uint4*>(bs + off) = make_uint4(dk_[4 * c2], dk_[4 * c2 + 1], dk_[4 * c2 + 2], dk_[4 * c2 + 3]);
+                }
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(bar_p_full);
+        }
+        // ---- last dQ tile, then dK / dV of this key block (thread = key row) ----
+        if (cq == 0) {
+            drain_dq(ntiles - 1);
+            const int key = k0 + r;
+            const int ld = 3 * E;
+            __nv_bfloat16* dkp = dqkv + (static_cast<size_t>(row_base) + key) * ld + E + h * D;
+            __nv_bfloat16* dvp = dqkv + (static_cast<size_t>(row_base) + key) * ld + 2 * E + h * D;
+            const float dk_scale = scale * ks_scale;
+#pragma unroll
+            for (int c0 = 0; c0 < D; c0 += 16) {
+                uint32_t vk[16], vv[16];
+                tmem_ld16(t_lane + COL_DK + c0, vk);
+                tmem_ld16(t_lane + COL_DV + c0, vv);
+                tmem_ld_wait();
+                if (key < T) {
+                    uint32_t ok[8], ov[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        ok[j] = pack_bf16(__uint_as_float(vk[2 * j]) * dk_scale, __uint_as_float(vk[2 * j + 1]) * dk_scale);
+                        ov[j] = pack_bf16(__uint_as_float(vv[2 * j]) * ks_scale, __uint_as_float(vv[2 * j + 1]) * ks_scale);
+                    }
+                    reinterpret_cast<uint4*>(dkp + c0)[0] = make_uint4(ok[0], ok[1], ok[2], ok[3]);
+                    reinterpret_cast<uint4*>(dkp + c0)[1] = make_uint4(ok[4], ok[5], ok[6], ok[7]);
+                    reinterpret_cast<uint4*>(dvp + c0)[0] = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+                    reinterpret_cast<uint4*>(dvp + c0)[1] = make_uint4(ov[4], ov[5], ov[6], ov[7]);
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == TCB_SM_WARPS + 1) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem);
+    }
+}
+
+template <int D, bool DROP>
+static int launch_bwd_tc(const __nv_bfloat16* qkv, const __nv_bfloat16* dout, const float* lse, const float* delta,
+                         float* dq_acc, __nv_bfloat16* dqkv, int B, int T, int H, float scale, const AttnDropKey& key,
+                         cudaStream_t s) {
+    constexpr int RB = 2 * D;
+    constexpr size_t smem = TcbCfg<D>::SMEM;
+    const int E = H * D;
+    CUtensorMap tm_qkv, tm_do;
+    int rc = make_tmap_bf16_sw(&tm_qkv, qkv, 3 * E, static_cast<uint64_t>(B) * T, 3 * E, D, TCB_TILE, RB);
+    if (rc) return rc;
+    rc = make_tmap_bf16_sw(&tm_do, dout, E, static_cast<uint64_t>(B) * T, E, D, TCB_TILE, RB);
+    if (rc) return rc;
+    auto kernel = attn_bwd_tc_kernel<D, DROP>;
+    static bool configured = false;
+    if (!configured) {
+        CB200_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    dim3 grid((T + TCB_TILE - 1) / TCB_TILE, H, B);
+    kernel<<<grid, TCB_THREADS, smem, s>>>(tm_qkv, tm_do, lse, delta, dq_acc, dqkv, T, H, scale,
+                                            scale * 1.4426950408889634f, key);
+    CB200_CUDA_OK(cudaGetLastError());
+    note_launch(1);
+    return 0;
+}
+
+// The tcgen05 main kernel of attention_bwd (delta and the dq store stay in attention.cu).
+int attention_bwd_tc_main(const __nv_bfloat16* qkv, const __nv_bfloat16* dout, const float* lse, const float* delta,
+                          float* dq_acc, __nv_bfloat16* dqkv, int B, int T, int H, int D, float scale,
+                          const AttnDropKey& key, cudaStream_t s) {
+    const bool dropping = key.threshold32 != 0;
+    switch (D) {
+        case 16: return dropping ? launch_bwd_tc<16, true>(qkv, dout, lse, delta, dq_acc, dqkv, B, T, H, scale, key, s)
+                                 : launch_bwd_tc<16, false>(qkv, dout, lse, delta, dq_acc, dqkv, B, T, H, scale, key, s);
+        case 32: return dropping ? launch_bwd_tc<32, true>(qkv, dout, lse, delta, dq_acc, dqkv, B, T, H, scale, key, s)
+                                 : launch_bwd_tc<32, false>(qkv, dout, lse, delta, dq_acc, dqkv, B, T, H, scale, key, s);
+        case 64: return dropping ? launch_bwd_tc<64, true>(qkv, dout, lse, delta, dq_acc, dqkv, B, T, H, scale, key, s)
+                                 : launch_bwd_tc<64, false>(qkv, dout, lse, delta, dq_acc, dqkv, B, T, H, scale, key, s);
+        default: break;
+    }
+    set_error("attention head size %d is not supported (16, 32 or 64)", D);
+    return -1;
+}
+
+}  // namespace cb200

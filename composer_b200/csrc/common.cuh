@@ -181,6 +181,13 @@ __host__ __device__ constexpr uint32_t mcg_mul_pow(int n) {
     for (int i = 0; i < n; ++i) a *= ATTN_MCG_A;
     return a;
 }
+// A^-n modulo 2^32 (A is odd, so it is invertible): Newton iteration x <- x (2 - a x).
+__host__ __device__ constexpr uint32_t mcg_inv_pow(int n) {
+    const uint32_t a = mcg_mul_pow(n);
+    uint32_t x = a;
+    for (int i = 0; i < 6; ++i) x *= 2u - a * x;
+    return x;
+}
 
 __host__ __device__ __forceinline__ uint32_t fmix32(uint32_t h) {
     h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
@@ -243,14 +250,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t addr = smem_u32(bar);
     uint32_t done = 0;
     for (uint32_t spins = 0; !done; ++spins) {
+        // the suspend-time hint parks the thread instead of re-issuing the poll at full rate
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.b32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
-            : "r"(addr), "r"(parity)
+            : "r"(addr), "r"(parity), "r"(100000u)
             : "memory");
-        if (spins > (1u << 22)) __trap();
+        if (spins > (1u << 20)) __trap();
     }
 }
 
@@ -360,14 +368,25 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 //   bits  0-13 start address >> 4      bits 16-29 leading byte offset >> 4
 //   bits 32-45 stride byte offset >> 4 bits 46-47 descriptor version (1 on sm_100)
 //   bits 61-63 layout type (2 = SWIZZLE_128B)
-__device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+//   layout type codes: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout_type) {
     uint64_t d = 0;
     d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
     d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
     d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
     d |= static_cast<uint64_t>(1) << 46;
-    d |= static_cast<uint64_t>(2) << 61;
+    d |= static_cast<uint64_t>(layout_type) << 61;
     return d;
+}
+
+__device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return umma_smem_desc(smem_addr, lbo_bytes, sbo_bytes, 2u);
+}
+
+// Swizzle mode whose span equals a row of `row_bytes` (32, 64 or 128) bytes.
+__host__ __device__ constexpr uint32_t umma_layout_for_row_bytes(int row_bytes) {
+    return row_bytes == 128 ? 2u : row_bytes == 64 ? 4u : 6u;
 }
 
 // 32-bit instruction descriptor, kind::f16, bf16 x bf16 -> fp32.

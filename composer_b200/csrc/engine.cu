@@ -850,6 +850,12 @@ int cb200_attention_bwd(const void* qkv, const void* out, const void* dout, cons
                          static_cast<cudaStream_t>(stream));
 }
 
+int cb200_set_attention_bwd_impl(int impl) {
+    CB200_REQUIRE(impl == 0 || impl == 1, "attention backward implementation must be 0 (tcgen05) or 1 (mma.sync)");
+    attention_set_bwd_impl(impl);
+    return 0;
+}
+
 int cb200_attention_dropout_mask(uint8_t* mask, int B, int T, int H, float dropout_rate, uint64_t seed, uint32_t step,
                                  uint32_t layer, void* stream) {
     return attention_mask_export(mask, B, T, H, make_dropout(dropout_rate, seed, step, dropout_rate > 0.f), layer,

@@ -51,8 +51,14 @@ struct TmapKeyHash {
 // row, `outer` rows, `stride_elems` elements between rows; SWIZZLE_128B boxes.
 int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t stride_elems,
                    uint32_t box_inner, uint32_t box_outer) {
+    return make_tmap_bf16_sw(out, base, inner, outer, stride_elems, box_inner, box_outer, 128);
+}
+
+// Same with a 32-, 64- or 128-byte swizzle; the box's inner extent must span exactly one swizzle row.
+int make_tmap_bf16_sw(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t stride_elems,
+                      uint32_t box_inner, uint32_t box_outer, int swizzle_bytes) {
     static thread_local std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
-    TmapKey key{base, inner, outer, stride_elems, box_inner, box_outer};
+    TmapKey key{base, inner, outer, stride_elems, box_inner, box_outer};   // box_inner * 2 == swizzle span, so it keys the mode too
     auto it = cache.find(key);
     if (it != cache.end()) {
         *out = it->second;
@@ -63,14 +69,17 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t 
     CB200_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base address must be 16-byte aligned");
     CB200_REQUIRE((stride_elems * 2) % 16 == 0, "TMA row stride must be a multiple of 16 bytes (got %llu elements)",
                   (unsigned long long)stride_elems);
-    CB200_REQUIRE(box_inner * 2 == 128 && box_outer <= 256, "bad TMA box");
+    CB200_REQUIRE(static_cast<int>(box_inner) * 2 == swizzle_bytes && box_outer <= 256 &&
+                      (swizzle_bytes == 32 || swizzle_bytes == 64 || swizzle_bytes == 128), "bad TMA box");
+    const CUtensorMapSwizzle swz = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                   : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
     cuuint64_t dims[2] = {inner, outer};
     cuuint64_t strides[1] = {stride_elems * 2};
     cuuint32_t box[2] = {box_inner, box_outer};
     cuuint32_t estr[2] = {1, 1};
     alignas(64) CUtensorMap m;
     CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     CB200_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) inner=%llu outer=%llu stride=%llu box=%ux%u",
                   (int)r, (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)stride_elems,

@@ -39,4 +39,7 @@ int device_sm_count();
 int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t stride_elems,
                    uint32_t box_inner, uint32_t box_outer);
 
+int make_tmap_bf16_sw(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t stride_elems,
+                      uint32_t box_inner, uint32_t box_outer, int swizzle_bytes);
+
 }  // namespace cb200

@@ -148,6 +148,9 @@ int cb200_attention_fwd(const void* qkv, void* out, float* lse, int B, int T, in
 int cb200_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta,
                         float* dq_acc, void* dqkv, int B, int T, int H, int D, float scale, float dropout_rate,
                         uint64_t seed, uint32_t step, uint32_t layer, void* stream);
+/* Attention backward has two implementations of the same arithmetic: 0 = tcgen05 / TMEM (default),
+ * 1 = warp-level mma.sync (kept for A/B measurements and as a cross-check in the tests). */
+int cb200_set_attention_bwd_impl(int impl);
 /* Keep masks (1 = kept) exactly as the kernels draw them; for parity tests with dropout on. */
 int cb200_attention_dropout_mask(uint8_t* mask, int B, int T, int H, float dropout_rate, uint64_t seed, uint32_t step,
                                  uint32_t layer, void* stream);

@@ -301,7 +301,8 @@ def _attention_reference(qkv, B, T, H, D, scale, keep=None, rate=0.0):
     return out
 
 
-def check_attention(B=2, T=200, H=16, D=16, rate=0.0, backward=True):
+def check_attention(B=2, T=200, H=16, D=16, rate=0.0, backward=True, bwd_impl=0):
+    _lib.call('cb200_set_attention_bwd_impl', bwd_impl)
     E = H * D
     scale = 1.0 / math.sqrt(D)
     qkv = _randn(B, T, 3 * E, scale=1.0, seed=61)
@@ -334,6 +335,7 @@ def check_attention(B=2, T=200, H=16, D=16, rate=0.0, backward=True):
             results.append(_stats('attention_bwd %s' % nm, d[:, i * E:(i + 1) * E], g[:, i * E:(i + 1) * E], 3e-2))
         results.append(_stats('attention_bwd dq_acc rezeroed', dq_acc.reshape(B * T, E),
                               torch.zeros(B * T, E, device=DEV), 0.0, scale=1.0))
+        _lib.call('cb200_set_attention_bwd_impl', 0)
     return _finish(results)
 
 
@@ -398,7 +400,11 @@ GROUPS = {
                       lambda: check_attention(2, 200, 16, 16, rate=0.1, backward=False)],
     'attention_bwd': [lambda: check_attention(1, 64, 2, 16), lambda: check_attention(2, 200, 16, 16),
                       lambda: check_attention(1, 256, 4, 64), lambda: check_attention(1, 192, 4, 32),
-                      lambda: check_attention(2, 200, 16, 16, rate=0.1)],
+                      lambda: check_attention(2, 200, 16, 16, rate=0.1),
+                      lambda: check_attention(1, 4096, 2, 16, rate=0.1), lambda: check_attention(1, 1000, 2, 64, rate=0.1),
+                      lambda: check_attention(3, 130, 4, 32, rate=0.1), lambda: check_attention(2, 16, 4, 16),
+                      lambda: check_attention(2, 200, 16, 16, rate=0.1, bwd_impl=1),
+                      lambda: check_attention(1, 256, 4, 64, bwd_impl=1), lambda: check_attention(1, 192, 4, 32, rate=0.1, bwd_impl=1)],
     'decode_linear': [check_decode_linear, lambda: check_decode_linear(256, 1024, 256, 1),
                       lambda: check_decode_linear(130, 256, 1024, 2), lambda: check_decode_linear(1, 256, 256, 2),
                       lambda: check_decode_linear(32, 3072, 1024, 0)],
