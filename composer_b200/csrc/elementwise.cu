@@ -288,66 +288,74 @@ int layernorm_bwd(const __nv_bfloat16* dy_a, const __nv_bfloat16* dy_b, const __
 // Bias gradient (+ dropout backward):  g = dropout_bwd(dy);  dbias += colsum(g);
 // optionally writes g (the dgrad/wgrad operand) when dropout is active.
 // ---------------------------------------------------------------------------
+// A block owns `rows_per_block` rows of one slice of at most 256 column groups (8 columns each);
+// blockDim is a multiple of the slice's group count, so a thread keeps one column group for all its rows
+// and accumulates in registers; one shared-memory reduction and N atomics per block at the end.
 __global__ void __launch_bounds__(256)
 bias_grad_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ g_out, float* __restrict__ dbias,
-                 int rows, int N, int rows_per_block, DropoutParams drop, uint32_t site, uint32_t layer) {
-    extern __shared__ float red[];   // [N]
-    for (int i = threadIdx.x; i < N; i += blockDim.x) red[i] = 0.f;
+                 int rows, int N, int rows_per_block, int groups_per_slice, DropoutParams drop, uint32_t site,
+                 uint32_t layer) {
+    extern __shared__ float red[];   // [8 * groups in this slice]
+    const int group0 = blockIdx.y * groups_per_slice;
+    const int groups = min(groups_per_slice, N / 8 - group0);
+    for (int i = threadIdx.x; i < groups * 8; i += blockDim.x) red[i] = 0.f;
     __syncthreads();
-    const int groups = N / 8;                      // 8-column groups per row
+    const int lanes = blockDim.x / groups;          // rows handled per pass
+    const int my_group = threadIdx.x % groups;
+    const int my_lane = threadIdx.x / groups;
     const int r0 = blockIdx.x * rows_per_block;
     const int r1 = min(rows, r0 + rows_per_block);
-    const int total = (r1 - r0) * groups;
-    // a thread keeps the same column group when blockDim % groups == 0; otherwise fall back to smem atomics per item
-    const bool fixed_col = (blockDim.x % groups) == 0;
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    int my_group = threadIdx.x % groups;
-    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-        const int row = r0 + idx / groups;
-        const int grp = idx % groups;
-        const size_t off = static_cast<size_t>(row) * N + grp * 8;
-        const uint4 raw = *reinterpret_cast<const uint4*>(dy + off);
-        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
-        float f[8];
+    if (my_lane < lanes) {
+        const int grp = group0 + my_group;
+        for (int row = r0 + my_lane; row < r1; row += lanes) {
+            const size_t off = static_cast<size_t>(row) * N + grp * 8;
+            const uint4 raw = *reinterpret_cast<const uint4*>(dy + off);
+            const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+            float f[8];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) { const float2 p = unpack_bf16(w[e]); f[2 * e] = p.x; f[2 * e + 1] = p.y; }
-        if (drop.threshold16 != 0) {
-            const Philox4 r = drop_bits_rowmajor(drop, site, layer, row, grp);
+            for (int e = 0; e < 4; ++e) { const float2 p = unpack_bf16(w[e]); f[2 * e] = p.x; f[2 * e + 1] = p.y; }
+            if (drop.threshold16 != 0) {
+                const Philox4 r = drop_bits_rowmajor(drop, site, layer, row, grp);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = (drop_u16(r, e) < drop.threshold16) ? 0.f : f[e] * drop.keep_scale;
-            if (g_out != nullptr) {
-                uint4 o;
-                o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]);
-                o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
-                *reinterpret_cast<uint4*>(g_out + off) = o;
+                for (int e = 0; e < 8; ++e) f[e] = (drop_u16(r, e) < drop.threshold16) ? 0.f : f[e] * drop.keep_scale;
+                if (g_out != nullptr) {
+                    uint4 o;
+                    o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]);
+                    o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+                    *reinterpret_cast<uint4*>(g_out + off) = o;
+                }
             }
-        }
-        if (fixed_col) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) acc[e] += f[e];
-        } else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) atomicAdd(&red[grp * 8 + e], f[e]);
         }
-    }
-    if (fixed_col) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) atomicAdd(&red[my_group * 8 + e], acc[e]);
     }
     __syncthreads();
     if (dbias != nullptr)
-        for (int i = threadIdx.x; i < N; i += blockDim.x) atomicAdd(&dbias[i], red[i]);
+        for (int i = threadIdx.x; i < groups * 8; i += blockDim.x) atomicAdd(&dbias[group0 * 8 + i], red[i]);
 }
 
 int bias_grad(const __nv_bfloat16* dy, __nv_bfloat16* g_out, float* dbias, int rows, int N, const DropoutParams& drop,
               uint32_t site, uint32_t layer, cudaStream_t s) {
     CB200_REQUIRE(N % 8 == 0, "bias_grad needs N %% 8 == 0");
     if (rows == 0) return 0;
-    const int target_blocks = 4 * device_sm_count_ew();
+    const int groups_total = N / 8;
+    // slices of at most 256 groups whose size divides evenly: 256, or all groups when there are fewer
+    const int groups_per_slice = groups_total <= 256 ? groups_total : 256;
+    const int slices = (groups_total + groups_per_slice - 1) / groups_per_slice;
+    // the last slice may be smaller; the block size must be a multiple of every slice's group count
+    const int last = groups_total - (slices - 1) * groups_per_slice;
+    int threads = (256 / groups_per_slice) * groups_per_slice;
+    if (slices > 1 && threads % last != 0) threads = 256;     // 256 groups per full slice: any divisor of 256 works
+    CB200_REQUIRE(threads % last == 0 || slices == 1, "bias_grad: unsupported width %d", N);
+    const int target_blocks = 8 * device_sm_count_ew() / slices;
     int rows_per_block = (rows + target_blocks - 1) / target_blocks;
     if (rows_per_block < 8) rows_per_block = 8;
-    const int grid = (rows + rows_per_block - 1) / rows_per_block;
-    bias_grad_kernel<<<grid, 256, N * sizeof(float), s>>>(dy, g_out, dbias, rows, N, rows_per_block, drop, site, layer);
+    dim3 grid((rows + rows_per_block - 1) / rows_per_block, slices);
+    bias_grad_kernel<<<grid, threads, groups_per_slice * 8 * sizeof(float), s>>>(dy, g_out, dbias, rows, N, rows_per_block,
+                                                                                  groups_per_slice, drop, site, layer);
     CB200_CUDA_OK(cudaGetLastError());
     note_launch(1);
     return 0;

@@ -392,7 +392,8 @@ GROUPS = {
                        check_gemm_dgelu],
     'logits_ce': [check_logits_ce, lambda: check_logits_ce(M=1024, V=390), lambda: check_logits_ce(M=130, V=500)],
     'elementwise': [check_embed, lambda: check_embed(rate=0.1), check_layernorm,
-                    lambda: check_layernorm(rows=77, E=1024), check_bias_grad, lambda: check_bias_grad(rate=0.0),
+                    lambda: check_layernorm(rows=77, E=1024), check_bias_grad, lambda: check_bias_grad(rate=0.0), lambda: check_bias_grad(500, 3072, 0.0),
+                    lambda: check_bias_grad(300, 4096, 0.1), lambda: check_bias_grad(64, 256, 0.1), lambda: check_bias_grad(5, 1536, 0.0),
                     check_adam],
     'attention_fwd': [lambda: check_attention(1, 64, 2, 16, backward=False),
                       lambda: check_attention(2, 200, 16, 16, backward=False),

@@ -3,7 +3,7 @@ Times the individual kernels at the benchmark shapes (config 2 of BASELINE.json
 by default: B 32, T 2048, E 256, H 16) with CUDA events and prints achieved
 TFLOP/s / GB/s.  Diagnostic tool; bench.py is the contract benchmark.
 
-    python tools/microbench.py [B T]
+    python tools/microbench.py [B T [E H]]
 '''
 
 import ctypes
@@ -42,7 +42,9 @@ def timeit(fn, iters=10, warmup=3):
 def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
     T = int(sys.argv[2]) if len(sys.argv) > 2 else 2048
-    E, H, V = 256, 16, 390
+    E = int(sys.argv[3]) if len(sys.argv) > 3 else 256
+    H = int(sys.argv[4]) if len(sys.argv) > 4 else 16
+    V = 390
     D, F, M = E // H, 4 * E, B * T
     dev = 'cuda'
     bf = torch.bfloat16
