@@ -25,4 +25,33 @@ int logits_sample(const __nv_bfloat16* x, const float* gamma, const float* beta,
 int decode_linear(int epilogue, const __nv_bfloat16* X, int ldx, const __nv_bfloat16* Wt, const float* bias,
                   const __nv_bfloat16* res, int ldres, __nv_bfloat16* Y, int ldy, int B, int N, int K, cudaStream_t s);
 
+// ---- persistent cluster decode (decode_mega.cu): all steps and layers of a generation in one launch ----
+constexpr int MG_MAX_LAYERS = 32;
+struct MegaLayer {      // element offsets: LayerNorm / bias into the fp32 parameter arena, weights into the bf16 shadow ([out, in])
+    uint32_t ln1_g, ln1_b, attn_b, proj_b, ln2_g, ln2_b, fc_b, proj2_b;
+    uint32_t attn_w, proj_w, fc_w, proj2_w;
+};
+struct MegaArgs {
+    const float* params;
+    const __nv_bfloat16* shadow;
+    __nv_bfloat16* cache;          // [L, 2, B, H, t_max, D]
+    const int32_t* first;          // [B] token fed at step 0
+    const int32_t* forced;         // [B, steps] teacher-forced ids (>= 0) or -1; may be null
+    int32_t* out_ids;              // [B, steps]
+    float* uniforms;               // [B, steps] or null
+    float* logits_out;             // [B, V] logits of the last step, or null
+    long long* prof;               // 16 cycle counters (phase profile of cluster 0), or null
+    long long layer_stride;        // elements per layer of the cache
+    int B, E, H, F, V, L, t_max, steps, use_ln, greedy, seq_base;
+    float eps, scale_log2, inv_temperature;
+    uint32_t seed_lo, seed_hi;
+    uint32_t wte, wpe, lnf_g, lnf_b;   // offsets into params
+    uint32_t wte_sh;                   // bf16 wte [V, E] in the shadow
+    MegaLayer layers[MG_MAX_LAYERS];
+};
+bool decode_mega_supported(int E, int H, int D, int V, int L);
+int decode_mega_capacity(int E, int V, int D);
+// max_clusters > 0 caps the number of clusters (tests); 0 = as many as are co-resident.
+int decode_mega(const MegaArgs& args, int D, int max_clusters, cudaStream_t s);
+
 }  // namespace cb200

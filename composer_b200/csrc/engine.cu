@@ -461,6 +461,10 @@ static int backward(Engine& e, int stage, cudaStream_t s) {
 // ---------------------------------------------------------------------------
 // Generation
 // ---------------------------------------------------------------------------
+static int g_decode_impl = 1;           // 0: persistent cluster kernel when the shape allows it, 1: per-step kernels + CUDA graph
+static long long* g_decode_prof = nullptr;   // device buffer of 16 counters for the cluster kernel's phase profile
+static int g_decode_max_clusters = 0;   // > 0 caps the clusters of the persistent kernel (tests)
+
 struct DecodeBuffers {
     int32_t *cur, *state, *all_ids, *forced;
     float *logits, *uniforms;
@@ -555,6 +559,37 @@ static int generate_on(Engine& e, bf16* cache, int t_max, uint8_t* ws, int64_t w
     CB200_CUDA_OK(cudaGetLastError());
     note_launch(1);
     int rc;
+    const bool mega = g_decode_impl == 0 && decode_mega_supported(e.E, e.H, e.D, e.V, e.L);
+    if (mega) {
+        // the whole generation (all steps, all layers) is one persistent cluster kernel
+        MegaArgs m{};
+        m.params = e.params; m.shadow = e.shadow; m.cache = cache;
+        m.first = d.cur; m.forced = d.forced; m.out_ids = d.all_ids; m.uniforms = d.uniforms; m.logits_out = d.logits;
+        m.prof = g_decode_prof;
+        m.layer_stride = 2ll * B * e.H * t_max * e.D;
+        m.B = B; m.E = e.E; m.H = e.H; m.F = e.F; m.V = e.V; m.L = e.L; m.t_max = t_max; m.steps = steps;
+        m.use_ln = e.cfg.use_layer_normalization ? 1 : 0;
+        m.greedy = temperature <= 0.f ? 1 : 0;
+        m.seq_base = static_cast<int>(seq_base);
+        m.eps = e.cfg.layer_normalization_epsilon;
+        m.scale_log2 = (e.cfg.scale_attention ? 1.0f / sqrtf(static_cast<float>(e.D)) : 1.0f) * 1.4426950408889634f;
+        m.inv_temperature = m.greedy ? 1.f : 1.0f / temperature;
+        m.seed_lo = static_cast<uint32_t>(seed); m.seed_hi = static_cast<uint32_t>(seed >> 32);
+        m.wte = static_cast<uint32_t>(e.lay.wte); m.wpe = static_cast<uint32_t>(e.lay.wpe);
+        m.lnf_g = static_cast<uint32_t>(e.lay.lnf_g); m.lnf_b = static_cast<uint32_t>(e.lay.lnf_b);
+        m.wte_sh = static_cast<uint32_t>(e.lay.wte);
+        for (int l = 0; l < e.L; ++l) {
+            const LayerOffsets& o = e.lay.layers[l];
+            MegaLayer& w = m.layers[l];
+            w.ln1_g = static_cast<uint32_t>(o.ln1_g); w.ln1_b = static_cast<uint32_t>(o.ln1_b);
+            w.ln2_g = static_cast<uint32_t>(o.ln2_g); w.ln2_b = static_cast<uint32_t>(o.ln2_b);
+            w.attn_b = static_cast<uint32_t>(o.attn_b); w.proj_b = static_cast<uint32_t>(o.proj_b);
+            w.fc_b = static_cast<uint32_t>(o.fc_b); w.proj2_b = static_cast<uint32_t>(o.proj2_b);
+            w.attn_w = static_cast<uint32_t>(e.shT_attn[l]); w.proj_w = static_cast<uint32_t>(e.shT_proj[l]);
+            w.fc_w = static_cast<uint32_t>(e.shT_fc[l]); w.proj2_w = static_cast<uint32_t>(e.shT_proj2[l]);
+        }
+        if ((rc = decode_mega(m, e.D, g_decode_max_clusters, s))) return rc;
+    } else {
     // step 0 runs eagerly (also configures kernel attributes outside of capture); the rest replays a graph
     if ((rc = decode_step(e, d, cache, t_max, B, steps, temperature, seed, seq_base, s))) return rc;
     if (steps > 1) {
@@ -581,6 +616,7 @@ static int generate_on(Engine& e, bf16* cache, int t_max, uint8_t* ws, int64_t w
         cudaGraphExecDestroy(exec);
         cudaGraphDestroy(graph);
         CB200_CUDA_OK(se);
+    }
     }
     CB200_CUDA_OK(cudaMemcpy2DAsync(out_ids, n_new * sizeof(int32_t), d.all_ids + (P - 1), steps * sizeof(int32_t),
                                     n_new * sizeof(int32_t), B, cudaMemcpyDeviceToDevice, s));
@@ -848,6 +884,26 @@ int cb200_attention_bwd(const void* qkv, const void* out, const void* dout, cons
                          lse, delta, dq_acc, static_cast<bf16*>(dqkv), B, T, H, D, scale,
                          make_dropout(dropout_rate, seed, step, dropout_rate > 0.f), layer,
                          static_cast<cudaStream_t>(stream));
+}
+
+int cb200_set_decode_impl(int impl, int max_clusters) {
+    CB200_REQUIRE(impl == 0 || impl == 1, "decode implementation must be 0 (persistent cluster kernel) or 1 (per-step kernels)");
+    CB200_REQUIRE(max_clusters >= 0, "max_clusters must be >= 0");
+    g_decode_impl = impl;
+    g_decode_max_clusters = max_clusters;
+    return 0;
+}
+
+int cb200_decode_cluster_capacity(void* engine) {
+    if (!engine) return -1;
+    Engine& e = *static_cast<Engine*>(engine);
+    if (!decode_mega_supported(e.E, e.H, e.D, e.V, e.L)) return 0;
+    return decode_mega_capacity(e.E, e.V, e.D);
+}
+
+int cb200_set_decode_profile(void* counters) {
+    g_decode_prof = static_cast<long long*>(counters);
+    return 0;
 }
 
 int cb200_set_attention_bwd_impl(int impl) {

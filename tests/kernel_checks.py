@@ -506,11 +506,58 @@ def check_engine_adam_step(B=2, T=64):
     return _finish(results)
 
 
-def check_generate(B=4, prompt_len=5, length=40):
+def check_generate(B=4, prompt_len=5, length=40, impl=0, max_clusters=0, embedding=256, heads=16):
+    '''impl 0 = persistent cluster kernel (decode_mega.cu), 1 = per-step kernels replayed as a CUDA graph.'''
+    _lib.call('cb200_set_decode_impl', impl, max_clusters)
+    try:
+        return _check_generate(B, prompt_len, length, embedding, heads)
+    finally:
+        _lib.call('cb200_set_decode_impl', 0, 0)
+
+
+def check_generate_impls_agree(B=19, prompt_len=3, length=50, embedding=256, heads=16):
+    '''The two decode implementations share every rounding point: same tokens (greedy and sampled) and the
+    same final logits up to accumulation order.'''
+    import numpy as np
+
+    model, cfg, _ = _small_model(3, embedding, heads, window=64)
+    rng = np.random.default_rng(21)
+    prompt = rng.integers(0, cfg.vocab_size, size=(B, prompt_len))
+    outs = {}
+    for impl, clusters in ((1, 0), (0, 0), (0, 2)):
+        _lib.call('cb200_set_decode_impl', impl, clusters)
+        try:
+            greedy, _, logits = model.generate(prompt, length, temperature=0.0, return_uniforms=True, return_last_logits=True)
+            sampled = model.generate(prompt, length, temperature=1.0, seed=77)
+            outs[(impl, clusters)] = (greedy.cpu().numpy(), sampled.cpu().numpy(), logits.float().cpu())
+        finally:
+            _lib.call('cb200_set_decode_impl', 0, 0)
+    ref = outs[(1, 0)]
+    results = []
+    for key in ((0, 0), (0, 2)):
+        got = outs[key]
+        # a near-tie may flip one token and change the continuation: compare up to the first difference
+        same_g = float((got[0] == ref[0]).mean())
+        same_s = float((got[1] == ref[1]).mean())
+        results.append({'name': 'cluster kernel (clusters %d) greedy tokens equal %.3f' % (key[1], same_g), 'rel': 1 - same_g,
+                        'tol': 0.1, 'nan': False, 'ok': same_g >= 0.9})
+        results.append({'name': 'cluster kernel (clusters %d) sampled tokens equal %.3f' % (key[1], same_s), 'rel': 1 - same_s,
+                        'tol': 0.1, 'nan': False, 'ok': same_s >= 0.9})
+        rows = (got[0] == ref[0]).all(axis=1)
+        if rows.any():
+            results.append(_stats('final logits vs per-step kernels (%d identical rows)' % int(rows.sum()),
+                                  got[2][torch.from_numpy(rows)], ref[2][torch.from_numpy(rows)], 2e-2))
+    a, b = outs[(0, 0)], outs[(0, 2)]
+    results.append({'name': 'tokens independent of the cluster count', 'rel': float((a[1] != b[1]).mean()), 'tol': 0.0,
+                    'nan': False, 'ok': bool((a[1] == b[1]).all() and (a[0] == b[0]).all())})
+    return _finish(results)
+
+
+def _check_generate(B, prompt_len, length, embedding, heads):
     import numpy as np
     from oracle import transformer_oracle as oracle
 
-    model, cfg, weights = _small_model(2, 256, 16, window=64)
+    model, cfg, weights = _small_model(2, embedding, heads, window=64)
     rng = np.random.default_rng(9)
     prompt = rng.integers(0, cfg.vocab_size, size=(B, prompt_len))
     results = []
@@ -570,4 +617,10 @@ def check_generate(B=4, prompt_len=5, length=40):
 
 GROUPS['engine'] = [check_engine_forward_backward, check_engine_adam_step,
                     lambda: check_engine_forward_backward(B=1, T=256, layers=3)]
-GROUPS['generate'] = [check_generate]
+GROUPS['generate'] = [check_generate, lambda: check_generate(impl=1),
+                      lambda: check_generate(B=21, prompt_len=2, length=30, max_clusters=1),
+                      lambda: check_generate(B=3, prompt_len=1, length=40, embedding=256, heads=8),
+                      lambda: check_generate(B=5, prompt_len=4, length=24, embedding=512, heads=8),
+                      lambda: check_generate(B=3, prompt_len=4, length=24, embedding=512, heads=16, impl=1),
+                      check_generate_impls_agree,
+                      lambda: check_generate_impls_agree(B=33, embedding=512, heads=16)]
