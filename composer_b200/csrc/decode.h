@@ -34,7 +34,8 @@ struct MegaLayer {      // element offsets: LayerNorm / bias into the fp32 param
 struct MegaArgs {
     const float* params;
     const __nv_bfloat16* shadow;
-    __nv_bfloat16* cache;          // [L, 2, B, H, t_max, D]
+    __nv_bfloat16* cache;          // [L, B, H, t_max, 2, D]: the k row and the v row of a token are adjacent
+    const uint8_t* wstream;        // packed weight stream (set by decode_mega)
     const int32_t* first;          // [B] token fed at step 0
     const int32_t* forced;         // [B, steps] teacher-forced ids (>= 0) or -1; may be null
     int32_t* out_ids;              // [B, steps]
@@ -50,8 +51,12 @@ struct MegaArgs {
     MegaLayer layers[MG_MAX_LAYERS];
 };
 bool decode_mega_supported(int E, int H, int D, int V, int L);
-int decode_mega_capacity(int E, int V, int D);
+int decode_mega_capacity(int E, int H, int V, int D, int L, int cluster_size);
 // max_clusters > 0 caps the number of clusters (tests); 0 = as many as are co-resident.
-int decode_mega(const MegaArgs& args, int D, int max_clusters, cudaStream_t s);
+// cluster_size: 0 = automatic, 4 or 8 CTAs per cluster.
+// stream_ws: device scratch of decode_mega_stream_bytes() bytes for the packed weight stream.
+int64_t decode_mega_stream_bytes(int E, int H, int D, int V, int L);
+int decode_mega(MegaArgs args, int D, int max_clusters, int cluster_size, uint8_t* stream_ws, int64_t stream_ws_bytes,
+                cudaStream_t s);
 
 }  // namespace cb200

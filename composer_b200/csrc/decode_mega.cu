@@ -2,24 +2,33 @@
 // in ONE kernel launch.
 //
 // Sequences never interact while decoding, so the batch is split over thread
-// block clusters of 8 CTAs, each cluster owning up to 16 sequences (= the M of
-// one m16n8k16 MMA) for the whole generation, and there is no grid-wide
-// synchronisation at all: the only barriers are hardware cluster barriers
-// (~0.2 us).  Inside a cluster every linear layer is split over the 8 CTAs by
-// output columns; c_attn is split by heads, so a CTA computes q, k, v of its own
-// H/8 heads, appends k, v to the cache and attends for those heads without any
-// exchange.  The activations that the next layer needs in full (attention
-// output, x2, gelu output, block output: 16 rows each) are all-gathered by
-// writing the CTA's column slice into the shared memory of all 8 peers (DSMEM),
-// 4 cluster barriers per decoder block.  Weights (bf16 [out, in] shadows) stream
-// from L2 straight into mma.sync B fragments (a lane reads 16 contiguous bytes
-// of one output row; the k-order inside a 32-wide step is permuted identically
-// for A and B, which a dot product does not notice).  The KV cache is streamed
-// by TMA bulk copies (cp.async.bulk + mbarrier) into a private 4-stage ring per
-// warp, so ~100 KB of cache reads are in flight per SM without holding
-// registers; a warp owns one (sequence, head) pair at a time and keeps the
-// softmax online.  The final CTA 0 of each cluster draws the tokens
-// (same Philox / inverse-CDF rule as logits_sample_kernel) and broadcasts them.
+// block clusters of 4 or 8 CTAs, each cluster owning up to 8 sequences (half the
+// M of an m16n8k16 MMA; the other rows are fed zeros) for the whole generation, and there is no grid-wide
+// synchronisation at all: the only barriers are hardware cluster barriers.
+// Inside a cluster every linear layer is split over the CTAs by output columns;
+// c_attn is split by heads, so a CTA computes q, k, v of its own heads, appends
+// k, v to the cache and attends for those heads without any exchange.  The
+// activations that the next layer needs in full (attention output, x2, gelu
+// output, block output: <= 8 rows each) are all-gathered by writing the CTA's
+// column slice into the shared memory of every peer (DSMEM), 4 cluster barriers
+// per decoder block.
+//
+// Everything that comes from memory arrives through TMA bulk copies
+// (cp.async.bulk + mbarrier), issued far ahead of its use:
+//  * Weights.  A pack kernel re-lays the bf16 weights once per generation into
+//    the order in which each CTA consumes them: a stream of 4 KB slots (8 output
+//    columns x 256 of K, already in mma.sync B-fragment order, + the 8 biases).
+//    The stream runs through a ring of slots in shared memory; the warp that
+//    consumes slot s re-arms it with stream position s + ring size, so weights
+//    are always a whole ring (>= 10 slots, several phases) ahead and a GEMM
+//    phase never waits on L2.
+//  * KV cache, [L, B, H, t_max, 2, d_h] (k and v of a token adjacent): each warp
+//    owns one (sequence, head) pair at a time and streams it in 2-4 KB stages
+//    through a private ring; scores and P.V run on the tensor cores (q as the A
+//    operand, K rows / V rows as B through ldmatrix / ldmatrix.trans, the score
+//    accumulators re-used as the A operand of P.V), the softmax stays online.
+// The first CTA of each cluster draws the tokens (same Philox / inverse-CDF
+// rule as logits_sample_kernel) and broadcasts them.
 //
 // Reference semantics: Transformer.call with `past=` (composer/models/
 // transformer.py:423-437, 583-597, 735-833) and the sampling rule of
@@ -30,13 +39,21 @@
 #include "decode_common.cuh"
 #include "mma_sync.cuh"
 
+#include <cstdlib>
+#include <vector>
+
 namespace cb200 {
 
-constexpr int MG_CL = 8;            // CTAs per cluster
 constexpr int MG_WARPS = 16;
 constexpr int MG_THREADS = MG_WARPS * 32;
-constexpr int MG_ROWS = 16;         // sequences per cluster
-constexpr int MG_CHUNK = 1024;      // bytes of K (and of V) per ring stage
+constexpr int MG_ROWS = 8;          // sequences per cluster: rows 0 .. 7 of the m16n8k16 MMAs (rows 8 .. 15 are fed zeros)
+#ifndef MG_CT16
+#define MG_CT16 64
+#endif
+// tokens per KV ring stage (one bulk copy of k|v records): 4 KB whatever the head size
+#define MG_CT(D) ((D) == 64 ? 16 : (D) == 32 ? 32 : MG_CT16)
+constexpr int MG_SLOT_W = 4096;            // weight bytes of a slot: 8 output columns x 256 of K in B-fragment order
+constexpr int MG_SLOT = MG_SLOT_W + 32;    // + the 8 biases of those columns
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -55,6 +72,9 @@ __device__ __forceinline__ void st_cluster_v4(uint32_t addr, const uint4& v) {
     asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                  : "memory");
 }
+__device__ __forceinline__ void st_cluster_v2(uint32_t addr, uint32_t x, uint32_t y) {
+    asm volatile("st.shared::cluster.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(x), "r"(y) : "memory");
+}
 __device__ __forceinline__ void st_cluster_u32(uint32_t addr, uint32_t v) {
     asm volatile("st.shared::cluster.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
@@ -63,7 +83,7 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
-__device__ __forceinline__ uint4 ldg_nc_v4_keep(const void* p) {   // weights: let L1 keep the other half of the line
+__device__ __forceinline__ uint4 ldg_nc_v4_keep(const void* p) {
     uint4 r;
     asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
@@ -77,64 +97,124 @@ __device__ __forceinline__ void mma_16816(float (&d)[4], uint32_t a0, uint32_t a
         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-struct MegaSmem {        // byte offsets into dynamic shared memory (computed on the host, identical in every CTA)
+struct MegaSmem {        // shared-memory layout and weight-stream plan (computed on the host, identical in every CTA)
     int pe, pf;          // row pitch of the [16, E] and [16, F] bf16 buffers (2E + 64, 2F + 64: conflict-free A reads)
-    int buf0, buf1, bufn, bufg, qkv, red, ring, bars, toks, total;
-    int nst;             // ring stages per warp
-    int zp;              // floats per row of the logits matrix (aliases the ring of CTA 0)
+    int buf0, buf1, bufn, bufg, qkv, red, ring, wring, bars, wseq, toks, total;
+    int nst;             // KV ring stages per warp
+    int nslot;           // weight ring slots
+    int zp;              // floats per row of the logits matrix (aliases the KV ring of CTA 0)
+    int vs;              // vocabulary rows per CTA (whole n-tiles)
+    int ks_proj2;        // K split of the mlp c_proj
+    int sub_e, sub_p2;   // 256-wide K pieces per unit: K = E phases, mlp c_proj
+    int n_attn, n_proj, n_fc, n_proj2, n_logits;   // slots per phase
+    int per_layer, per_step;                       // slots per decoder block / per step
 };
 
-// A[16, K] (bf16, shared memory, row pitch `pitch` bytes)  x  W[rows of an [N, K] bf16 matrix]^T.
-// Work unit = (n-tile of 8 output columns, K split); a warp takes units warp, warp + 16, ...  Partial sums go to
-// red[ks][row][ncols] (fp32).  wrow(nt) = first weight row of n-tile nt (rows wrow .. wrow + 7).
-template <typename RowFn>
-__device__ __forceinline__ void mma_units(const uint8_t* A, int pitch, int K, const __nv_bfloat16* __restrict__ W,
-                                          int ntiles, int ksplit, RowFn wrow, int row_limit, float* red, int warp,
-                                          int lane) {
-    const int g = lane >> 2, tig = lane & 3;
-    const int ncols = ntiles * 8;
-    const int kper = K / ksplit;
-    for (int u = warp; u < ntiles * ksplit; u += MG_WARPS) {
-        const int nt = u % ntiles, ks = u / ntiles;
-        const int wr_row = min(wrow(nt) + g, row_limit);
-        const __nv_bfloat16* wr = W + static_cast<size_t>(wr_row) * K + ks * kper + 8 * tig;
-        const uint8_t* a0 = A + g * pitch + (ks * kper + 8 * tig) * 2;
-        const uint8_t* a1 = a0 + 8 * pitch;
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int kk = 0; kk < kper; kk += 256) {
-            uint4 w[8];
+// One linear layer as this CTA sees it: `ntiles` n-tiles of 8 output columns, K split `ksplit` ways; unit u =
+// (n-tile u % ntiles, K part u / ntiles) belongs to warp u % 16 and occupies `sub` consecutive slots of the weight
+// stream starting at pos0 + u * sub.
+struct Phase {
+    int pos0, ntiles, ksplit, sub;
+};
+
+struct WRing {
+    uint8_t* base;
+    uint64_t* full;
+    volatile int* seq;       // stream position whose copy was last issued into each slot
+    const uint8_t* src;      // this CTA's weight stream (one step; it repeats every step)
+    int nslot, per_step, total;
+};
+
+// A slot is re-armed by whichever warp consumed its previous occupant, so a waiter may be several ring turns ahead
+// of the slot's mbarrier, and an mbarrier wait only tells phases apart by parity: first wait (on the sequence word)
+// until the copy of position s has been issued into the slot, then for its bytes.
+__device__ __forceinline__ const uint8_t* wring_wait(const WRing& r, int s) {
+    const int idx = s % r.nslot;
+    uint32_t spins = 0;
+    while (r.seq[idx] != s) {
+        if (++spins > (1u << 26)) __trap();
+    }
+    __threadfence_block();
+    mbar_wait(&r.full[idx], (s / r.nslot) & 1);
+    return r.base + idx * MG_SLOT;
+}
+
+__device__ __forceinline__ void wring_issue(const WRing& r, int s) {     // one thread
+    const int idx = s % r.nslot;
+    mbar_expect_tx(&r.full[idx], MG_SLOT);
+    bulk_g2s(smem_u32(r.base + idx * MG_SLOT), r.src + static_cast<size_t>(s % r.per_step) * MG_SLOT, MG_SLOT, &r.full[idx]);
+    __threadfence_block();
+    r.seq[idx] = s;
+}
+
+// The warp has read slot s: lane 0 re-arms it with the stream position one ring ahead.
+__device__ __forceinline__ void wring_refill(const WRing& r, int s, int lane) {
+    __syncwarp();
+    if (lane == 0 && s + r.nslot < r.total) wring_issue(r, s + r.nslot);
+}
+
+// acc += A[8, 256 of K] x slot: a0 points at (row g, first k of the piece + 8 * tig); MMA rows 8 .. 15 are zero.
+__device__ __forceinline__ void slot_mma(float (&acc)[4], const uint8_t* slot, const uint8_t* a0, int lane) {
+    uint4 w[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-                if (kk + i * 32 < kper) w[i] = ldg_nc_v4_keep(wr + kk + i * 32);
+    for (int i = 0; i < 8; ++i) w[i] = *reinterpret_cast<const uint4*>(slot + i * 512 + lane * 16);
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-                if (kk + i * 32 < kper) {
-                    const uint4 xa = *reinterpret_cast<const uint4*>(a0 + (kk + i * 32) * 2);
-                    const uint4 xb = *reinterpret_cast<const uint4*>(a1 + (kk + i * 32) * 2);
-                    mma_16816(acc, xa.x, xb.x, xa.y, xb.y, w[i].x, w[i].y);
-                    mma_16816(acc, xa.z, xb.z, xa.w, xb.w, w[i].z, w[i].w);
-                }
-        }
-        float* r = red + (ks * MG_ROWS + g) * ncols + nt * 8 + 2 * tig;
-        *reinterpret_cast<float2*>(r) = make_float2(acc[0], acc[1]);
-        *reinterpret_cast<float2*>(r + 8 * ncols) = make_float2(acc[2], acc[3]);
+    for (int i = 0; i < 8; ++i) {
+        const uint4 xa = *reinterpret_cast<const uint4*>(a0 + i * 64);
+        mma_16816(acc, xa.x, 0u, xa.y, 0u, w[i].x, w[i].y);
+        mma_16816(acc, xa.z, 0u, xa.w, 0u, w[i].z, w[i].w);
     }
 }
 
-// Sums the K-split partials of output chunk (row, 8 columns starting at col) and adds the bias.
-__device__ __forceinline__ void gather8(const float* red, int ksplit, int ncols, int row, int col, const float* bias,
-                                        float (&v)[8]) {
-    if (bias != nullptr) {
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias)), b1 = __ldg(reinterpret_cast<const float4*>(bias + 4));
-        v[0] = b0.x; v[1] = b0.y; v[2] = b0.z; v[3] = b0.w; v[4] = b1.x; v[5] = b1.y; v[6] = b1.z; v[7] = b1.w;
-    } else {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = 0.f;
+// Runs this warp's units of `ph` on A[16, K] (bf16 in shared memory, row pitch `pitch` bytes).  K-split partials
+// meet in `red`; the warp that owns K part 0 of an n-tile calls epi(nt, acc, bias) with the complete sums:
+// acc[0], acc[1] = (row g, columns nt*8 + 2*tig, +1).  With ksplit > 1 all 16 warps must call this (it contains
+// a __syncthreads).
+template <typename Epi>
+__device__ __forceinline__ void run_phase(const Phase& ph, const uint8_t* A, int pitch, const WRing& wr, float* red,
+                                          int warp, int lane, Epi epi) {
+    const int g = lane >> 2, tig = lane & 3;
+    const uint8_t* a0 = A + g * pitch + tig * 16;
+    if (ph.ksplit == 1) {
+        for (int u = warp; u < ph.ntiles; u += MG_WARPS) {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            float2 bias = make_float2(0.f, 0.f);
+            for (int j = 0; j < ph.sub; ++j) {
+                const int s = ph.pos0 + u * ph.sub + j;
+                const uint8_t* slot = wring_wait(wr, s);
+                if (j == 0) bias = *reinterpret_cast<const float2*>(slot + MG_SLOT_W + tig * 8);
+                slot_mma(acc, slot, a0 + j * 512, lane);
+                wring_refill(wr, s, lane);
+            }
+            epi(u, acc, bias);
+        }
+        return;
     }
-    for (int ks = 0; ks < ksplit; ++ks) {
-        const float* r = red + (ks * MG_ROWS + row) * ncols + col;
-        const float4 p0 = *reinterpret_cast<const float4*>(r), p1 = *reinterpret_cast<const float4*>(r + 4);
-        v[0] += p0.x; v[1] += p0.y; v[2] += p0.z; v[3] += p0.w; v[4] += p1.x; v[5] += p1.y; v[6] += p1.z; v[7] += p1.w;
+    // K split: every warp has at most one unit (ntiles * ksplit <= 16)
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float2 bias = make_float2(0.f, 0.f);
+    const int nt = warp % ph.ntiles, ks = warp / ph.ntiles;
+    const bool active = warp < ph.ntiles * ph.ksplit;
+    if (active) {
+        for (int j = 0; j < ph.sub; ++j) {
+            const int s = ph.pos0 + warp * ph.sub + j;
+            const uint8_t* slot = wring_wait(wr, s);
+            if (j == 0) bias = *reinterpret_cast<const float2*>(slot + MG_SLOT_W + tig * 8);
+            slot_mma(acc, slot, a0 + (ks * ph.sub + j) * 512, lane);
+            wring_refill(wr, s, lane);
+        }
+        if (ks > 0) {
+            float* r = red + (((ks - 1) * ph.ntiles + nt) * 32 + lane) * 2;
+            *reinterpret_cast<float2*>(r) = make_float2(acc[0], acc[1]);
+        }
+    }
+    __syncthreads();
+    if (active && ks == 0) {
+        for (int k2 = 1; k2 < ph.ksplit; ++k2) {
+            const float2 p = *reinterpret_cast<const float2*>(red + (((k2 - 1) * ph.ntiles + nt) * 32 + lane) * 2);
+            acc[0] += p.x; acc[1] += p.y;
+        }
+        epi(nt, acc, bias);
     }
 }
 
@@ -142,25 +222,49 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
     return make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
 }
 
-__device__ __forceinline__ void add8(float (&v)[8], const uint4& r) {
-    const float2 a = unpack_bf16(r.x), b = unpack_bf16(r.y), c = unpack_bf16(r.z), d = unpack_bf16(r.w);
-    v[0] += a.x; v[1] += a.y; v[2] += b.x; v[3] += b.y; v[4] += c.x; v[5] += c.y; v[6] += d.x; v[7] += d.y;
-}
-
-// Writes a 16-byte chunk to the same shared-memory offset of all 8 CTAs of the cluster.
-__device__ __forceinline__ void broadcast16(const uint8_t* local, const uint4& val) {
+// Writes one bf16 pair to the same shared-memory offset of all CL CTAs of the cluster (rows without a sequence
+// are skipped: DSMEM bandwidth is the cost of the all-gathers).
+template <int CL>
+__device__ __forceinline__ void broadcast_u32(const uint8_t* local, uint32_t val, bool valid) {
+    if (!valid) return;
     const uint32_t a = smem_u32(local);
 #pragma unroll
-    for (int r = 0; r < MG_CL; ++r) st_cluster_v4(map_to_cta(a, r), val);
+    for (int r = 0; r < CL; ++r) st_cluster_u32(map_to_cta(a, r), val);
+}
+
+// gamma / beta of one LayerNorm as the lanes of a warp need them (lane = 16-byte chunk of the row, two chunks for
+// E = 512); fetched a phase ahead so that the L2 round trip is hidden.
+struct LnFrag {
+    float4 g[2][2], b[2][2];
+};
+
+__device__ __forceinline__ void ln_prefetch(LnFrag& f, const float* gamma, const float* beta, int E, int lane) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int ch = lane + 32 * i;
+        if (ch < E / 8) {
+            f.g[i][0] = __ldg(reinterpret_cast<const float4*>(gamma + ch * 8)); f.g[i][1] = __ldg(reinterpret_cast<const float4*>(gamma + ch * 8 + 4));
+            f.b[i][0] = __ldg(reinterpret_cast<const float4*>(beta + ch * 8)); f.b[i][1] = __ldg(reinterpret_cast<const float4*>(beta + ch * 8 + 4));
+        }
+    }
 }
 
 // LayerNorm of the 16 rows of `src` into `dst` (warp = row), both [16, E] bf16 with pitch pe.  Two passes in
 // registers like layernorm_fwd_kernel; the output is rounded to bf16 (what the next GEMM consumes).
-__device__ __forceinline__ void layernorm_rows(const uint8_t* src, uint8_t* dst, int pe, int E, const float* gamma,
-                                               const float* beta, float eps, bool enabled, int warp, int lane) {
+__device__ __forceinline__ void layernorm_rows(const uint8_t* src, uint8_t* dst, int pe, int E, const LnFrag& f, float eps,
+                                               bool enabled, int warp, int lane) {
+    if (warp >= MG_ROWS) return;
     const uint8_t* s = src + warp * pe;
     uint8_t* d = dst + warp * pe;
     const int nchunk = E / 8;                 // 16-byte chunks per row: 32 (E 256) or 64 (E 512)
+    if (!enabled) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int ch = lane + 32 * i;
+            if (ch < nchunk) *reinterpret_cast<uint4*>(d + ch * 16) = *reinterpret_cast<const uint4*>(s + ch * 16);
+        }
+        return;
+    }
     float v[2][8];
     float sum = 0.f;
 #pragma unroll
@@ -177,14 +281,6 @@ __device__ __forceinline__ void layernorm_rows(const uint8_t* src, uint8_t* dst,
             for (int k = 0; k < 8; ++k) v[i][k] = 0.f;
         }
     }
-    if (!enabled) {
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const int ch = lane + 32 * i;
-            if (ch < nchunk) *reinterpret_cast<uint4*>(d + ch * 16) = *reinterpret_cast<const uint4*>(s + ch * 16);
-        }
-        return;
-    }
     const float mean = warp_sum(sum) / E;
     float sq = 0.f;
 #pragma unroll
@@ -197,82 +293,152 @@ __device__ __forceinline__ void layernorm_rows(const uint8_t* src, uint8_t* dst,
     for (int i = 0; i < 2; ++i) {
         const int ch = lane + 32 * i;
         if (ch < nchunk) {
-            const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + ch * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + ch * 8 + 4));
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + ch * 8)), b1 = __ldg(reinterpret_cast<const float4*>(beta + ch * 8 + 4));
             float o[8];
-            o[0] = (v[i][0] - mean) * rstd * g0.x + b0.x; o[1] = (v[i][1] - mean) * rstd * g0.y + b0.y;
-            o[2] = (v[i][2] - mean) * rstd * g0.z + b0.z; o[3] = (v[i][3] - mean) * rstd * g0.w + b0.w;
-            o[4] = (v[i][4] - mean) * rstd * g1.x + b1.x; o[5] = (v[i][5] - mean) * rstd * g1.y + b1.y;
-            o[6] = (v[i][6] - mean) * rstd * g1.z + b1.z; o[7] = (v[i][7] - mean) * rstd * g1.w + b1.w;
+            o[0] = (v[i][0] - mean) * rstd * f.g[i][0].x + f.b[i][0].x; o[1] = (v[i][1] - mean) * rstd * f.g[i][0].y + f.b[i][0].y;
+            o[2] = (v[i][2] - mean) * rstd * f.g[i][0].z + f.b[i][0].z; o[3] = (v[i][3] - mean) * rstd * f.g[i][0].w + f.b[i][0].w;
+            o[4] = (v[i][4] - mean) * rstd * f.g[i][1].x + f.b[i][1].x; o[5] = (v[i][5] - mean) * rstd * f.g[i][1].y + f.b[i][1].y;
+            o[6] = (v[i][6] - mean) * rstd * f.g[i][1].z + f.b[i][1].z; o[7] = (v[i][7] - mean) * rstd * f.g[i][1].w + f.b[i][1].w;
             *reinterpret_cast<uint4*>(d + ch * 16) = pack8(o);
         }
     }
 }
 
-template <int D>
+// sample_row of decode_common.cuh with the exponentials cached in place (z is overwritten): same expressions,
+// same order of additions, hence the same token as the per-step sampler.
+__device__ __forceinline__ int sample_row_smem(float* z, int V, float inv_temperature, int greedy, uint32_t seed_lo,
+                                               uint32_t seed_hi, uint32_t seq_index, uint32_t step, int lane, float* u_used) {
+    float vmax = -INFINITY;
+    int amax = 0x7fffffff;
+    for (int c = lane; c < V; c += 32) {
+        const float v = z[c];
+        if (v > vmax) { vmax = v; amax = c; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float v2 = __shfl_xor_sync(0xffffffffu, vmax, o);
+        const int a2 = __shfl_xor_sync(0xffffffffu, amax, o);
+        if (v2 > vmax || (v2 == vmax && a2 < amax)) { vmax = v2; amax = a2; }
+    }
+    int chosen = amax;
+    float u = 0.f;
+    if (!greedy) {
+        const float c = inv_temperature * 1.4426950408889634f;
+        const int per = (V + 31) / 32;
+        const int lo = lane * per, hi = min(V, lo + per);
+        float mass = 0.f;
+        for (int i = lo; i < hi; ++i) {
+            const float e = exp2f((z[i] - vmax) * c);
+            z[i] = e;
+            mass += e;
+        }
+        float prefix = mass;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float t = __shfl_up_sync(0xffffffffu, prefix, o);
+            if (lane >= o) prefix += t;
+        }
+        const float total = __shfl_sync(0xffffffffu, prefix, 31);
+        const Philox4 r = philox4x32_10(step, seq_index, 0x5A17u, 0u, seed_lo, seed_hi);
+        u = (r.x >> 8) * (1.0f / 16777216.0f);
+        const float target = u * total;
+        const float before = prefix - mass;
+        const bool mine = (target >= before && target < prefix) || (lane == 31 && target >= prefix);
+        int pick = -1;
+        if (mine) {
+            float run = before;
+            pick = max(hi - 1, lo);
+            for (int i = lo; i < hi; ++i) {
+                run += z[i];
+                if (target < run) { pick = i; break; }
+            }
+            if (pick >= V) pick = V - 1;
+        }
+        const uint32_t ballot = __ballot_sync(0xffffffffu, pick >= 0);
+        const int src = ballot ? (__ffs(ballot) - 1) : 0;
+        chosen = __shfl_sync(0xffffffffu, pick, src);
+        if (chosen < 0) chosen = amax;
+    }
+    *u_used = u;
+    return chosen;
+}
+
+template <int D, int CL>
 __global__ void __launch_bounds__(MG_THREADS, 1)
 decode_mega_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ MegaSmem sm) {
-    constexpr int CH = D / 8;                 // 16-byte chunks per head row
-    constexpr int KPW = 32 / CH;              // keys per warp-wide shared-memory read
-    constexpr int CT = MG_CHUNK / (2 * D);    // tokens per ring stage (= 2 * KPW)
+    constexpr int CH = D / 8;                     // 16-byte chunks per head row
+    constexpr int CT = MG_CT(D);                  // tokens per KV ring stage
+    constexpr int REC = 4 * D;                    // bytes of one cached token of one head: k row | v row
+    constexpr int STAGE = CT * REC;
+    constexpr int NT_S = CT / 8;                  // score n-tiles per stage
+    constexpr int NT_O = D / 8;                   // output n-tiles
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int g = lane >> 2, tig = lane & 3;
     const int crank = static_cast<int>(cluster_ctarank());
-    const int cid = blockIdx.x / MG_CL, ncl = gridDim.x / MG_CL;
+    const int cid = blockIdx.x / CL, ncl = gridDim.x / CL;
     // sequences of this cluster: the first (B % ncl) clusters take one more
     const int base = a.B / ncl, rem = a.B % ncl;
     const int G = base + (cid < rem ? 1 : 0);
     const int s0 = cid * base + min(cid, rem);
-    if (G == 0) return;                        // whole cluster leaves together
+    if (G == 0) return;                            // whole cluster leaves together
 
-    const int E = a.E, F = a.F, H = a.H, V = a.V;
-    const int HS = E / MG_CL;                  // columns of the residual stream owned by this CTA (its heads)
-    const int FS = F / MG_CL;
-    const int HPC = H / MG_CL;                 // heads per CTA
-    const int VS = 8 * ((V + 63) / 64);        // vocabulary rows per CTA (whole n-tiles)
+    const int E = a.E, H = a.H, V = a.V;
+    const int HS = E / CL;                         // columns of the residual stream owned by this CTA (its heads)
+    const int FS = a.F / CL;
+    const int HPC = H / CL;                        // heads per CTA
+    const int VS = sm.vs;
     const int pe = sm.pe, pf = sm.pf;
-    uint8_t* bufU = smem + sm.buf0;            // block input x, later x2
-    uint8_t* bufW = smem + sm.buf1;            // attention output, later the block output
-    uint8_t* bufN = smem + sm.bufn;            // LayerNorm output (ln_1: the residual stream of the block)
-    uint8_t* bufG = smem + sm.bufg;            // gelu output [16, F]
-    uint8_t* qkvs = smem + sm.qkv;             // q | k | v of this CTA's heads, [16][3 * HS] bf16
+    uint8_t* bufU = smem + sm.buf0;                // block input x, later x2
+    uint8_t* bufW = smem + sm.buf1;                // attention output, later the block output
+    uint8_t* bufN = smem + sm.bufn;                // LayerNorm output (ln_1: the residual stream of the block)
+    uint8_t* bufG = smem + sm.bufg;                // gelu output [16, F]
+    uint8_t* qkvs = smem + sm.qkv;                 // q | k | v of this CTA's heads, [16][3 * HS] bf16
     float* red = reinterpret_cast<float*>(smem + sm.red);
     uint8_t* ring = smem + sm.ring;
-    float* Z = reinterpret_cast<float*>(smem + sm.ring);   // logits [16][zp], valid in CTA 0 between the last two barriers of a step
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sm.bars);
+    float* Z = reinterpret_cast<float*>(smem + sm.ring);   // logits [16][zp]: CTA 0, between the last two barriers of a step
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sm.bars);       // [16 * NST] KV stages, then [nslot] weight slots
     int* toks = reinterpret_cast<int*>(smem + sm.toks);
     const int NST = sm.nst;
 
+    WRing wr;
+    wr.base = smem + sm.wring;
+    wr.full = bars + MG_WARPS * NST;
+    wr.seq = reinterpret_cast<volatile int*>(smem + sm.wseq);
+    wr.src = a.wstream + static_cast<size_t>(crank) * sm.per_step * MG_SLOT;
+    wr.nslot = sm.nslot; wr.per_step = sm.per_step; wr.total = a.steps * sm.per_step;
+
     // ---- one-time setup ----
     for (int i = tid * 16; i < sm.bars; i += MG_THREADS * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
-    if (tid < MG_WARPS * NST) mbar_init(&bars[tid], 1);
+    if (tid < MG_WARPS * NST + sm.nslot) mbar_init(&bars[tid], 1);
     if (tid < MG_ROWS) toks[tid] = (tid < G) ? a.first[s0 + tid] : 0;
+    if (tid < sm.nslot) wr.seq[tid] = -1;
     mbar_fence_init();
     __syncthreads();
-    cluster_sync_all();                        // every CTA of the cluster is resident before any DSMEM access
-
-    // optional phase profile (cluster 0, CTA 0, thread 0): cycles accumulated per phase over the whole generation
-    long long prof_acc[16];
-    long long prof_t = 0;
-    const bool profiling = a.prof != nullptr && blockIdx.x == 0 && tid == 0;
-    if (profiling) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) prof_acc[i] = 0;
-        prof_t = clock64();
+    if (tid == 0) {                                // prime the weight ring
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // the zero fill above vs the bulk copies
+        for (int s = 0; s < min(wr.nslot, wr.total); ++s) wring_issue(wr, s);
     }
+    cluster_sync_all();                            // every CTA of the cluster is resident before any DSMEM access
+
+    // optional phase profile (cluster 0, CTA 0, thread 0): cycles per phase, accumulated in global memory
+    const bool profiling = a.prof != nullptr && blockIdx.x == 0 && tid == 0;
+    long long prof_t = profiling ? clock64() : 0;
 #define MG_PROF(slot)                                                        \
     if (profiling) {                                                         \
         const long long now_ = clock64();                                    \
-        prof_acc[slot] += now_ - prof_t;                                     \
+        a.prof[slot] += now_ - prof_t;                                       \
         prof_t = now_;                                                       \
     }
-    uint32_t ring_count = 0;                   // stages consumed by this warp so far (stage = count % NST, parity from count / NST)
+    uint32_t ring_count = 0;                       // KV stages consumed by this warp so far (stage = count % NST, parity from count / NST)
     const float* P = a.params;
-    const __nv_bfloat16* S = a.shadow;
+    const bool use_ln = a.use_ln != 0;
+    LnFrag lnf;
+    if (use_ln) ln_prefetch(lnf, P + a.layers[0].ln1_g, P + a.layers[0].ln1_b, E, lane);
 
     for (int step = 0; step < a.steps; ++step) {
         const int pos = step;
+        const int spos = step * sm.per_step;       // weight-stream position of this step
         // ---- token + positional embedding: warp = row ----
         if (warp < G) {
             int id = toks[warp];
@@ -289,248 +455,226 @@ decode_mega_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ M
         __syncthreads();
         MG_PROF(0)
 
-        uint8_t* X = bufU;                     // block input (full rows)
-        uint8_t* Y = bufW;                     // the other full-row buffer
+        uint8_t* X = bufU;                         // block input (full rows)
+        uint8_t* Y = bufW;                         // the other full-row buffer
         for (int l = 0; l < a.L; ++l) {
             const MegaLayer& lw = a.layers[l];
+            const int lpos = spos + l * sm.per_layer;
+            const Phase ph_attn{lpos, 3 * HS / 8, 1, sm.sub_e};
+            const Phase ph_proj{lpos + sm.n_attn, HS / 8, 1, sm.sub_e};
+            const Phase ph_fc{lpos + sm.n_attn + sm.n_proj, FS / 8, 1, sm.sub_e};
+            const Phase ph_proj2{lpos + sm.n_attn + sm.n_proj + sm.n_fc, HS / 8, sm.ks_proj2, sm.sub_p2};
             // ---- P1: x1 = ln_1(x) ----
-            layernorm_rows(X, bufN, pe, E, P + lw.ln1_g, P + lw.ln1_b, a.eps, a.use_ln != 0, warp, lane);
+            layernorm_rows(X, bufN, pe, E, lnf, a.eps, use_ln, warp, lane);
             __syncthreads();
             MG_PROF(1)
-            // ---- P2: q, k, v of this CTA's heads ----
-            {
-                const int ntiles = 3 * HS / 8;
-                const int tiles_per_part = HS / 8;
-                mma_units(bufN, pe, E, S + lw.attn_w, ntiles, 1,
-                          [&](int nt) { return (nt / tiles_per_part) * E + crank * HS + (nt % tiles_per_part) * 8; },
-                          3 * E - 1, red, warp, lane);
-                __syncthreads();
-                const int ncols = 3 * HS, cpr = ncols / 8;
-                for (int it = tid; it < MG_ROWS * cpr; it += MG_THREADS) {
-                    const int row = it / cpr, col = (it % cpr) * 8;
-                    const int part = col / HS, jj = col % HS;
-                    float v[8];
-                    gather8(red, 1, ncols, row, col, P + lw.attn_b + part * E + crank * HS + jj, v);
-                    *reinterpret_cast<uint4*>(qkvs + (row * ncols + col) * 2) = pack8(v);
-                }
-                __syncthreads();
-            }
+            // ---- P2: q, k, v of this CTA's heads (bf16, local) ----
+            run_phase(ph_attn, bufN, pe, wr, red, warp, lane, [&](int nt, const float (&acc)[4], float2 bias) {
+                uint8_t* dst = qkvs + (g * 3 * HS + nt * 8 + 2 * tig) * 2;
+                *reinterpret_cast<uint32_t*>(dst) = pack_bf16(acc[0] + bias.x, acc[1] + bias.y);
+            });
+            __syncthreads();
             MG_PROF(2)
-            // ---- P3: append k, v; attention of (sequence, head) pairs; all-gather the output into Y ----
+            // ---- P3: append k, v; attention of (sequence, head) pairs on the tensor cores; all-gather into Y ----
             {
-                __nv_bfloat16* kc = a.cache + static_cast<size_t>(l) * a.layer_stride;
-                __nv_bfloat16* vc = kc + a.layer_stride / 2;
+                __nv_bfloat16* cache_l = a.cache + static_cast<size_t>(l) * a.layer_stride;
                 const int npairs = G * HPC;
                 const int nmine = (npairs > warp) ? (npairs - warp + MG_WARPS - 1) / MG_WARPS : 0;
                 const int nchunks = (pos + CT - 1) / CT;
                 const int njobs = nmine * nchunks;
-                const int part = lane % CH;
-                auto issue = [&](int j) {      // lane 0: stream chunk j of this warp's job list into its ring slot
+                auto issue = [&](int j) {          // lane 0: stream chunk j of this warp's job list into its ring slot
                     const int q = warp + MG_WARPS * (j / nchunks), c = j % nchunks;
                     const int b = s0 + q / HPC, h = crank * HPC + q % HPC;
-                    const size_t off = ((static_cast<size_t>(b) * H + h) * a.t_max + static_cast<size_t>(c) * CT) * D;
-                    const uint32_t bytes = static_cast<uint32_t>(min(CT, pos - c * CT)) * 2 * D;
+                    const size_t off = ((static_cast<size_t>(b) * H + h) * a.t_max + static_cast<size_t>(c) * CT) * (2 * D);
+                    const uint32_t bytes = static_cast<uint32_t>(min(CT, pos - c * CT)) * REC;
                     const uint32_t slot = (ring_count + j) % NST;
                     uint64_t* bar = &bars[warp * NST + slot];
-                    uint8_t* dst = ring + (warp * NST + slot) * (2 * MG_CHUNK);
-                    mbar_expect_tx(bar, 2 * bytes);
-                    bulk_g2s(smem_u32(dst), kc + off, bytes, bar);
-                    bulk_g2s(smem_u32(dst + MG_CHUNK), vc + off, bytes, bar);
+                    mbar_expect_tx(bar, bytes);
+                    bulk_g2s(smem_u32(ring + (warp * NST + slot) * STAGE), cache_l + off, bytes, bar);
                 };
                 if (lane == 0)
                     for (int j = 0; j < min(NST, njobs); ++j) issue(j);
+                // ldmatrix row addresses of this lane inside a 16-token tile of k|v records
+                const int mi = lane >> 3, mr = lane & 7;
+                const uint32_t k_lane = static_cast<uint32_t>(((mi >> 1) * 8 + mr) * REC + (mi & 1) * 16);
+                const uint32_t v_lane = static_cast<uint32_t>(((mi & 1) * 8 + mr) * REC + 2 * D + (mi >> 1) * 16);
                 for (int pi = 0; pi < nmine; ++pi) {
                     const int q = warp + MG_WARPS * pi;
                     const int sl = q / HPC, hh = q % HPC;
                     const int b = s0 + sl, h = crank * HPC + hh;
-                    const uint8_t* qrow = qkvs + (sl * 3 * HS + hh * D + part * 8) * 2;
-                    float qf[8];
-                    {
-                        const uint4 qv = *reinterpret_cast<const uint4*>(qrow);
-                        const float2 a0 = unpack_bf16(qv.x), a1 = unpack_bf16(qv.y), a2 = unpack_bf16(qv.z), a3 = unpack_bf16(qv.w);
-                        qf[0] = a0.x; qf[1] = a0.y; qf[2] = a1.x; qf[3] = a1.y; qf[4] = a2.x; qf[5] = a2.y; qf[6] = a3.x; qf[7] = a3.y;
-                    }
-                    const uint4 knew = *reinterpret_cast<const uint4*>(qrow + HS * 2);
-                    const uint4 vnew = *reinterpret_cast<const uint4*>(qrow + 2 * HS * 2);
-                    // append (global cache, read back by TMA in later steps)
-                    if (lane < 2 * CH) {
-                        const size_t off = ((static_cast<size_t>(b) * H + h) * a.t_max + pos) * D + part * 8;
-                        *reinterpret_cast<uint4*>((lane < CH ? kc : vc) + off) = (lane < CH) ? knew : vnew;
-                    }
-                    // the new token seeds the online softmax of the first lane group
-                    float snew = dot8(knew, qf);
+                    const uint32_t* qw = reinterpret_cast<const uint32_t*>(qkvs + (sl * 3 * HS + hh * D) * 2);
+                    const uint32_t* kw = qw + HS / 2;
+                    const uint32_t* vw = qw + HS;
+                    // query as the A operand (every MMA row carries the same query), new token as the softmax seed
+                    uint32_t qa[D / 16][2];
+                    float snew = 0.f;
 #pragma unroll
-                    for (int o = 1; o < CH; o <<= 1) snew += __shfl_xor_sync(0xffffffffu, snew, o);
-                    float m = -INFINITY, lsum = 0.f, acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                    if (lane < CH) {
-                        m = snew * a.scale_log2;
-                        lsum = 1.f;
-                        const float2 v0 = unpack_bf16(vnew.x), v1 = unpack_bf16(vnew.y), v2 = unpack_bf16(vnew.z), v3 = unpack_bf16(vnew.w);
-                        acc[0] = v0.x; acc[1] = v0.y; acc[2] = v1.x; acc[3] = v1.y; acc[4] = v2.x; acc[5] = v2.y; acc[6] = v3.x; acc[7] = v3.y;
+                    for (int ks = 0; ks < D / 16; ++ks) {
+                        qa[ks][0] = qw[ks * 8 + tig];
+                        qa[ks][1] = qw[ks * 8 + 4 + tig];
+                        const float2 q0 = unpack_bf16(qa[ks][0]), q1 = unpack_bf16(qa[ks][1]);
+                        const float2 k0 = unpack_bf16(kw[ks * 8 + tig]), k1 = unpack_bf16(kw[ks * 8 + 4 + tig]);
+                        snew += q0.x * k0.x + q0.y * k0.y + q1.x * k1.x + q1.y * k1.y;
+                    }
+                    snew += __shfl_xor_sync(0xffffffffu, snew, 1);
+                    snew += __shfl_xor_sync(0xffffffffu, snew, 2);
+                    float m = snew * a.scale_log2;                  // running maximum (log2 units)
+                    float lsum = (tig == 0) ? 1.f : 0.f;            // this lane's share of the denominator
+                    float o[NT_O][4];
+#pragma unroll
+                    for (int dt = 0; dt < NT_O; ++dt) {
+                        const float2 vn = unpack_bf16(vw[dt * 4 + tig]);
+                        o[dt][0] = vn.x; o[dt][1] = vn.y; o[dt][2] = 0.f; o[dt][3] = 0.f;
+                    }
+                    // append the k|v record to the global cache (read back by TMA in later steps)
+                    if (lane < 2 * CH) {
+                        const int part = lane % CH;
+                        const size_t off = ((static_cast<size_t>(b) * H + h) * a.t_max + pos) * (2 * D) + lane * 8;
+                        const uint4 val = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(lane < CH ? kw : vw) + part * 16);
+                        *reinterpret_cast<uint4*>(cache_l + off) = val;
                     }
                     for (int c = 0; c < nchunks; ++c) {
                         const int j = pi * nchunks + c;
                         const uint32_t cnt = ring_count + j;
                         const uint32_t slot = cnt % NST;
                         mbar_wait(&bars[warp * NST + slot], (cnt / NST) & 1);
-                        const uint8_t* sk = ring + (warp * NST + slot) * (2 * MG_CHUNK);
-                        const uint8_t* sv = sk + MG_CHUNK;
+                        uint8_t* st = ring + (warp * NST + slot) * STAGE;
                         const int ntok = min(CT, pos - c * CT);
-                        uint4 kv[2], vv[2];
-                        float sc[2];
-                        float mn = m;
-#pragma unroll
-                        for (int u = 0; u < 2; ++u) {
-                            const int key = u * KPW + lane / CH;
-                            const bool valid = key < ntok;
-                            kv[u] = *reinterpret_cast<const uint4*>(sk + key * 2 * D + part * 16);
-                            vv[u] = *reinterpret_cast<const uint4*>(sv + key * 2 * D + part * 16);
-                            if (!valid) vv[u] = make_uint4(0, 0, 0, 0);
-                            float s = dot8(kv[u], qf);
-#pragma unroll
-                            for (int o = 1; o < CH; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                            sc[u] = valid ? s * a.scale_log2 : -INFINITY;
-                            mn = fmaxf(mn, sc[u]);
+                        if (ntok < CT) {           // last, partial chunk: stale V rows must not reach the MMA as NaN
+                            for (int i = lane; i < (CT - ntok) * CH; i += 32)
+                                *reinterpret_cast<uint4*>(st + (ntok + i / CH) * REC + 2 * D + (i % CH) * 16) = make_uint4(0, 0, 0, 0);
+                            __syncwarp();
                         }
-                        if (mn != -INFINITY) {
-                            const float corr = fast_exp2(m - mn);
-                            lsum *= corr;
+                        // S = q K^T for CT tokens: K rows are the col-major B operand as they lie in shared memory
+                        float s[NT_S][4];
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) acc[e] *= corr;
+                        for (int n = 0; n < NT_S; ++n) { s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f; }
+                        const uint32_t sk_a = smem_u32(st) + k_lane, sv_a = smem_u32(st) + v_lane;
 #pragma unroll
-                            for (int u = 0; u < 2; ++u) {
-                                const float p = fast_exp2(sc[u] - mn);
-                                lsum += p;
-                                const float2 v0 = unpack_bf16(vv[u].x), v1 = unpack_bf16(vv[u].y), v2 = unpack_bf16(vv[u].z), v3 = unpack_bf16(vv[u].w);
-                                acc[0] += p * v0.x; acc[1] += p * v0.y; acc[2] += p * v1.x; acc[3] += p * v1.y;
-                                acc[4] += p * v2.x; acc[5] += p * v2.y; acc[6] += p * v3.x; acc[7] += p * v3.y;
+                        for (int jt = 0; jt < CT / 16; ++jt)
+#pragma unroll
+                            for (int ks = 0; ks < D / 16; ++ks) {
+                                uint32_t kb[4];
+                                ldmatrix_x4(kb, sk_a + jt * 16 * REC + ks * 32);
+                                mma_16816(s[2 * jt], qa[ks][0], qa[ks][0], qa[ks][1], qa[ks][1], kb[0], kb[1]);
+                                mma_16816(s[2 * jt + 1], qa[ks][0], qa[ks][0], qa[ks][1], qa[ks][1], kb[2], kb[3]);
                             }
-                            m = mn;
+                        if (ntok < CT) {
+#pragma unroll
+                            for (int n = 0; n < NT_S; ++n) {
+                                if (n * 8 + 2 * tig >= ntok) s[n][0] = -INFINITY;
+                                if (n * 8 + 2 * tig + 1 >= ntok) s[n][1] = -INFINITY;
+                            }
+                        }
+                        float mx = -INFINITY;
+#pragma unroll
+                        for (int n = 0; n < NT_S; ++n) mx = fmaxf(mx, fmaxf(s[n][0], s[n][1]));
+                        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+                        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+                        const float mn = fmaxf(m, mx * a.scale_log2);
+                        const float corr = fast_exp2(m - mn);
+                        m = mn;
+                        lsum *= corr;
+#pragma unroll
+                        for (int dt = 0; dt < NT_O; ++dt) { o[dt][0] *= corr; o[dt][1] *= corr; }
+#pragma unroll
+                        for (int n = 0; n < NT_S; ++n) {
+                            s[n][0] = fast_exp2(fmaf(s[n][0], a.scale_log2, -mn));
+                            s[n][1] = fast_exp2(fmaf(s[n][1], a.scale_log2, -mn));
+                            lsum += s[n][0] + s[n][1];
+                        }
+                        // O += P V: the score accumulators are already laid out as the A operand
+#pragma unroll
+                        for (int jt = 0; jt < CT / 16; ++jt) {
+                            const uint32_t p0 = pack_bf16(s[2 * jt][0], s[2 * jt][1]), p1 = pack_bf16(s[2 * jt + 1][0], s[2 * jt + 1][1]);
+#pragma unroll
+                            for (int dp = 0; dp < D / 16; ++dp) {
+                                uint32_t vb[4];
+                                ldmatrix_x4_trans(vb, sv_a + jt * 16 * REC + dp * 32);
+                                mma_16816(o[2 * dp], p0, 0u, p1, 0u, vb[0], vb[1]);
+                                mma_16816(o[2 * dp + 1], p0, 0u, p1, 0u, vb[2], vb[3]);
+                            }
                         }
                         __syncwarp();
                         if (lane == 0 && j + NST < njobs) issue(j + NST);
                     }
-                    // merge the lane groups (every lane ends with the totals of its slice `part`)
-#pragma unroll
-                    for (int o = CH; o < 32; o <<= 1) {
-                        const float m2 = __shfl_xor_sync(0xffffffffu, m, o);
-                        const float l2 = __shfl_xor_sync(0xffffffffu, lsum, o);
-                        const float mn = fmaxf(m, m2);
-                        const float c1 = (m == -INFINITY) ? 0.f : fast_exp2(m - mn);
-                        const float c2 = (m2 == -INFINITY) ? 0.f : fast_exp2(m2 - mn);
-                        lsum = lsum * c1 + l2 * c2;
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            const float a2 = __shfl_xor_sync(0xffffffffu, acc[e], o);
-                            acc[e] = acc[e] * c1 + a2 * c2;
-                        }
-                        m = mn;
-                    }
+                    lsum += __shfl_xor_sync(0xffffffffu, lsum, 1);
+                    lsum += __shfl_xor_sync(0xffffffffu, lsum, 2);
                     const float inv = 1.0f / lsum;
-                    float o8[8];
+                    // every quad holds the same output row: quad g sends it to CTA g of the cluster
+                    if (g < CL) {
+                        const uint32_t dst = map_to_cta(smem_u32(Y + sl * pe + (h * D + 2 * tig) * 2), g);
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) o8[e] = acc[e] * inv;
-                    const uint4 packed = pack8(o8);
-                    const uint32_t dst = smem_u32(Y + sl * pe + (h * D + part * 8) * 2);
-                    for (int i = lane; i < MG_CL * CH; i += 32) st_cluster_v4(map_to_cta(dst, i / CH), packed);
+                        for (int dt = 0; dt < NT_O; ++dt) st_cluster_u32(dst + dt * 16, pack_bf16(o[dt][0] * inv, o[dt][1] * inv));
+                    }
                 }
                 ring_count += njobs;
                 // the appended rows are read through the async proxy (TMA) in later steps
                 asm volatile("fence.proxy.async.global;" ::: "memory");
             }
+            if (use_ln) ln_prefetch(lnf, P + lw.ln2_g, P + lw.ln2_b, E, lane);
             MG_PROF(3)
-            cluster_sync_all();                // A: attention output of all heads is in Y everywhere
+            cluster_sync_all();                    // A: attention output of all heads is in Y everywhere
             MG_PROF(4)
             // ---- P4: x2 = x1 + c_proj(att) for this CTA's columns, all-gathered into X ----
-            {
-                const int ntiles = HS / 8;
-                const int ksplit = max(1, min(MG_WARPS / ntiles, E / 64));
-                mma_units(Y, pe, E, S + lw.proj_w, ntiles, ksplit, [&](int nt) { return crank * HS + nt * 8; }, E - 1, red,
-                          warp, lane);
-                __syncthreads();
-                const int cpr = HS / 8;
-                for (int it = tid; it < MG_ROWS * cpr; it += MG_THREADS) {
-                    const int row = it / cpr, col = (it % cpr) * 8, gcol = crank * HS + col;
-                    float v[8];
-                    gather8(red, ksplit, HS, row, col, P + lw.proj_b + gcol, v);
-                    add8(v, *reinterpret_cast<const uint4*>(bufN + row * pe + gcol * 2));
-                    broadcast16(X + row * pe + gcol * 2, pack8(v));
-                }
-            }
+            run_phase(ph_proj, Y, pe, wr, red, warp, lane, [&](int nt, const float (&acc)[4], float2 bias) {
+                const int gcol = crank * HS + nt * 8 + 2 * tig;
+                const float2 r0 = unpack_bf16(*reinterpret_cast<const uint32_t*>(bufN + g * pe + gcol * 2));
+                broadcast_u32<CL>(X + g * pe + gcol * 2, pack_bf16(acc[0] + bias.x + r0.x, acc[1] + bias.y + r0.y), g < G);
+            });
             MG_PROF(5)
-            cluster_sync_all();                // B: x2 is in X everywhere
+            cluster_sync_all();                    // B: x2 is in X everywhere
             MG_PROF(6)
             // ---- P5: m = ln_2(x2);  P6: gelu(c_fc(m)) for this CTA's columns, all-gathered into bufG ----
-            layernorm_rows(X, bufN, pe, E, P + lw.ln2_g, P + lw.ln2_b, a.eps, a.use_ln != 0, warp, lane);
-            __syncthreads();
-            {
-                const int ntiles = FS / 8;
-                mma_units(bufN, pe, E, S + lw.fc_w, ntiles, 1, [&](int nt) { return crank * FS + nt * 8; }, F - 1, red, warp,
-                          lane);
-                __syncthreads();
-                const int cpr = FS / 8;
-                for (int it = tid; it < MG_ROWS * cpr; it += MG_THREADS) {
-                    const int row = it / cpr, col = (it % cpr) * 8, gcol = crank * FS + col;
-                    float v[8];
-                    gather8(red, 1, FS, row, col, P + lw.fc_b + gcol, v);
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) v[e] = gelu_tanh(v[e]);
-                    broadcast16(bufG + row * pf + gcol * 2, pack8(v));
-                }
+            layernorm_rows(X, bufN, pe, E, lnf, a.eps, use_ln, warp, lane);
+            if (use_ln) {
+                if (l + 1 < a.L) ln_prefetch(lnf, P + a.layers[l + 1].ln1_g, P + a.layers[l + 1].ln1_b, E, lane);
+                else ln_prefetch(lnf, P + a.lnf_g, P + a.lnf_b, E, lane);
             }
+            __syncthreads();
+            run_phase(ph_fc, bufN, pe, wr, red, warp, lane, [&](int nt, const float (&acc)[4], float2 bias) {
+                const int gcol = crank * FS + nt * 8 + 2 * tig;
+                broadcast_u32<CL>(bufG + g * pf + gcol * 2, pack_bf16(gelu_tanh(acc[0] + bias.x), gelu_tanh(acc[1] + bias.y)), g < G);
+            });
             MG_PROF(7)
-            cluster_sync_all();                // C: gelu output is in bufG everywhere
+            cluster_sync_all();                    // C: gelu output is in bufG everywhere
             MG_PROF(8)
             // ---- P7: out = x2 + c_proj(gelu) for this CTA's columns, all-gathered into Y ----
-            {
-                const int ntiles = HS / 8;
-                const int ksplit = max(1, min(MG_WARPS / ntiles, F / 64));
-                mma_units(bufG, pf, F, S + lw.proj2_w, ntiles, ksplit, [&](int nt) { return crank * HS + nt * 8; }, E - 1,
-                          red, warp, lane);
-                __syncthreads();
-                const int cpr = HS / 8;
-                for (int it = tid; it < MG_ROWS * cpr; it += MG_THREADS) {
-                    const int row = it / cpr, col = (it % cpr) * 8, gcol = crank * HS + col;
-                    float v[8];
-                    gather8(red, ksplit, HS, row, col, P + lw.proj2_b + gcol, v);
-                    add8(v, *reinterpret_cast<const uint4*>(X + row * pe + gcol * 2));
-                    broadcast16(Y + row * pe + gcol * 2, pack8(v));
-                }
-            }
+            run_phase(ph_proj2, bufG, pf, wr, red, warp, lane, [&](int nt, const float (&acc)[4], float2 bias) {
+                const int gcol = crank * HS + nt * 8 + 2 * tig;
+                const float2 r0 = unpack_bf16(*reinterpret_cast<const uint32_t*>(X + g * pe + gcol * 2));
+                broadcast_u32<CL>(Y + g * pe + gcol * 2, pack_bf16(acc[0] + bias.x + r0.x, acc[1] + bias.y + r0.y), g < G);
+            });
             MG_PROF(9)
-            cluster_sync_all();                // D: the block output is in Y everywhere
+            cluster_sync_all();                    // D: the block output is in Y everywhere
             MG_PROF(10)
             uint8_t* t = X; X = Y; Y = t;
         }
 
         // ---- ln_f, tied logits for this CTA's vocabulary rows -> Z of CTA 0 ----
-        layernorm_rows(X, bufN, pe, E, P + a.lnf_g, P + a.lnf_b, a.eps, a.use_ln != 0, warp, lane);
-        __syncthreads();
         {
-            const int ntiles = VS / 8;
-            const int ksplit = max(1, min(MG_WARPS / ntiles, E / 64));
-            mma_units(bufN, pe, E, S + a.wte_sh, ntiles, ksplit, [&](int nt) { return crank * VS + nt * 8; }, V - 1, red,
-                      warp, lane);
+            const Phase ph{spos + a.L * sm.per_layer, VS / 8, 1, sm.sub_e};
+            layernorm_rows(X, bufN, pe, E, lnf, a.eps, use_ln, warp, lane);
+            if (use_ln) ln_prefetch(lnf, P + a.layers[0].ln1_g, P + a.layers[0].ln1_b, E, lane);
             __syncthreads();
-            const int cpr = VS / 8;
             const uint32_t zbase = map_to_cta(smem_u32(Z), 0);
-            for (int it = tid; it < MG_ROWS * cpr; it += MG_THREADS) {
-                const int row = it / cpr, col = (it % cpr) * 8, gcol = crank * VS + col;
-                float v[8];
-                gather8(red, ksplit, VS, row, col, nullptr, v);
-                const uint32_t dst = zbase + (row * sm.zp + gcol) * 4;
-                st_cluster_v4(dst, make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3])));
-                st_cluster_v4(dst + 16, make_uint4(__float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7])));
-            }
+            run_phase(ph, bufN, pe, wr, red, warp, lane, [&](int nt, const float (&acc)[4], float2) {
+                const uint32_t dst = zbase + (g * sm.zp + crank * VS + nt * 8 + 2 * tig) * 4;
+                if (g < G) st_cluster_v2(dst, __float_as_uint(acc[0]), __float_as_uint(acc[1]));
+            });
         }
         MG_PROF(11)
-        cluster_sync_all();                    // E: all logits are in CTA 0
+        cluster_sync_all();                        // E: all logits are in CTA 0
         MG_PROF(12)
         if (crank == 0 && warp < G) {
             const int b = s0 + warp;
             float u;
-            int chosen = sample_row(Z + warp * sm.zp, V, a.inv_temperature, a.greedy, a.seed_lo, a.seed_hi,
-                                    static_cast<uint32_t>(a.seq_base + b), static_cast<uint32_t>(step), lane, &u);
+            float* zrow = Z + warp * sm.zp;
+            if (a.logits_out != nullptr && step == a.steps - 1)
+                for (int c = lane; c < V; c += 32) a.logits_out[static_cast<size_t>(b) * V + c] = zrow[c];
+            __syncwarp();
+            int chosen = sample_row_smem(zrow, V, a.inv_temperature, a.greedy, a.seed_lo, a.seed_hi,
+                                         static_cast<uint32_t>(a.seq_base + b), static_cast<uint32_t>(step), lane, &u);
             if (a.forced != nullptr) {
                 const int f = a.forced[static_cast<size_t>(b) * a.steps + step];
                 if (f >= 0) chosen = f;
@@ -539,24 +683,79 @@ decode_mega_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ M
                 a.out_ids[static_cast<size_t>(b) * a.steps + step] = chosen;
                 if (a.uniforms != nullptr) a.uniforms[static_cast<size_t>(b) * a.steps + step] = u;
             }
-            if (lane < MG_CL) st_cluster_u32(map_to_cta(smem_u32(&toks[warp]), lane), static_cast<uint32_t>(chosen));
-            if (a.logits_out != nullptr && step == a.steps - 1)
-                for (int c = lane; c < V; c += 32) a.logits_out[static_cast<size_t>(b) * V + c] = Z[warp * sm.zp + c];
+            if (lane < CL) st_cluster_u32(map_to_cta(smem_u32(&toks[warp]), lane), static_cast<uint32_t>(chosen));
         }
         MG_PROF(13)
-        cluster_sync_all();                    // F: next tokens are everywhere; Z (= ring of CTA 0) is free again
+        cluster_sync_all();                        // F: next tokens are everywhere; Z (= KV ring of CTA 0) is free again
         MG_PROF(14)
     }
-    if (profiling)
-        for (int i = 0; i < 16; ++i) a.prof[i] = prof_acc[i];
 #undef MG_PROF
 }
 
-static MegaSmem mega_smem_layout(int E, int F, int V, int nst) {
+// ---------------------------------------------------------------------------
+// Weight stream: one entry per linear layer, in the order the kernel consumes them.
+// ---------------------------------------------------------------------------
+struct PackPhase {
+    long long w_src;      // bf16 [N, K] matrix in the shadow arena
+    long long b_src;      // fp32 bias in the parameter arena, or -1
+    int K, ntiles, ksplit, tpp, pstride, cols_per_cta, row_limit, sub, slot0, nslots;
+};
+
+// One block per (slot, CTA rank): 256 16-byte weight chunks in B-fragment order + 2 chunks of bias.
+__global__ void __launch_bounds__(288)
+mega_pack_kernel(const __nv_bfloat16* __restrict__ shadow, const float* __restrict__ params, uint8_t* __restrict__ stream,
+                 const PackPhase* __restrict__ table, int nphase, int per_step) {
+    const int s = blockIdx.x, c = blockIdx.y, t = threadIdx.x;
+    if (t >= 258) return;
+    int pi = 0;
+    while (pi + 1 < nphase && s >= table[pi + 1].slot0) ++pi;
+    const PackPhase ph = table[pi];
+    const int local = s - ph.slot0;
+    const int u = local / ph.sub, j = local % ph.sub;
+    const int nt = u % ph.ntiles, ks = u / ph.ntiles;
+    const int kper = ph.K / ph.ksplit;
+    const int row0 = c * ph.cols_per_cta + (nt / ph.tpp) * ph.pstride + (nt % ph.tpp) * 8;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (t < 256) {
+        const int i = t >> 5, lane = t & 31, g = lane >> 2, tig = lane & 3;
+        const int row = row0 + g;
+        const int k = ks * kper + j * 256 + 32 * i + 8 * tig;
+        if (row <= ph.row_limit) val = *reinterpret_cast<const uint4*>(shadow + ph.w_src + static_cast<long long>(row) * ph.K + k);
+    } else if (ph.b_src >= 0 && ks == 0 && j == 0) {
+        float b[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int row = row0 + (t - 256) * 4 + e;
+            b[e] = row <= ph.row_limit ? params[ph.b_src + row] : 0.f;
+        }
+        val = make_uint4(__float_as_uint(b[0]), __float_as_uint(b[1]), __float_as_uint(b[2]), __float_as_uint(b[3]));
+    }
+    *reinterpret_cast<uint4*>(stream + (static_cast<size_t>(c) * per_step + s) * MG_SLOT + t * 16) = val;
+}
+
+static int mega_ks_proj2(int E, int CL) {      // K split of the mlp c_proj: fill the 16 warps, pieces of >= 256
+    const int ntiles = E / CL / 8;
+    int ks = 1;
+    while (ntiles * ks * 2 <= MG_WARPS && (4 * E) / (ks * 2) >= 256) ks *= 2;
+    return ks;
+}
+
+static MegaSmem mega_smem_layout(int E, int F, int V, int D, int CL, int nst, int nslot) {
     MegaSmem s{};
-    const int HS = E / MG_CL, FS = F / MG_CL, VS = 8 * ((V + 63) / 64);
+    const int HS = E / CL, FS = F / CL;
+    const int stage = MG_CT(D) * 4 * D;
+    s.vs = 8 * ((V + 8 * CL - 1) / (8 * CL));
     s.pe = 2 * E + 64;
     s.pf = 2 * F + 64;
+    s.ks_proj2 = mega_ks_proj2(E, CL);
+    s.sub_e = E / 256;
+    s.sub_p2 = F / s.ks_proj2 / 256;
+    s.n_attn = (3 * HS / 8) * s.sub_e;
+    s.n_proj = (HS / 8) * s.sub_e;
+    s.n_fc = (FS / 8) * s.sub_e;
+    s.n_proj2 = (HS / 8) * s.ks_proj2 * s.sub_p2;
+    s.n_logits = (s.vs / 8) * s.sub_e;
+    s.per_layer = s.n_attn + s.n_proj + s.n_fc + s.n_proj2;
     int off = 0;
     auto take = [&](int bytes) { int o = off; off = (off + bytes + 127) & ~127; return o; };
     s.buf0 = take(MG_ROWS * s.pe);
@@ -564,107 +763,187 @@ static MegaSmem mega_smem_layout(int E, int F, int V, int nst) {
     s.bufn = take(MG_ROWS * s.pe);
     s.bufg = take(MG_ROWS * s.pf);
     s.qkv = take(MG_ROWS * 3 * HS * 2);
-    // partial sums: the widest phase is c_fc (FS columns) or a K-split phase (<= 16 / ntiles splits of HS or VS columns)
-    int red_cols = FS > 3 * HS ? FS : 3 * HS;
-    {
-        const int nt = HS / 8, ks = nt >= MG_WARPS ? 1 : MG_WARPS / nt;
-        if (ks * HS > red_cols) red_cols = ks * HS;
-        const int ntv = VS / 8, ksv = ntv >= MG_WARPS ? 1 : MG_WARPS / ntv;
-        if (ksv * VS > red_cols) red_cols = ksv * VS;
-    }
-    s.red = take(MG_ROWS * red_cols * 4);
+    s.red = take(MG_WARPS * 32 * 8);       // K-split partials: <= 15 units x 32 lanes x 2 floats
     s.nst = nst;
-    s.zp = MG_CL * VS;
-    int ring_bytes = MG_WARPS * nst * 2 * MG_CHUNK;
+    s.nslot = nslot;
+    s.zp = CL * s.vs;
+    int ring_bytes = MG_WARPS * nst * stage;
     if (MG_ROWS * s.zp * 4 > ring_bytes) ring_bytes = MG_ROWS * s.zp * 4;
     s.ring = take(ring_bytes);
-    s.bars = take(MG_WARPS * nst * 8);
+    s.wring = take(nslot * MG_SLOT);
+    s.bars = take((MG_WARPS * nst + nslot) * 8);
+    s.wseq = take(nslot * 4);
     s.toks = take(MG_ROWS * 4);
     s.total = off;
     return s;
 }
 
-template <int D>
-static int launch_mega(const MegaArgs& args, const MegaSmem& sm, int max_clusters_hint, cudaStream_t s) {
-    auto kernel = decode_mega_kernel<D>;
+// KV ring stages per warp (2 x 4 KB preferred: ~100 KB of cache reads in flight per SM) and as many weight slots as
+// still fit (at least 8).
+static MegaSmem mega_smem_fit(int E, int V, int D, int CL, int L) {
+    constexpr int LIMIT = 227 * 1024;
+    int nst = 2;
+    if (const char* env = getenv("CB200_DECODE_RING_STAGES")) {      // tuning knob: KV ring stages per warp (2 .. 4)
+        const int v = atoi(env);
+        if (v >= 2 && v <= 4) nst = v;
+    }
+    MegaSmem sm{};
+    for (; nst >= 2; --nst) {
+        const MegaSmem base = mega_smem_layout(E, 4 * E, V, D, CL, nst, 0);
+        int nslot = (LIMIT - base.total - 768) / (MG_SLOT + 12);
+        if (nslot > 24) nslot = 24;
+        if (const char* env = getenv("CB200_DECODE_WEIGHT_SLOTS")) {
+            const int v = atoi(env);
+            if (v >= 4 && v < nslot) nslot = v;
+        }
+        sm = mega_smem_layout(E, 4 * E, V, D, CL, nst, nslot < 1 ? 1 : nslot);
+        if (nslot >= 8 && sm.total <= LIMIT) break;
+    }
+    sm.per_step = L * sm.per_layer + sm.n_logits;
+    return sm;
+}
+
+template <int D, int CL>
+static int mega_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, const MegaSmem& sm) {
+    auto kernel = decode_mega_kernel<D, CL>;
     static int configured_smem = 0;
     if (configured_smem < sm.total) {
         CB200_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sm.total));
         configured_smem = sm.total;
     }
-    cudaLaunchConfig_t cfg{};
-    cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = MG_CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.blockDim = dim3(MG_THREADS);
+    cfg.gridDim = dim3(CL);
     cfg.dynamicSmemBytes = sm.total;
-    cfg.stream = s;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cfg.gridDim = dim3(MG_CL);
+    return 0;
+}
+
+template <int D, int CL>
+static int mega_capacity(const MegaSmem& sm) {
+    static int cached = -1, cached_smem = -1;
+    if (cached >= 0 && cached_smem == sm.total) return cached;
+    cudaLaunchConfig_t cfg{};
+    cudaLaunchAttribute attr[1];
+    if (mega_config<D, CL>(cfg, attr, sm)) return -1;
     int resident = 0;
-    CB200_CUDA_OK(cudaOccupancyMaxActiveClusters(&resident, kernel, &cfg));
-    CB200_REQUIRE(resident >= 1, "the cluster decode kernel does not fit on this device");
+    if (cudaOccupancyMaxActiveClusters(&resident, decode_mega_kernel<D, CL>, &cfg) != cudaSuccess) return -1;
+    cached = resident; cached_smem = sm.total;
+    return resident;
+}
+
+// Clusters to launch: one wave when the batch fits (<= 8 sequences per cluster), otherwise 8-sequence clusters in
+// several waves.
+static int mega_cluster_count(int B, int resident, int max_clusters_hint) {
     if (max_clusters_hint > 0 && max_clusters_hint < resident) resident = max_clusters_hint;
-    // one wave when the batch fits (<= 16 sequences per cluster), otherwise 16-sequence clusters in several waves
-    int ncl = args.B < resident ? args.B : resident;
-    if (static_cast<long long>(ncl) * MG_ROWS < args.B) ncl = (args.B + MG_ROWS - 1) / MG_ROWS;
-    cfg.gridDim = dim3(ncl * MG_CL);
-    CB200_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, args, sm));
+    int ncl = B < resident ? B : resident;
+    if (static_cast<long long>(ncl) * MG_ROWS < B) ncl = (B + MG_ROWS - 1) / MG_ROWS;
+    return ncl;
+}
+
+template <int D, int CL>
+static int launch_mega(const MegaArgs& args, const MegaSmem& sm, int ncl, cudaStream_t s) {
+    cudaLaunchConfig_t cfg{};
+    cudaLaunchAttribute attr[1];
+    int rc = mega_config<D, CL>(cfg, attr, sm);
+    if (rc) return rc;
+    cfg.stream = s;
+    cfg.gridDim = dim3(ncl * CL);
+    CB200_CUDA_OK(cudaLaunchKernelEx(&cfg, decode_mega_kernel<D, CL>, args, sm));
     note_launch(1);
     return 0;
 }
 
-template <int D>
-static int mega_capacity(const MegaSmem& sm) {
-    auto kernel = decode_mega_kernel<D>;
-    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sm.total) != cudaSuccess) return -1;
-    cudaLaunchConfig_t cfg{};
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = MG_CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.blockDim = dim3(MG_THREADS);
-    cfg.gridDim = dim3(MG_CL);
-    cfg.dynamicSmemBytes = sm.total;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    int resident = 0;
-    if (cudaOccupancyMaxActiveClusters(&resident, kernel, &cfg) != cudaSuccess) return -1;
-    return resident;
-}
-
-// Number of 8-CTA clusters of the persistent decode kernel that are co-resident on the current device.
-int decode_mega_capacity(int E, int V, int D) {
-    int nst = 4;
-    MegaSmem sm = mega_smem_layout(E, 4 * E, V, nst);
-    while (sm.total > 227 * 1024 && nst > 2) sm = mega_smem_layout(E, 4 * E, V, --nst);
-    switch (D) {
-        case 16: return mega_capacity<16>(sm);
-        case 32: return mega_capacity<32>(sm);
-        default: return mega_capacity<64>(sm);
-    }
+static bool mega_shape_ok(int E, int H, int D, int V, int L, int CL) {
+    if (!(E == 256 || E == 512)) return false;
+    if (H % CL != 0 || H * D != E) return false;
+    if (!(D == 16 || D == 32 || D == 64)) return false;
+    if (L < 1 || L > MG_MAX_LAYERS || V < 1 || V > 4096) return false;
+    if ((E / CL) % 8 != 0) return false;
+    const MegaSmem sm = mega_smem_fit(E, V, D, CL, L);
+    return sm.nslot >= 8 && sm.total <= 227 * 1024;
 }
 
 bool decode_mega_supported(int E, int H, int D, int V, int L) {
-    if (!(E == 256 || E == 512)) return false;
-    if (H % MG_CL != 0 || H * D != E) return false;
-    if (!(D == 16 || D == 32 || D == 64)) return false;
-    if (L > MG_MAX_LAYERS || V < 1 || V > 4096) return false;
-    const MegaSmem sm = mega_smem_layout(E, 4 * E, V, 2);
-    return sm.total <= 227 * 1024;
+    return mega_shape_ok(E, H, D, V, L, 8) || mega_shape_ok(E, H, D, V, L, 4);
 }
 
-int decode_mega(const MegaArgs& args, int D, int max_clusters, cudaStream_t s) {
-    CB200_REQUIRE(decode_mega_supported(args.E, args.H, D, args.V, args.L), "shape not supported by the cluster decode kernel");
-    if (args.B == 0 || args.steps == 0) return 0;
-    int nst = 4;
-    MegaSmem sm = mega_smem_layout(args.E, args.F, args.V, nst);
-    while (sm.total > 227 * 1024 && nst > 2) sm = mega_smem_layout(args.E, args.F, args.V, --nst);
-    switch (D) {
-        case 16: return launch_mega<16>(args, sm, max_clusters, s);
-        case 32: return launch_mega<32>(args, sm, max_clusters, s);
-        default: return launch_mega<64>(args, sm, max_clusters, s);
+// Bytes of the packed weight stream (+ its phase table) for the larger of the two cluster sizes.
+int64_t decode_mega_stream_bytes(int E, int H, int D, int V, int L) {
+    int64_t need = 0;
+    for (int CL = 4; CL <= 8; CL += 4) {
+        if (!mega_shape_ok(E, H, D, V, L, CL)) continue;
+        const MegaSmem sm = mega_smem_fit(E, V, D, CL, L);
+        const int64_t bytes = static_cast<int64_t>(CL) * sm.per_step * MG_SLOT + (4 * MG_MAX_LAYERS + 1) * sizeof(PackPhase) + 256;
+        if (bytes > need) need = bytes;
     }
+    return need;
+}
+
+#define CB200_MEGA_DISPATCH(FN, ...)                                            \
+    (CL == 8 ? (D == 16 ? FN<16, 8>(__VA_ARGS__) : D == 32 ? FN<32, 8>(__VA_ARGS__) : FN<64, 8>(__VA_ARGS__)) \
+             : (D == 16 ? FN<16, 4>(__VA_ARGS__) : D == 32 ? FN<32, 4>(__VA_ARGS__) : FN<64, 4>(__VA_ARGS__)))
+
+// Clusters of `CL` CTAs of the persistent decode kernel that are co-resident on the current device.
+int decode_mega_capacity(int E, int H, int V, int D, int L, int CL) {
+    if (!mega_shape_ok(E, H, D, V, L, CL)) return 0;
+    const MegaSmem sm = mega_smem_fit(E, V, D, CL, L);
+    return CB200_MEGA_DISPATCH(mega_capacity, sm);
+}
+
+// cluster_size 0 = automatic: 8-CTA clusters (each weight is read by fewer CTAs) when the batch fits one wave of
+// them, otherwise 4-CTA clusters (more of them are co-resident: GPCs rarely have a multiple of 8 SMs free).
+// `stream_ws` receives the packed weight stream (decode_mega_stream_bytes).
+int decode_mega(MegaArgs args, int D, int max_clusters, int cluster_size, uint8_t* stream_ws, int64_t stream_ws_bytes,
+                cudaStream_t s) {
+    CB200_REQUIRE(decode_mega_supported(args.E, args.H, D, args.V, args.L), "shape not supported by the cluster decode kernel");
+    CB200_REQUIRE(cluster_size == 0 || cluster_size == 4 || cluster_size == 8, "cluster size must be 0 (auto), 4 or 8");
+    if (args.B == 0 || args.steps == 0) return 0;
+    int CL = cluster_size;
+    if (CL == 0) {
+        const int cap8 = decode_mega_capacity(args.E, args.H, args.V, D, args.L, 8);
+        const int cap4 = decode_mega_capacity(args.E, args.H, args.V, D, args.L, 4);
+        CL = (cap8 > 0 && (args.B <= cap8 * MG_ROWS || cap4 <= 0)) ? 8 : 4;
+    }
+    CB200_REQUIRE(mega_shape_ok(args.E, args.H, D, args.V, args.L, CL), "cluster size %d does not fit this shape", CL);
+    const int resident = decode_mega_capacity(args.E, args.H, args.V, D, args.L, CL);
+    CB200_REQUIRE(resident >= 1, "the cluster decode kernel does not fit on this device");
+    const int ncl = mega_cluster_count(args.B, resident, max_clusters);
+    const MegaSmem sm = mega_smem_fit(args.E, args.V, D, CL, args.L);
+    // ---- pack the weight stream ----
+    const int E = args.E, F = args.F, HS = E / CL, FS = F / CL;
+    std::vector<PackPhase> table;
+    int slot = 0;
+    auto add = [&](long long w, long long b, int K, int ntiles, int ksplit, int tpp, int pstride, int cols, int limit, int sub) {
+        PackPhase p{w, b, K, ntiles, ksplit, tpp, pstride, cols, limit, sub, slot, ntiles * ksplit * sub};
+        slot += p.nslots;
+        table.push_back(p);
+    };
+    for (int l = 0; l < args.L; ++l) {
+        const MegaLayer& w = args.layers[l];
+        add(w.attn_w, w.attn_b, E, 3 * HS / 8, 1, HS / 8, E, HS, 3 * E - 1, sm.sub_e);
+        add(w.proj_w, w.proj_b, E, HS / 8, 1, HS / 8, 0, HS, E - 1, sm.sub_e);
+        add(w.fc_w, w.fc_b, E, FS / 8, 1, FS / 8, 0, FS, F - 1, sm.sub_e);
+        add(w.proj2_w, w.proj2_b, F, HS / 8, sm.ks_proj2, HS / 8, 0, HS, E - 1, sm.sub_p2);
+    }
+    add(args.wte_sh, -1, E, sm.vs / 8, 1, sm.vs / 8, 0, sm.vs, args.V - 1, sm.sub_e);
+    CB200_REQUIRE(slot == sm.per_step, "weight stream plan mismatch: %d slots, expected %d", slot, sm.per_step);
+    const int64_t stream_bytes = static_cast<int64_t>(CL) * sm.per_step * MG_SLOT;
+    const int64_t table_off = (stream_bytes + 255) & ~int64_t(255);
+    CB200_REQUIRE(stream_ws != nullptr && stream_ws_bytes >= table_off + static_cast<int64_t>(table.size() * sizeof(PackPhase)),
+                  "weight stream workspace too small");
+    CB200_CUDA_OK(cudaMemcpyAsync(stream_ws + table_off, table.data(), table.size() * sizeof(PackPhase), cudaMemcpyHostToDevice, s));
+    CB200_CUDA_OK(cudaStreamSynchronize(s));       // `table` is pageable host memory that dies with this frame
+    mega_pack_kernel<<<dim3(sm.per_step, CL), 288, 0, s>>>(args.shadow, args.params, stream_ws,
+                                                            reinterpret_cast<const PackPhase*>(stream_ws + table_off),
+                                                            static_cast<int>(table.size()), sm.per_step);
+    CB200_CUDA_OK(cudaGetLastError());
+    note_launch(1);
+    args.wstream = stream_ws;
+    if (args.prof != nullptr) CB200_CUDA_OK(cudaMemsetAsync(args.prof, 0, 16 * sizeof(long long), s));
+    return CB200_MEGA_DISPATCH(launch_mega, args, sm, ncl, s);
 }
 
 }  // namespace cb200

@@ -461,8 +461,9 @@ static int backward(Engine& e, int stage, cudaStream_t s) {
 // ---------------------------------------------------------------------------
 // Generation
 // ---------------------------------------------------------------------------
-static int g_decode_impl = 1;           // 0: persistent cluster kernel when the shape allows it, 1: per-step kernels + CUDA graph
+static int g_decode_impl = 0;           // 0: persistent cluster kernel when the shape allows it, 1: per-step kernels + CUDA graph
 static long long* g_decode_prof = nullptr;   // device buffer of 16 counters for the cluster kernel's phase profile
+static int g_decode_cluster_size = 0;    // 0 = automatic, 4 or 8 CTAs per cluster
 static int g_decode_max_clusters = 0;   // > 0 caps the clusters of the persistent kernel (tests)
 
 struct DecodeBuffers {
@@ -470,6 +471,8 @@ struct DecodeBuffers {
     float *logits, *uniforms;
     bf16 *x, *x1, *qkv, *att, *x2, *mln, *u, *gl, *y;
     float* stats;
+    uint8_t* mega_stream;      // packed weight stream of the persistent cluster kernel
+    int64_t mega_stream_bytes;
 };
 
 static int64_t carve_decode(const Engine& e, uint8_t* base, int B, int steps, DecodeBuffers& d) {
@@ -491,6 +494,8 @@ static int64_t carve_decode(const Engine& e, uint8_t* base, int B, int steps, De
     d.mln = b.take<bf16>(B * E);
     d.u = b.take<bf16>(B * F);
     d.gl = b.take<bf16>(B * F);
+    d.mega_stream_bytes = decode_mega_supported(e.E, e.H, e.D, e.V, e.L) ? decode_mega_stream_bytes(e.E, e.H, e.D, e.V, e.L) : 0;
+    d.mega_stream = b.take<uint8_t>(d.mega_stream_bytes);
     return (b.off + 255) & ~int64_t(255);
 }
 
@@ -588,7 +593,7 @@ static int generate_on(Engine& e, bf16* cache, int t_max, uint8_t* ws, int64_t w
             w.attn_w = static_cast<uint32_t>(e.shT_attn[l]); w.proj_w = static_cast<uint32_t>(e.shT_proj[l]);
             w.fc_w = static_cast<uint32_t>(e.shT_fc[l]); w.proj2_w = static_cast<uint32_t>(e.shT_proj2[l]);
         }
-        if ((rc = decode_mega(m, e.D, g_decode_max_clusters, s))) return rc;
+        if ((rc = decode_mega(m, e.D, g_decode_max_clusters, g_decode_cluster_size, d.mega_stream, d.mega_stream_bytes, s))) return rc;
     } else {
     // step 0 runs eagerly (also configures kernel attributes outside of capture); the rest replays a graph
     if ((rc = decode_step(e, d, cache, t_max, B, steps, temperature, seed, seq_base, s))) return rc;
@@ -886,19 +891,21 @@ int cb200_attention_bwd(const void* qkv, const void* out, const void* dout, cons
                          static_cast<cudaStream_t>(stream));
 }
 
-int cb200_set_decode_impl(int impl, int max_clusters) {
+int cb200_set_decode_impl(int impl, int max_clusters, int cluster_size) {
     CB200_REQUIRE(impl == 0 || impl == 1, "decode implementation must be 0 (persistent cluster kernel) or 1 (per-step kernels)");
     CB200_REQUIRE(max_clusters >= 0, "max_clusters must be >= 0");
+    CB200_REQUIRE(cluster_size == 0 || cluster_size == 4 || cluster_size == 8, "cluster_size must be 0 (automatic), 4 or 8");
     g_decode_impl = impl;
     g_decode_max_clusters = max_clusters;
+    g_decode_cluster_size = cluster_size;
     return 0;
 }
 
-int cb200_decode_cluster_capacity(void* engine) {
+int cb200_decode_cluster_capacity(void* engine, int cluster_size) {
     if (!engine) return -1;
     Engine& e = *static_cast<Engine*>(engine);
-    if (!decode_mega_supported(e.E, e.H, e.D, e.V, e.L)) return 0;
-    return decode_mega_capacity(e.E, e.V, e.D);
+    if (cluster_size != 4 && cluster_size != 8) return 0;
+    return decode_mega_capacity(e.E, e.H, e.V, e.D, e.L, cluster_size);
 }
 
 int cb200_set_decode_profile(void* counters) {

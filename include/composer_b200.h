@@ -152,16 +152,17 @@ int cb200_attention_bwd(const void* qkv, const void* out, const void* dout, cons
  * 1 = warp-level mma.sync (kept for A/B measurements and as a cross-check in the tests). */
 int cb200_set_attention_bwd_impl(int impl);
 /* Selects how cb200_generate runs: 0 (default) = one persistent thread-block-cluster kernel for the whole
- * generation when the shape allows it (embedding_size 256 or 512, heads a multiple of 8), 1 = one CUDA graph
- * of per-layer kernels per step.  max_clusters > 0 caps the clusters of the persistent kernel (tests). */
-int cb200_set_decode_impl(int impl, int max_clusters);
+ * generation when the shape allows it (embedding_size 256 or 512, heads a multiple of 4), 1 = one CUDA graph
+ * of per-layer kernels per step.  max_clusters > 0 caps the clusters of the persistent kernel (tests);
+ * cluster_size 0 = automatic, 4 or 8 = CTAs per cluster. */
+int cb200_set_decode_impl(int impl, int max_clusters, int cluster_size);
 /* Diagnostic: device buffer of 16 int64 that receives the cycles the first CTA of the persistent decode kernel
  * spent in each phase (embedding, ln_1, c_attn, attention, barrier, c_proj, barrier, ln_2 + c_fc, barrier,
  * mlp c_proj, barrier, ln_f + logits, barrier, sampling, barrier), summed over the generation.  NULL disables. */
 int cb200_set_decode_profile(void* counters);
-/* Clusters (8 CTAs, up to 16 sequences each) of the persistent decode kernel that are co-resident on the current
- * device; 0 when the engine's shape is served by the per-step kernels instead. */
-int cb200_decode_cluster_capacity(void* engine);
+/* Clusters of `cluster_size` (4 or 8) CTAs, up to 16 sequences each, of the persistent decode kernel that are
+ * co-resident on the current device; 0 when the engine's shape is not served at that cluster size. */
+int cb200_decode_cluster_capacity(void* engine, int cluster_size);
 /* Keep masks (1 = kept) exactly as the kernels draw them; for parity tests with dropout on. */
 int cb200_attention_dropout_mask(uint8_t* mask, int B, int T, int H, float dropout_rate, uint64_t seed, uint32_t step,
                                  uint32_t layer, void* stream);

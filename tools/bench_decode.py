@@ -1,6 +1,7 @@
 '''Times cached generation (BASELINE.json configs[2] shape by default) under both decode implementations.
 
-    python tools/bench_decode.py [B [steps [impls...]]]     impls: 0 = persistent cluster kernel, 1 = per-step graph
+    python tools/bench_decode.py [B [steps [impls...]]]     impls: 1 = per-step graph, 0 = persistent cluster
+    kernel (automatic cluster size), 8 / 4 = persistent kernel with that cluster size
 '''
 import os
 import sys
@@ -22,9 +23,10 @@ model = Transformer(390, E, 1024, L, H, False, 0.0, 0.02, 0.1, 0.1, 1e-5, True, 
 prompt = np.random.default_rng(99).integers(0, 390, size=(B, 1))
 weights = 2 * (model.count_params() - 1024 * E + E)
 model.generate(prompt[:2], 4)
-print('co-resident clusters of the persistent kernel:', _lib.call('cb200_decode_cluster_capacity', model._engine), flush=True)
+print('co-resident clusters of the persistent kernel: %d x 8 CTAs, %d x 4 CTAs' % (
+    _lib.call('cb200_decode_cluster_capacity', model._engine, 8), _lib.call('cb200_decode_cluster_capacity', model._engine, 4)), flush=True)
 for impl in impls:
-    _lib.call('cb200_set_decode_impl', impl, 0)
+    _lib.call('cb200_set_decode_impl', 1 if impl == 1 else 0, 0, impl if impl in (4, 8) else 0)
     model.generate(prompt, 16, temperature=1.0, seed=7)
     torch.cuda.synchronize()
     for length in sorted({N // 4, N}):
@@ -38,19 +40,19 @@ for impl in impls:
                  out[0, :6].tolist()), flush=True)
 
 # phase profile of the persistent kernel (cycles of cluster 0 / CTA 0 / thread 0)
-if 0 in impls:
+for size in [v for v in impls if v != 1]:
     import ctypes
     names = ['embed', 'ln_1', 'c_attn', 'attention', 'barrier A', 'c_proj', 'barrier B', 'ln_2 + c_fc', 'barrier C',
              'mlp c_proj', 'barrier D', 'ln_f + logits', 'barrier E', 'sample', 'barrier F']
     counters = torch.zeros(16, dtype=torch.int64, device='cuda')
-    _lib.call('cb200_set_decode_impl', 0, 0)
+    _lib.call('cb200_set_decode_impl', 0, 0, size if size in (4, 8) else 0)
     _lib.call('cb200_set_decode_profile', ctypes.c_void_p(counters.data_ptr()))
     model.generate(prompt, N, temperature=1.0, seed=7)
     torch.cuda.synchronize()
     _lib.call('cb200_set_decode_profile', None)
     c = counters.cpu().tolist()
-    total = sum(c)
-    print('phase profile over %d steps (cycles per step; per layer for block phases):' % N)
+    total = sum(c) or 1
+    print('phase profile, cluster size %s, over %d steps (cycles per step; per layer for block phases):' % (size or 'auto', N))
     for i, name in enumerate(names):
         per = c[i] / N / (L if 1 <= i <= 10 else 1)
         print('  %-14s %9.0f cyc  %5.1f%%' % (name, per, 100.0 * c[i] / total))
