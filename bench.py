@@ -387,6 +387,22 @@ def dominant_kernel_roofline(model, B, T, peaks, peak_kind, step_seconds):
     return roofline, breakdown
 
 
+def decode_implementation(model, batch):
+    '''Which decode path cb200_generate takes for this batch (mirrors decode_mega's choice of cluster size).'''
+
+    from composer_b200 import _lib
+
+    cap8 = _lib.call('cb200_decode_cluster_capacity', model._engine, 8)
+    cap4 = _lib.call('cb200_decode_cluster_capacity', model._engine, 4)
+    if cap8 <= 0 and cap4 <= 0:
+        return {'kernel': 'per-step kernels replayed as a CUDA graph'}
+    size = 8 if cap8 > 0 and (batch <= cap8 * 8 or cap4 <= 0) else 4
+    cap = cap8 if size == 8 else cap4
+    clusters = min(batch, cap) if min(batch, cap) * 8 >= batch else -(-batch // 8)
+    return {'kernel': 'decode_mega_kernel (one persistent launch per generation)', 'cluster_size': size,
+            'clusters': clusters, 'co_resident_clusters': cap, 'launches_per_generation': 3}
+
+
 def generation_benchmark(model, world, rank, device, dist):
     '''configs[2]: 256 sequences sharded over the GPUs, prompt 1, 1024 events, temperature 1.0, KV cache.'''
 
@@ -425,7 +441,8 @@ def generation_benchmark(model, world, rank, device, dist):
             'roofline': {'bound': 'hbm', 'achieved': bytes_per_gpu / seconds / 1e9, 'peak': peaks['hbm_gbs'],
                          'unit': 'GB/s', 'frac': bytes_per_gpu / seconds / 1e9 / peaks['hbm_gbs'], 'traffic': None,
                          'peak_source': kind},
-            'sample_ids': out[0, :8].tolist()}
+            'sample_ids': out[0, :8].tolist(),
+            'implementation': decode_implementation(gen_model, per_rank)}
 
 
 def main():

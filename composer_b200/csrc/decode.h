@@ -41,9 +41,10 @@ struct MegaArgs {
     int32_t* out_ids;              // [B, steps]
     float* uniforms;               // [B, steps] or null
     float* logits_out;             // [B, V] logits of the last step, or null
-    long long* prof;               // 16 cycle counters (phase profile of cluster 0), or null
+    long long* prof;               // 24 cycle counters (phase profile of cluster 0: 15 phases, then ring waits per phase), or null
     long long layer_stride;        // elements per layer of the cache
     int B, E, H, F, V, L, t_max, steps, use_ln, greedy, seq_base;
+    int l2_hints;                  // 1: cache reads evict-first, weight stream evict-last (set by decode_mega)
     float eps, scale_log2, inv_temperature;
     uint32_t seed_lo, seed_hi;
     uint32_t wte, wpe, lnf_g, lnf_b;   // offsets into params

@@ -52,8 +52,8 @@ constexpr int MG_ROWS = 8;          // sequences per cluster: rows 0 .. 7 of the
 #endif
 // tokens per KV ring stage (one bulk copy of k|v records): 4 KB whatever the head size
 #define MG_CT(D) ((D) == 64 ? 16 : (D) == 32 ? 32 : MG_CT16)
-constexpr int MG_SLOT_W = 4096;            // weight bytes of a slot: 8 output columns x 256 of K in B-fragment order
-constexpr int MG_SLOT = MG_SLOT_W + 32;    // + the 8 biases of those columns
+constexpr int MG_SLOT_W = 4096;            // weight bytes of a slot: 16 output columns x 128 of K in A-fragment order
+constexpr int MG_SLOT = MG_SLOT_W + 64;    // + the 16 biases of those columns
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -78,10 +78,35 @@ __device__ __forceinline__ void st_cluster_v2(uint32_t addr, uint32_t x, uint32_
 __device__ __forceinline__ void st_cluster_u32(uint32_t addr, uint32_t v) {
     asm volatile("st.shared::cluster.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+// Copies global -> shared are 16-byte cp.async (LDGSTS) issued by the whole warp, 512 contiguous bytes per
+// instruction, completion reported to an mbarrier: measured here, one SM ingests ~3x more through this path than
+// through cp.async.bulk (whose per-SM engine moved ~22 B/clk whatever the copy size or the source, L2 or HBM).
+// L2 eviction policies: the KV cache is streamed once per step (evict first), the weight stream is re-read by every
+// cluster every step (evict last), so that 1 GB of cache reads per step does not push the 13 MB of weights out.
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_normal() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void cp_async_16_hint(uint32_t dst, const void* src, bool valid, uint64_t policy) {
+    const int src_bytes = valid ? 16 : 0;          // src-size 0 => the 16 bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;" ::"r"(dst), "l"(src), "r"(src_bytes),
+                 "l"(policy)
                  : "memory");
+}
+// The mbarrier receives one arrival from this thread once all its cp.async issued so far have landed.
+__device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ uint4 ldg_nc_v4_keep(const void* p) {
     uint4 r;
@@ -98,123 +123,202 @@ __device__ __forceinline__ void mma_16816(float (&d)[4], uint32_t a0, uint32_t a
 }
 
 struct MegaSmem {        // shared-memory layout and weight-stream plan (computed on the host, identical in every CTA)
-    int pe, pf;          // row pitch of the [16, E] and [16, F] bf16 buffers (2E + 64, 2F + 64: conflict-free A reads)
-    int buf0, buf1, bufn, bufg, qkv, red, ring, wring, bars, wseq, toks, total;
-    int nst;             // KV ring stages per warp
-    int nslot;           // weight ring slots
-    int zp;              // floats per row of the logits matrix (aliases the KV ring of CTA 0)
-    int vs;              // vocabulary rows per CTA (whole n-tiles)
-    int ks_proj2;        // K split of the mlp c_proj
-    int sub_e, sub_p2;   // 256-wide K pieces per unit: K = E phases, mlp c_proj
-    int n_attn, n_proj, n_fc, n_proj2, n_logits;   // slots per phase
-    int per_layer, per_step;                       // slots per decoder block / per step
+    int pe, pf;          // row pitch of the [8, E] and [8, F] bf16 buffers (2E + 64, 2F + 64: conflict-free operand reads)
+    int buf0, buf1, bufn, bufg, qkv, red, zbuf, jobtab, ring, bars, toks, total;
+    int nst;             // ring stages per warp ...
+    int nst_extra;       // ... plus one more for the first nst_extra warps (whatever still fits)
+    int zp;              // floats per row of the logits matrix (CTA 0)
+    int vs;              // vocabulary rows per CTA (whole 16-row tiles)
+    int ks_attn, ks_proj, ks_fc, ks_proj2, ks_logits;        // K split of each phase
+    int n_attn, n_proj, n_fc, n_proj2, n_logits;             // slots per phase
+    int per_layer, per_step;                                 // slots per decoder block / per step
 };
 
-// One linear layer as this CTA sees it: `ntiles` n-tiles of 8 output columns, K split `ksplit` ways; unit u =
-// (n-tile u % ntiles, K part u / ntiles) belongs to warp u % 16 and occupies `sub` consecutive slots of the weight
-// stream starting at pos0 + u * sub.
+// One linear layer as this CTA sees it, computed transposed (out^T = W x^T) so that the 16 rows of an m16n8k16 MMA
+// are 16 output columns and its 8 columns are the <= 8 sequences of the cluster: `ntiles` tiles of 16 output columns,
+// K split `ksplit` ways; unit u = (tile u % ntiles, K part u / ntiles) belongs to warp u % 16 and occupies `sub`
+// consecutive slots (128 of K each) of the weight stream.
 struct Phase {
-    int pos0, ntiles, ksplit, sub;
+    int ntiles, ksplit, sub;
 };
 
-struct WRing {
-    uint8_t* base;
-    uint64_t* full;
-    volatile int* seq;       // stream position whose copy was last issued into each slot
-    const uint8_t* src;      // this CTA's weight stream (one step; it repeats every step)
-    int nslot, per_step, total;
+// ---------------------------------------------------------------------------
+// Per-warp job ring.  Everything a warp reads from global memory on the hot path, the weight slots of its GEMM
+// units and the KV stages of its (sequence, head) pairs, is one sequence of TMA bulk copies in the warp's own
+// program order, which is fully static (it depends on the step, not on data).  The warp owns NST stages of
+// MG_STAGE bytes; after consuming job k it issues job k + NST into the stage it has just freed, so its next
+// NST jobs are always in flight, across phase and barrier boundaries: the weights of a GEMM phase were requested
+// while the previous phase (or the attention) was still running.
+// ---------------------------------------------------------------------------
+constexpr int MG_STAGE = MG_SLOT;          // >= the 4 KB of a KV stage
+
+struct JobPlan {           // what the cursor needs to enumerate this warp's jobs (uniform per warp)
+    const uint8_t* wsrc;   // this CTA's weight stream (one step; it repeats every step)
+    const __nv_bfloat16* cache;
+    long long layer_stride;
+    uint64_t w_policy, kv_policy;
+    const uint16_t* tab;   // this warp's weight jobs of one decoder block: slots before the attention (c_attn), slots
+                           // after it (c_proj, c_fc, mlp c_proj), then the logits slots; relative stream positions
+    int n_pre, n_post, n_logit;
+    int warp, steps, L, s0, nmine, hpc_shift, HPC, H, crank, t_max, per_layer;
+};
+constexpr int MG_TAB = 32;                 // table entries per warp: [0, 8) pre, [8, 24) post, [24, 32) logits
+
+struct JobCursor {
+    int step, l, k, pi, c;                 // k: weight jobs of this block issued so far; (pi, c): next KV job
 };
 
-// A slot is re-armed by whichever warp consumed its previous occupant, so a waiter may be several ring turns ahead
-// of the slot's mbarrier, and an mbarrier wait only tells phases apart by parity: first wait (on the sequence word)
-// until the copy of position s has been issued into the slot, then for its bytes.
-__device__ __forceinline__ const uint8_t* wring_wait(const WRing& r, int s) {
-    const int idx = s % r.nslot;
-    uint32_t spins = 0;
-    while (r.seq[idx] != s) {
-        if (++spins > (1u << 26)) __trap();
+struct JobRing {
+    uint8_t* base;         // this warp's stages
+    uint64_t* bars;        // this warp's mbarriers
+    uint32_t count;        // jobs consumed so far
+    int nst;
+    JobCursor cur;         // next job to issue (always `nst` jobs ahead of `count`)
+    long long* wait_prof;  // diagnostic accumulator or null
+};
+
+__device__ __forceinline__ int units_of(int warp, int n) { return n > warp ? (n - warp + MG_WARPS - 1) / MG_WARPS : 0; }
+
+// Issues the job at the cursor into `stage` (the whole warp: 8 x 512 bytes + completion arrival on `bar`, whose
+// phase needs 32 arrivals) and advances the cursor.  D selects the KV geometry.  A KV stage is zero-filled beyond
+// its tokens, so stale rows never reach an MMA.
+template <int D>
+__device__ __forceinline__ void job_issue(const JobPlan& p, JobCursor& c, uint8_t* stage, uint64_t* bar, int lane) {
+    constexpr int CT = MG_CT(D);
+    const uint32_t dst = smem_u32(stage) + lane * 16;
+    int wpos = -1;                                  // weight job: stream position
+    for (;;) {
+        if (c.step >= p.steps) return;
+        if (c.l < p.L) {
+            if (c.k < p.n_pre) { wpos = c.l * p.per_layer + p.tab[c.k]; ++c.k; break; }
+            const int nchunks = (c.step + CT - 1) / CT;
+            if (c.pi < p.nmine && nchunks > 0) break;          // KV job (pi, c)
+            const int kk = c.k - p.n_pre;
+            if (kk < p.n_post) { wpos = c.l * p.per_layer + p.tab[8 + kk]; ++c.k; break; }
+            ++c.l; c.k = 0; c.pi = 0; c.c = 0;
+        } else {
+            if (c.k < p.n_logit) { wpos = p.L * p.per_layer + p.tab[24 + c.k]; ++c.k; break; }
+            ++c.step; c.l = 0; c.k = 0; c.pi = 0; c.c = 0;
+        }
     }
-    __threadfence_block();
-    mbar_wait(&r.full[idx], (s / r.nslot) & 1);
-    return r.base + idx * MG_SLOT;
+    if (wpos >= 0) {
+        const uint8_t* src = p.wsrc + static_cast<size_t>(wpos) * MG_SLOT + lane * 16;
+#pragma unroll
+        for (int i = 0; i < MG_SLOT_W / 512; ++i) cp_async_16_hint(dst + i * 512, src + i * 512, true, p.w_policy);
+        if (lane < (MG_SLOT - MG_SLOT_W) / 16) cp_async_16_hint(dst + MG_SLOT_W, src + MG_SLOT_W, true, p.w_policy);
+    } else {
+        const int q = p.warp + MG_WARPS * c.pi;
+        const int b = p.s0 + (q >> p.hpc_shift), h = p.crank * p.HPC + (q & (p.HPC - 1));
+        const size_t off = ((static_cast<size_t>(b) * p.H + h) * p.t_max + static_cast<size_t>(c.c) * CT) * (2 * D);
+        const int pieces = min(CT, c.step - c.c * CT) * (4 * D / 16);             // 16-byte pieces that exist
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(p.cache + static_cast<size_t>(c.l) * p.layer_stride + off);
+#pragma unroll
+        for (int i = 0; i < CT * 4 * D / 512; ++i) {
+            const int idx = i * 32 + lane;
+            cp_async_16_hint(dst + i * 512, src + (idx < pieces ? idx * 16 : 0), idx < pieces, p.kv_policy);
+        }
+        if (++c.c == (c.step + CT - 1) / CT) { c.c = 0; ++c.pi; }
+    }
+    cp_async_arrive(bar);
 }
 
-__device__ __forceinline__ void wring_issue(const WRing& r, int s) {     // one thread
-    const int idx = s % r.nslot;
-    mbar_expect_tx(&r.full[idx], MG_SLOT);
-    bulk_g2s(smem_u32(r.base + idx * MG_SLOT), r.src + static_cast<size_t>(s % r.per_step) * MG_SLOT, MG_SLOT, &r.full[idx]);
-    __threadfence_block();
-    r.seq[idx] = s;
+// Waits for the warp's next job and returns its stage.
+__device__ __forceinline__ uint8_t* ring_acquire(const JobRing& r) {
+    const uint32_t st = r.count % r.nst;
+    if (r.wait_prof != nullptr) {                  // diagnostic: cycles this thread waits for its jobs
+        const long long t0 = clock64();
+        mbar_wait(&r.bars[st], (r.count / r.nst) & 1);
+        *r.wait_prof += clock64() - t0;
+    } else {
+        mbar_wait(&r.bars[st], (r.count / r.nst) & 1);
+    }
+    return r.base + st * MG_STAGE;
 }
 
-// The warp has read slot s: lane 0 re-arms it with the stream position one ring ahead.
-__device__ __forceinline__ void wring_refill(const WRing& r, int s, int lane) {
+// The warp is done with the stage of its current job: it is re-armed with the job NST ahead.
+template <int D>
+__device__ __forceinline__ void ring_release(JobRing& r, const JobPlan& p, int lane) {
     __syncwarp();
-    if (lane == 0 && s + r.nslot < r.total) wring_issue(r, s + r.nslot);
+    const uint32_t st = r.count % r.nst;
+    job_issue<D>(p, r.cur, r.base + st * MG_STAGE, &r.bars[st], lane);
+    ++r.count;
 }
 
-// acc += A[8, 256 of K] x slot: a0 points at (row g, first k of the piece + 8 * tig); MMA rows 8 .. 15 are zero.
-__device__ __forceinline__ void slot_mma(float (&acc)[4], const uint8_t* slot, const uint8_t* a0, int lane) {
-    uint4 w[8];
+// acc (16 output columns x 8 sequences) += slot (16 x 128 weights, A operand, one 16-byte read per MMA) times
+// x^T: b0 points at (sequence g, first k of the slot + 8 * tig) of the activations (B operand: the k order inside
+// a 32-wide block is permuted identically on both sides).
+__device__ __forceinline__ void slot_mma(float (&acc)[4], const uint8_t* slot, const uint8_t* b0, int lane) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) w[i] = *reinterpret_cast<const uint4*>(slot + i * 512 + lane * 16);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const uint4 xa = *reinterpret_cast<const uint4*>(a0 + i * 64);
-        mma_16816(acc, xa.x, 0u, xa.y, 0u, w[i].x, w[i].y);
-        mma_16816(acc, xa.z, 0u, xa.w, 0u, w[i].z, w[i].w);
+    for (int i = 0; i < 4; ++i) {
+        const uint4 x = *reinterpret_cast<const uint4*>(b0 + i * 64);
+        const uint4 wa = *reinterpret_cast<const uint4*>(slot + (2 * i * 32 + lane) * 16);
+        const uint4 wb = *reinterpret_cast<const uint4*>(slot + ((2 * i + 1) * 32 + lane) * 16);
+        mma_16816(acc, wa.x, wa.y, wa.z, wa.w, x.x, x.y);
+        mma_16816(acc, wb.x, wb.y, wb.z, wb.w, x.z, x.w);
     }
 }
 
-// Runs this warp's units of `ph` on A[16, K] (bf16 in shared memory, row pitch `pitch` bytes).  K-split partials
-// meet in `red`; the warp that owns K part 0 of an n-tile calls epi(nt, acc, bias) with the complete sums:
-// acc[0], acc[1] = (row g, columns nt*8 + 2*tig, +1).  With ksplit > 1 all 16 warps must call this (it contains
-// a __syncthreads).
-template <typename Epi>
-__device__ __forceinline__ void run_phase(const Phase& ph, const uint8_t* A, int pitch, const WRing& wr, float* red,
-                                          int warp, int lane, Epi epi) {
+// Runs this warp's units of `ph` on the activations X[8, K] (bf16 in shared memory, row pitch `pitch` bytes); the
+// weight slots are the warp's next jobs.  K-split partials meet in `red`.  The warp that owns K part 0 of a tile
+// calls epi(col, seq, lo, hi) once per lane with the complete sums (bias added) of sequence `seq` at output columns
+// (col, col + 1) = lo and (col + 8, col + 9) = hi, col relative to this CTA's slice.  All 16 warps must call this
+// (it may contain a __syncthreads).
+template <int D, typename Epi>
+__device__ __forceinline__ void run_phase(const Phase& ph, const uint8_t* X, int pitch, JobRing& ring, const JobPlan& plan,
+                                          float* red, int warp, int lane, Epi epi) {
     const int g = lane >> 2, tig = lane & 3;
-    const uint8_t* a0 = A + g * pitch + tig * 16;
-    if (ph.ksplit == 1) {
-        for (int u = warp; u < ph.ntiles; u += MG_WARPS) {
+    const uint8_t* b0 = X + g * pitch + tig * 16;
+    auto finish = [&](int nt, float (&acc)[4], float bias_lo, float bias_hi) {
+        acc[0] += bias_lo; acc[1] += bias_lo; acc[2] += bias_hi; acc[3] += bias_hi;
+        // lanes g and g ^ 1 trade one sequence each: afterwards a lane holds two adjacent columns of one sequence
+        const bool odd = g & 1;
+        const float r0 = __shfl_xor_sync(0xffffffffu, odd ? acc[0] : acc[1], 4);
+        const float r1 = __shfl_xor_sync(0xffffffffu, odd ? acc[2] : acc[3], 4);
+        const float2 lo = odd ? make_float2(r0, acc[1]) : make_float2(acc[0], r0);
+        const float2 hi = odd ? make_float2(r1, acc[3]) : make_float2(acc[2], r1);
+        epi(nt * 16 + (g & ~1), 2 * tig + (odd ? 1 : 0), lo, hi);
+    };
+    const int nunits = ph.ntiles * ph.ksplit;
+    if (nunits > MG_WARPS) {                       // several units per warp (then ksplit == 1)
+        for (int u = warp; u < nunits; u += MG_WARPS) {
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
-            float2 bias = make_float2(0.f, 0.f);
+            float bias_lo = 0.f, bias_hi = 0.f;
             for (int j = 0; j < ph.sub; ++j) {
-                const int s = ph.pos0 + u * ph.sub + j;
-                const uint8_t* slot = wring_wait(wr, s);
-                if (j == 0) bias = *reinterpret_cast<const float2*>(slot + MG_SLOT_W + tig * 8);
-                slot_mma(acc, slot, a0 + j * 512, lane);
-                wring_refill(wr, s, lane);
+                const uint8_t* slot = ring_acquire(ring);
+                if (j == 0) {
+                    bias_lo = *reinterpret_cast<const float*>(slot + MG_SLOT_W + g * 4);
+                    bias_hi = *reinterpret_cast<const float*>(slot + MG_SLOT_W + (g + 8) * 4);
+                }
+                slot_mma(acc, slot, b0 + j * 256, lane);
+                ring_release<D>(ring, plan, lane);
             }
-            epi(u, acc, bias);
+            finish(u, acc, bias_lo, bias_hi);
         }
         return;
     }
-    // K split: every warp has at most one unit (ntiles * ksplit <= 16)
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    float2 bias = make_float2(0.f, 0.f);
+    float bias_lo = 0.f, bias_hi = 0.f;
     const int nt = warp % ph.ntiles, ks = warp / ph.ntiles;
-    const bool active = warp < ph.ntiles * ph.ksplit;
+    const bool active = warp < nunits;
     if (active) {
         for (int j = 0; j < ph.sub; ++j) {
-            const int s = ph.pos0 + warp * ph.sub + j;
-            const uint8_t* slot = wring_wait(wr, s);
-            if (j == 0) bias = *reinterpret_cast<const float2*>(slot + MG_SLOT_W + tig * 8);
-            slot_mma(acc, slot, a0 + (ks * ph.sub + j) * 512, lane);
-            wring_refill(wr, s, lane);
+            const uint8_t* slot = ring_acquire(ring);
+            if (j == 0) {
+                bias_lo = *reinterpret_cast<const float*>(slot + MG_SLOT_W + g * 4);
+                bias_hi = *reinterpret_cast<const float*>(slot + MG_SLOT_W + (g + 8) * 4);
+            }
+            slot_mma(acc, slot, b0 + (ks * ph.sub + j) * 256, lane);
+            ring_release<D>(ring, plan, lane);
         }
-        if (ks > 0) {
-            float* r = red + (((ks - 1) * ph.ntiles + nt) * 32 + lane) * 2;
-            *reinterpret_cast<float2*>(r) = make_float2(acc[0], acc[1]);
-        }
+        if (ks > 0) *reinterpret_cast<float4*>(red + (((ks - 1) * ph.ntiles + nt) * 32 + lane) * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
     }
-    __syncthreads();
+    if (ph.ksplit > 1) __syncthreads();
     if (active && ks == 0) {
         for (int k2 = 1; k2 < ph.ksplit; ++k2) {
-            const float2 p = *reinterpret_cast<const float2*>(red + (((k2 - 1) * ph.ntiles + nt) * 32 + lane) * 2);
-            acc[0] += p.x; acc[1] += p.y;
+            const float4 p = *reinterpret_cast<const float4*>(red + (((k2 - 1) * ph.ntiles + nt) * 32 + lane) * 4);
+            acc[0] += p.x; acc[1] += p.y; acc[2] += p.z; acc[3] += p.w;
         }
-        epi(nt, acc, bias);
+        finish(nt, acc, bias_lo, bias_hi);
     }
 }
 
@@ -368,7 +472,7 @@ decode_mega_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ M
     constexpr int CH = D / 8;                     // 16-byte chunks per head row
     constexpr int CT = MG_CT(D);                  // tokens per KV ring stage
     constexpr int REC = 4 * D;                    // bytes of one cached token of one head: k row | v row
-    constexpr int STAGE = CT * REC;
+    static_assert(CT * REC <= MG_STAGE, "a KV stage must fit a ring stage");
     constexpr int NT_S = CT / 8;                  // score n-tiles per stage
     constexpr int NT_O = D / 8;                   // output n-tiles
     extern __shared__ __align__(128) uint8_t smem[];
@@ -396,29 +500,62 @@ decode_mega_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ M
     uint8_t* qkvs = smem + sm.qkv;                 // q | k | v of this CTA's heads, [16][3 * HS] bf16
     float* red = reinterpret_cast<float*>(smem + sm.red);
     uint8_t* ring = smem + sm.ring;
-    float* Z = reinterpret_cast<float*>(smem + sm.ring);   // logits [16][zp]: CTA 0, between the last two barriers of a step
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sm.bars);       // [16 * NST] KV stages, then [nslot] weight slots
+    float* Z = reinterpret_cast<float*>(smem + sm.zbuf);   // logits [8][zp], used in CTA 0
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sm.bars);       // [16 warps][NST stages]
     int* toks = reinterpret_cast<int*>(smem + sm.toks);
     const int NST = sm.nst;
 
-    WRing wr;
-    wr.base = smem + sm.wring;
-    wr.full = bars + MG_WARPS * NST;
-    wr.seq = reinterpret_cast<volatile int*>(smem + sm.wseq);
-    wr.src = a.wstream + static_cast<size_t>(crank) * sm.per_step * MG_SLOT;
-    wr.nslot = sm.nslot; wr.per_step = sm.per_step; wr.total = a.steps * sm.per_step;
-
     // ---- one-time setup ----
     for (int i = tid * 16; i < sm.bars; i += MG_THREADS * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
-    if (tid < MG_WARPS * NST + sm.nslot) mbar_init(&bars[tid], 1);
+    if (tid < MG_WARPS * NST + sm.nst_extra) mbar_init(&bars[tid], 32);
     if (tid < MG_ROWS) toks[tid] = (tid < G) ? a.first[s0 + tid] : 0;
-    if (tid < sm.nslot) wr.seq[tid] = -1;
     mbar_fence_init();
     __syncthreads();
-    if (tid == 0) {                                // prime the weight ring
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // the zero fill above vs the bulk copies
-        for (int s = 0; s < min(wr.nslot, wr.total); ++s) wring_issue(wr, s);
+
+    // phases of a decoder block and of the head as this CTA sees them (16-column tiles, K split, slots per unit)
+    const Phase ph_attn{3 * HS / 16, sm.ks_attn, E / 128 / sm.ks_attn};
+    const Phase ph_proj{HS / 16, sm.ks_proj, E / 128 / sm.ks_proj};
+    const Phase ph_fc{FS / 16, sm.ks_fc, E / 128 / sm.ks_fc};
+    const Phase ph_proj2{HS / 16, sm.ks_proj2, a.F / 128 / sm.ks_proj2};
+    const Phase ph_logits{VS / 16, sm.ks_logits, E / 128 / sm.ks_logits};
+
+    // this warp's weight jobs in the order it consumes them (stream positions relative to the block / to the head)
+    uint16_t* tab = reinterpret_cast<uint16_t*>(smem + sm.jobtab) + warp * MG_TAB;
+    int n_pre = 0, n_post = 0, n_logit = 0;
+    {
+        auto list = [&](const Phase& ph, int pos0, int first, int& n) {
+            for (int u = warp; u < ph.ntiles * ph.ksplit; u += MG_WARPS)
+                for (int j = 0; j < ph.sub; ++j) {
+                    if (lane == 0) tab[first + n] = static_cast<uint16_t>(pos0 + u * ph.sub + j);
+                    ++n;
+                }
+        };
+        list(ph_attn, 0, 0, n_pre);
+        list(ph_proj, sm.n_attn, 8, n_post);
+        list(ph_fc, sm.n_attn + sm.n_proj, 8, n_post);
+        list(ph_proj2, sm.n_attn + sm.n_proj + sm.n_fc, 8, n_post);
+        list(ph_logits, 0, 24, n_logit);
+        __syncwarp();
     }
+    JobPlan plan;
+    plan.wsrc = a.wstream + static_cast<size_t>(crank) * sm.per_step * MG_SLOT;
+    plan.cache = a.cache; plan.layer_stride = a.layer_stride;
+    plan.w_policy = a.l2_hints ? l2_policy_evict_last() : l2_policy_evict_normal();
+    plan.kv_policy = a.l2_hints ? l2_policy_evict_first() : l2_policy_evict_normal();
+    plan.tab = tab; plan.n_pre = n_pre; plan.n_post = n_post; plan.n_logit = n_logit;
+    plan.warp = warp; plan.steps = a.steps; plan.L = a.L; plan.s0 = s0; plan.nmine = units_of(warp, G * HPC);
+    plan.hpc_shift = 31 - __clz(HPC); plan.HPC = HPC; plan.H = H; plan.crank = crank; plan.t_max = a.t_max;
+    plan.per_layer = sm.per_layer;
+    JobRing jr;
+    const int first_stage = warp * NST + min(warp, sm.nst_extra);        // stages of the warps before this one
+    jr.base = ring + first_stage * MG_STAGE;
+    jr.bars = bars + first_stage;
+    jr.count = 0; jr.nst = NST + (warp < sm.nst_extra ? 1 : 0);
+    jr.cur = JobCursor{0, 0, 0, 0, 0};
+    jr.wait_prof = nullptr;
+    const bool wait_profiling = a.prof != nullptr && blockIdx.x == 0 && tid == 0;
+#define MG_WAIT_SLOT(k) if (wait_profiling) jr.wait_prof = a.prof + 16 + (k);
+    for (int st = 0; st < jr.nst; ++st) job_issue<D>(plan, jr.cur, jr.base + st * MG_STAGE, &jr.bars[st], lane);
     cluster_sync_all();                            // every CTA of the cluster is resident before any DSMEM access
 
     // optional phase profile (cluster 0, CTA 0, thread 0): cycles per phase, accumulated in global memory
@@ -430,7 +567,6 @@ decode_mega_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ M
         a.prof[slot] += now_ - prof_t;                                       \
         prof_t = now_;                                                       \
     }
-    uint32_t ring_count = 0;                       // KV stages consumed by this warp so far (stage = count % NST, parity from count / NST)
     const float* P = a.params;
     const bool use_ln = a.use_ln != 0;
     LnFrag lnf;
@@ -438,7 +574,6 @@ decode_mega_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ M
 
     for (int step = 0; step < a.steps; ++step) {
         const int pos = step;
-        const int spos = step * sm.per_step;       // weight-stream position of this step
         // ---- token + positional embedding: warp = row ----
         if (warp < G) {
             int id = toks[warp];
@@ -459,41 +594,26 @@ decode_mega_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ M
         uint8_t* Y = bufW;                         // the other full-row buffer
         for (int l = 0; l < a.L; ++l) {
             const MegaLayer& lw = a.layers[l];
-            const int lpos = spos + l * sm.per_layer;
-            const Phase ph_attn{lpos, 3 * HS / 8, 1, sm.sub_e};
-            const Phase ph_proj{lpos + sm.n_attn, HS / 8, 1, sm.sub_e};
-            const Phase ph_fc{lpos + sm.n_attn + sm.n_proj, FS / 8, 1, sm.sub_e};
-            const Phase ph_proj2{lpos + sm.n_attn + sm.n_proj + sm.n_fc, HS / 8, sm.ks_proj2, sm.sub_p2};
             // ---- P1: x1 = ln_1(x) ----
             layernorm_rows(X, bufN, pe, E, lnf, a.eps, use_ln, warp, lane);
             __syncthreads();
             MG_PROF(1)
             // ---- P2: q, k, v of this CTA's heads (bf16, local) ----
-            run_phase(ph_attn, bufN, pe, wr, red, warp, lane, [&](int nt, const float (&acc)[4], float2 bias) {
-                uint8_t* dst = qkvs + (g * 3 * HS + nt * 8 + 2 * tig) * 2;
-                *reinterpret_cast<uint32_t*>(dst) = pack_bf16(acc[0] + bias.x, acc[1] + bias.y);
+            MG_WAIT_SLOT(0)
+            run_phase<D>(ph_attn, bufN, pe, jr, plan, red, warp, lane, [&](int col, int seq, float2 lo, float2 hi) {
+                uint8_t* dst = qkvs + (seq * 3 * HS + col) * 2;
+                *reinterpret_cast<uint32_t*>(dst) = pack_bf16(lo.x, lo.y);
+                *reinterpret_cast<uint32_t*>(dst + 16) = pack_bf16(hi.x, hi.y);
             });
             __syncthreads();
             MG_PROF(2)
             // ---- P3: append k, v; attention of (sequence, head) pairs on the tensor cores; all-gather into Y ----
             {
+                MG_WAIT_SLOT(1)
                 __nv_bfloat16* cache_l = a.cache + static_cast<size_t>(l) * a.layer_stride;
                 const int npairs = G * HPC;
                 const int nmine = (npairs > warp) ? (npairs - warp + MG_WARPS - 1) / MG_WARPS : 0;
                 const int nchunks = (pos + CT - 1) / CT;
-                const int njobs = nmine * nchunks;
-                auto issue = [&](int j) {          // lane 0: stream chunk j of this warp's job list into its ring slot
-                    const int q = warp + MG_WARPS * (j / nchunks), c = j % nchunks;
-                    const int b = s0 + q / HPC, h = crank * HPC + q % HPC;
-                    const size_t off = ((static_cast<size_t>(b) * H + h) * a.t_max + static_cast<size_t>(c) * CT) * (2 * D);
-                    const uint32_t bytes = static_cast<uint32_t>(min(CT, pos - c * CT)) * REC;
-                    const uint32_t slot = (ring_count + j) % NST;
-                    uint64_t* bar = &bars[warp * NST + slot];
-                    mbar_expect_tx(bar, bytes);
-                    bulk_g2s(smem_u32(ring + (warp * NST + slot) * STAGE), cache_l + off, bytes, bar);
-                };
-                if (lane == 0)
-                    for (int j = 0; j < min(NST, njobs); ++j) issue(j);
                 // ldmatrix row addresses of this lane inside a 16-token tile of k|v records
                 const int mi = lane >> 3, mr = lane & 7;
                 const uint32_t k_lane = static_cast<uint32_t>(((mi >> 1) * 8 + mr) * REC + (mi & 1) * 16);
@@ -532,19 +652,12 @@ decode_mega_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ M
                         const size_t off = ((static_cast<size_t>(b) * H + h) * a.t_max + pos) * (2 * D) + lane * 8;
                         const uint4 val = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(lane < CH ? kw : vw) + part * 16);
                         *reinterpret_cast<uint4*>(cache_l + off) = val;
+                        __threadfence_block();     // read back by cp.async of other lanes of this warp in a later job
                     }
+                    __syncwarp();
                     for (int c = 0; c < nchunks; ++c) {
-                        const int j = pi * nchunks + c;
-                        const uint32_t cnt = ring_count + j;
-                        const uint32_t slot = cnt % NST;
-                        mbar_wait(&bars[warp * NST + slot], (cnt / NST) & 1);
-                        uint8_t* st = ring + (warp * NST + slot) * STAGE;
+                        uint8_t* st = ring_acquire(jr);
                         const int ntok = min(CT, pos - c * CT);
-                        if (ntok < CT) {           // last, partial chunk: stale V rows must not reach the MMA as NaN
-                            for (int i = lane; i < (CT - ntok) * CH; i += 32)
-                                *reinterpret_cast<uint4*>(st + (ntok + i / CH) * REC + 2 * D + (i % CH) * 16) = make_uint4(0, 0, 0, 0);
-                            __syncwarp();
-                        }
                         // S = q K^T for CT tokens: K rows are the col-major B operand as they lie in shared memory
                         float s[NT_S][4];
 #pragma unroll
@@ -595,8 +708,7 @@ decode_mega_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ M
                                 mma_16816(o[2 * dp + 1], p0, 0u, p1, 0u, vb[2], vb[3]);
                             }
                         }
-                        __syncwarp();
-                        if (lane == 0 && j + NST < njobs) issue(j + NST);
+                        ring_release<D>(jr, plan, lane);
                     }
                     lsum += __shfl_xor_sync(0xffffffffu, lsum, 1);
                     lsum += __shfl_xor_sync(0xffffffffu, lsum, 2);
@@ -608,19 +720,19 @@ decode_mega_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ M
                         for (int dt = 0; dt < NT_O; ++dt) st_cluster_u32(dst + dt * 16, pack_bf16(o[dt][0] * inv, o[dt][1] * inv));
                     }
                 }
-                ring_count += njobs;
-                // the appended rows are read through the async proxy (TMA) in later steps
-                asm volatile("fence.proxy.async.global;" ::: "memory");
             }
             if (use_ln) ln_prefetch(lnf, P + lw.ln2_g, P + lw.ln2_b, E, lane);
             MG_PROF(3)
             cluster_sync_all();                    // A: attention output of all heads is in Y everywhere
             MG_PROF(4)
             // ---- P4: x2 = x1 + c_proj(att) for this CTA's columns, all-gathered into X ----
-            run_phase(ph_proj, Y, pe, wr, red, warp, lane, [&](int nt, const float (&acc)[4], float2 bias) {
-                const int gcol = crank * HS + nt * 8 + 2 * tig;
-                const float2 r0 = unpack_bf16(*reinterpret_cast<const uint32_t*>(bufN + g * pe + gcol * 2));
-                broadcast_u32<CL>(X + g * pe + gcol * 2, pack_bf16(acc[0] + bias.x + r0.x, acc[1] + bias.y + r0.y), g < G);
+            MG_WAIT_SLOT(2)
+            run_phase<D>(ph_proj, Y, pe, jr, plan, red, warp, lane, [&](int col, int seq, float2 lo, float2 hi) {
+                const int off = seq * pe + (crank * HS + col) * 2;
+                const float2 r0 = unpack_bf16(*reinterpret_cast<const uint32_t*>(bufN + off));
+                const float2 r1 = unpack_bf16(*reinterpret_cast<const uint32_t*>(bufN + off + 16));
+                broadcast_u32<CL>(X + off, pack_bf16(lo.x + r0.x, lo.y + r0.y), seq < G);
+                broadcast_u32<CL>(X + off + 16, pack_bf16(hi.x + r1.x, hi.y + r1.y), seq < G);
             });
             MG_PROF(5)
             cluster_sync_all();                    // B: x2 is in X everywhere
@@ -632,18 +744,23 @@ decode_mega_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ M
                 else ln_prefetch(lnf, P + a.lnf_g, P + a.lnf_b, E, lane);
             }
             __syncthreads();
-            run_phase(ph_fc, bufN, pe, wr, red, warp, lane, [&](int nt, const float (&acc)[4], float2 bias) {
-                const int gcol = crank * FS + nt * 8 + 2 * tig;
-                broadcast_u32<CL>(bufG + g * pf + gcol * 2, pack_bf16(gelu_tanh(acc[0] + bias.x), gelu_tanh(acc[1] + bias.y)), g < G);
+            MG_WAIT_SLOT(3)
+            run_phase<D>(ph_fc, bufN, pe, jr, plan, red, warp, lane, [&](int col, int seq, float2 lo, float2 hi) {
+                const int off = seq * pf + (crank * FS + col) * 2;
+                broadcast_u32<CL>(bufG + off, pack_bf16(gelu_tanh(lo.x), gelu_tanh(lo.y)), seq < G);
+                broadcast_u32<CL>(bufG + off + 16, pack_bf16(gelu_tanh(hi.x), gelu_tanh(hi.y)), seq < G);
             });
             MG_PROF(7)
             cluster_sync_all();                    // C: gelu output is in bufG everywhere
             MG_PROF(8)
             // ---- P7: out = x2 + c_proj(gelu) for this CTA's columns, all-gathered into Y ----
-            run_phase(ph_proj2, bufG, pf, wr, red, warp, lane, [&](int nt, const float (&acc)[4], float2 bias) {
-                const int gcol = crank * HS + nt * 8 + 2 * tig;
-                const float2 r0 = unpack_bf16(*reinterpret_cast<const uint32_t*>(X + g * pe + gcol * 2));
-                broadcast_u32<CL>(Y + g * pe + gcol * 2, pack_bf16(acc[0] + bias.x + r0.x, acc[1] + bias.y + r0.y), g < G);
+            MG_WAIT_SLOT(4)
+            run_phase<D>(ph_proj2, bufG, pf, jr, plan, red, warp, lane, [&](int col, int seq, float2 lo, float2 hi) {
+                const int off = seq * pe + (crank * HS + col) * 2;
+                const float2 r0 = unpack_bf16(*reinterpret_cast<const uint32_t*>(X + off));
+                const float2 r1 = unpack_bf16(*reinterpret_cast<const uint32_t*>(X + off + 16));
+                broadcast_u32<CL>(Y + off, pack_bf16(lo.x + r0.x, lo.y + r0.y), seq < G);
+                broadcast_u32<CL>(Y + off + 16, pack_bf16(hi.x + r1.x, hi.y + r1.y), seq < G);
             });
             MG_PROF(9)
             cluster_sync_all();                    // D: the block output is in Y everywhere
@@ -653,14 +770,17 @@ decode_mega_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ M
 
         // ---- ln_f, tied logits for this CTA's vocabulary rows -> Z of CTA 0 ----
         {
-            const Phase ph{spos + a.L * sm.per_layer, VS / 8, 1, sm.sub_e};
             layernorm_rows(X, bufN, pe, E, lnf, a.eps, use_ln, warp, lane);
             if (use_ln) ln_prefetch(lnf, P + a.layers[0].ln1_g, P + a.layers[0].ln1_b, E, lane);
             __syncthreads();
             const uint32_t zbase = map_to_cta(smem_u32(Z), 0);
-            run_phase(ph, bufN, pe, wr, red, warp, lane, [&](int nt, const float (&acc)[4], float2) {
-                const uint32_t dst = zbase + (g * sm.zp + crank * VS + nt * 8 + 2 * tig) * 4;
-                if (g < G) st_cluster_v2(dst, __float_as_uint(acc[0]), __float_as_uint(acc[1]));
+            MG_WAIT_SLOT(5)
+            run_phase<D>(ph_logits, bufN, pe, jr, plan, red, warp, lane, [&](int col, int seq, float2 lo, float2 hi) {
+                const uint32_t dst = zbase + (seq * sm.zp + crank * VS + col) * 4;
+                if (seq < G) {
+                    st_cluster_v2(dst, __float_as_uint(lo.x), __float_as_uint(lo.y));
+                    st_cluster_v2(dst + 32, __float_as_uint(hi.x), __float_as_uint(hi.y));
+                }
             });
         }
         MG_PROF(11)
@@ -686,10 +806,11 @@ decode_mega_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ M
             if (lane < CL) st_cluster_u32(map_to_cta(smem_u32(&toks[warp]), lane), static_cast<uint32_t>(chosen));
         }
         MG_PROF(13)
-        cluster_sync_all();                        // F: next tokens are everywhere; Z (= KV ring of CTA 0) is free again
+        cluster_sync_all();                        // F: next tokens are everywhere
         MG_PROF(14)
     }
 #undef MG_PROF
+#undef MG_WAIT_SLOT
 }
 
 // ---------------------------------------------------------------------------
@@ -701,26 +822,29 @@ struct PackPhase {
     int K, ntiles, ksplit, tpp, pstride, cols_per_cta, row_limit, sub, slot0, nslots;
 };
 
-// One block per (slot, CTA rank): 256 16-byte weight chunks in B-fragment order + 2 chunks of bias.
+// One block per (slot, CTA rank): 256 16-byte weight chunks in A-fragment order + 4 chunks of bias.  Chunk
+// (i, m, lane = (g, tig)) of a slot holds what lane needs for MMA m of k-block i: weight rows r0 + g and r0 + g + 8
+// at k = kbase + 32 i + 8 tig + 4 m + {0, 1} and + {2, 3}.
 __global__ void __launch_bounds__(288)
 mega_pack_kernel(const __nv_bfloat16* __restrict__ shadow, const float* __restrict__ params, uint8_t* __restrict__ stream,
                  const PackPhase* __restrict__ table, int nphase, int per_step) {
     const int s = blockIdx.x, c = blockIdx.y, t = threadIdx.x;
-    if (t >= 258) return;
+    if (t >= 260) return;
     int pi = 0;
     while (pi + 1 < nphase && s >= table[pi + 1].slot0) ++pi;
     const PackPhase ph = table[pi];
     const int local = s - ph.slot0;
     const int u = local / ph.sub, j = local % ph.sub;
     const int nt = u % ph.ntiles, ks = u / ph.ntiles;
-    const int kper = ph.K / ph.ksplit;
-    const int row0 = c * ph.cols_per_cta + (nt / ph.tpp) * ph.pstride + (nt % ph.tpp) * 8;
+    const int row0 = c * ph.cols_per_cta + (nt / ph.tpp) * ph.pstride + (nt % ph.tpp) * 16;
     uint4 val = make_uint4(0, 0, 0, 0);
     if (t < 256) {
-        const int i = t >> 5, lane = t & 31, g = lane >> 2, tig = lane & 3;
-        const int row = row0 + g;
-        const int k = ks * kper + j * 256 + 32 * i + 8 * tig;
-        if (row <= ph.row_limit) val = *reinterpret_cast<const uint4*>(shadow + ph.w_src + static_cast<long long>(row) * ph.K + k);
+        const int i = t >> 6, m = (t >> 5) & 1, lane = t & 31, g = lane >> 2, tig = lane & 3;
+        const int k = (ks * ph.sub + j) * 128 + 32 * i + 8 * tig + 4 * m;
+        const uint32_t* lo = reinterpret_cast<const uint32_t*>(shadow + ph.w_src + static_cast<long long>(row0 + g) * ph.K + k);
+        const uint32_t* hi = reinterpret_cast<const uint32_t*>(shadow + ph.w_src + static_cast<long long>(row0 + g + 8) * ph.K + k);
+        if (row0 + g <= ph.row_limit) { val.x = lo[0]; val.z = lo[1]; }
+        if (row0 + g + 8 <= ph.row_limit) { val.y = hi[0]; val.w = hi[1]; }
     } else if (ph.b_src >= 0 && ks == 0 && j == 0) {
         float b[4];
 #pragma unroll
@@ -733,28 +857,29 @@ mega_pack_kernel(const __nv_bfloat16* __restrict__ shadow, const float* __restri
     *reinterpret_cast<uint4*>(stream + (static_cast<size_t>(c) * per_step + s) * MG_SLOT + t * 16) = val;
 }
 
-static int mega_ks_proj2(int E, int CL) {      // K split of the mlp c_proj: fill the 16 warps, pieces of >= 256
-    const int ntiles = E / CL / 8;
+// K split of a phase: fill the 16 warps (one unit each) with pieces of at least 128 of K.
+static int mega_ksplit(int ntiles, int K) {
     int ks = 1;
-    while (ntiles * ks * 2 <= MG_WARPS && (4 * E) / (ks * 2) >= 256) ks *= 2;
+    while (ntiles * ks * 2 <= MG_WARPS && K / (ks * 2) >= 128) ks *= 2;
     return ks;
 }
 
-static MegaSmem mega_smem_layout(int E, int F, int V, int D, int CL, int nst, int nslot) {
+static MegaSmem mega_smem_layout(int E, int F, int V, int D, int CL, int nst, int nst_extra) {
     MegaSmem s{};
     const int HS = E / CL, FS = F / CL;
-    const int stage = MG_CT(D) * 4 * D;
-    s.vs = 8 * ((V + 8 * CL - 1) / (8 * CL));
+    s.vs = 16 * ((V + 16 * CL - 1) / (16 * CL));
     s.pe = 2 * E + 64;
     s.pf = 2 * F + 64;
-    s.ks_proj2 = mega_ks_proj2(E, CL);
-    s.sub_e = E / 256;
-    s.sub_p2 = F / s.ks_proj2 / 256;
-    s.n_attn = (3 * HS / 8) * s.sub_e;
-    s.n_proj = (HS / 8) * s.sub_e;
-    s.n_fc = (FS / 8) * s.sub_e;
-    s.n_proj2 = (HS / 8) * s.ks_proj2 * s.sub_p2;
-    s.n_logits = (s.vs / 8) * s.sub_e;
+    s.ks_attn = mega_ksplit(3 * HS / 16, E);
+    s.ks_proj = mega_ksplit(HS / 16, E);
+    s.ks_fc = mega_ksplit(FS / 16, E);
+    s.ks_proj2 = mega_ksplit(HS / 16, F);
+    s.ks_logits = mega_ksplit(s.vs / 16, E);
+    s.n_attn = (3 * HS / 16) * (E / 128);
+    s.n_proj = (HS / 16) * (E / 128);
+    s.n_fc = (FS / 16) * (E / 128);
+    s.n_proj2 = (HS / 16) * (F / 128);
+    s.n_logits = (s.vs / 16) * (E / 128);
     s.per_layer = s.n_attn + s.n_proj + s.n_fc + s.n_proj2;
     int off = 0;
     auto take = [&](int bytes) { int o = off; off = (off + bytes + 127) & ~127; return o; };
@@ -763,42 +888,35 @@ static MegaSmem mega_smem_layout(int E, int F, int V, int D, int CL, int nst, in
     s.bufn = take(MG_ROWS * s.pe);
     s.bufg = take(MG_ROWS * s.pf);
     s.qkv = take(MG_ROWS * 3 * HS * 2);
-    s.red = take(MG_WARPS * 32 * 8);       // K-split partials: <= 15 units x 32 lanes x 2 floats
+    s.red = take(MG_WARPS * 32 * 16);      // K-split partials: <= 15 units x 32 lanes x 4 floats
+    s.jobtab = take(MG_WARPS * MG_TAB * 2);
     s.nst = nst;
-    s.nslot = nslot;
+    s.nst_extra = nst_extra;
     s.zp = CL * s.vs;
-    int ring_bytes = MG_WARPS * nst * stage;
-    if (MG_ROWS * s.zp * 4 > ring_bytes) ring_bytes = MG_ROWS * s.zp * 4;
-    s.ring = take(ring_bytes);
-    s.wring = take(nslot * MG_SLOT);
-    s.bars = take((MG_WARPS * nst + nslot) * 8);
-    s.wseq = take(nslot * 4);
+    s.zbuf = take(MG_ROWS * s.zp * 4);
+    s.ring = take((MG_WARPS * nst + nst_extra) * MG_STAGE);
+    s.bars = take((MG_WARPS * nst + nst_extra) * 8);
     s.toks = take(MG_ROWS * 4);
     s.total = off;
     return s;
 }
 
-// KV ring stages per warp (2 x 4 KB preferred: ~100 KB of cache reads in flight per SM) and as many weight slots as
-// still fit (at least 8).
+// Ring stages: as many as fit, at most 4 per warp (every stage is a 4 KB job in flight); when the number that fits
+// is not a multiple of 16 the first warps get one more.  A job is issued `stages` jobs ahead of its use and the KV
+// jobs of a step must not be issued before the previous step appended to the cache, which the >= 2 weight jobs per
+// layer and warp guarantee only from 2 layers on: a 1-layer model is limited to 2 stages.
 static MegaSmem mega_smem_fit(int E, int V, int D, int CL, int L) {
     constexpr int LIMIT = 227 * 1024;
-    int nst = 2;
-    if (const char* env = getenv("CB200_DECODE_RING_STAGES")) {      // tuning knob: KV ring stages per warp (2 .. 4)
+    int max_stages = (L >= 2 ? 4 : 2) * MG_WARPS;
+    if (const char* env = getenv("CB200_DECODE_RING_STAGES")) {      // tuning knob: stages per warp
         const int v = atoi(env);
-        if (v >= 2 && v <= 4) nst = v;
+        if (v >= 2 && v * MG_WARPS < max_stages) max_stages = v * MG_WARPS;
     }
-    MegaSmem sm{};
-    for (; nst >= 2; --nst) {
-        const MegaSmem base = mega_smem_layout(E, 4 * E, V, D, CL, nst, 0);
-        int nslot = (LIMIT - base.total - 768) / (MG_SLOT + 12);
-        if (nslot > 24) nslot = 24;
-        if (const char* env = getenv("CB200_DECODE_WEIGHT_SLOTS")) {
-            const int v = atoi(env);
-            if (v >= 4 && v < nslot) nslot = v;
-        }
-        sm = mega_smem_layout(E, 4 * E, V, D, CL, nst, nslot < 1 ? 1 : nslot);
-        if (nslot >= 8 && sm.total <= LIMIT) break;
-    }
+    const MegaSmem base = mega_smem_layout(E, 4 * E, V, D, CL, 0, 0);
+    int stages = (LIMIT - base.total - 512) / (MG_STAGE + 8);
+    if (stages > max_stages) stages = max_stages;
+    if (stages < 2 * MG_WARPS) stages = 2 * MG_WARPS;                 // does not fit: reported through .total
+    MegaSmem sm = mega_smem_layout(E, 4 * E, V, D, CL, stages / MG_WARPS, stages % MG_WARPS);
     sm.per_step = L * sm.per_layer + sm.n_logits;
     return sm;
 }
@@ -861,9 +979,9 @@ static bool mega_shape_ok(int E, int H, int D, int V, int L, int CL) {
     if (H % CL != 0 || H * D != E) return false;
     if (!(D == 16 || D == 32 || D == 64)) return false;
     if (L < 1 || L > MG_MAX_LAYERS || V < 1 || V > 4096) return false;
-    if ((E / CL) % 8 != 0) return false;
+    if ((E / CL) % 16 != 0) return false;
     const MegaSmem sm = mega_smem_fit(E, V, D, CL, L);
-    return sm.nslot >= 8 && sm.total <= 227 * 1024;
+    return sm.total <= 227 * 1024;
 }
 
 bool decode_mega_supported(int E, int H, int D, int V, int L) {
@@ -923,12 +1041,12 @@ int decode_mega(MegaArgs args, int D, int max_clusters, int cluster_size, uint8_
     };
     for (int l = 0; l < args.L; ++l) {
         const MegaLayer& w = args.layers[l];
-        add(w.attn_w, w.attn_b, E, 3 * HS / 8, 1, HS / 8, E, HS, 3 * E - 1, sm.sub_e);
-        add(w.proj_w, w.proj_b, E, HS / 8, 1, HS / 8, 0, HS, E - 1, sm.sub_e);
-        add(w.fc_w, w.fc_b, E, FS / 8, 1, FS / 8, 0, FS, F - 1, sm.sub_e);
-        add(w.proj2_w, w.proj2_b, F, HS / 8, sm.ks_proj2, HS / 8, 0, HS, E - 1, sm.sub_p2);
+        add(w.attn_w, w.attn_b, E, 3 * HS / 16, sm.ks_attn, HS / 16, E, HS, 3 * E - 1, E / 128 / sm.ks_attn);
+        add(w.proj_w, w.proj_b, E, HS / 16, sm.ks_proj, HS / 16, 0, HS, E - 1, E / 128 / sm.ks_proj);
+        add(w.fc_w, w.fc_b, E, FS / 16, sm.ks_fc, FS / 16, 0, FS, F - 1, E / 128 / sm.ks_fc);
+        add(w.proj2_w, w.proj2_b, F, HS / 16, sm.ks_proj2, HS / 16, 0, HS, E - 1, F / 128 / sm.ks_proj2);
     }
-    add(args.wte_sh, -1, E, sm.vs / 8, 1, sm.vs / 8, 0, sm.vs, args.V - 1, sm.sub_e);
+    add(args.wte_sh, -1, E, sm.vs / 16, sm.ks_logits, sm.vs / 16, 0, sm.vs, args.V - 1, E / 128 / sm.ks_logits);
     CB200_REQUIRE(slot == sm.per_step, "weight stream plan mismatch: %d slots, expected %d", slot, sm.per_step);
     const int64_t stream_bytes = static_cast<int64_t>(CL) * sm.per_step * MG_SLOT;
     const int64_t table_off = (stream_bytes + 255) & ~int64_t(255);
@@ -942,7 +1060,9 @@ int decode_mega(MegaArgs args, int D, int max_clusters, int cluster_size, uint8_
     CB200_CUDA_OK(cudaGetLastError());
     note_launch(1);
     args.wstream = stream_ws;
-    if (args.prof != nullptr) CB200_CUDA_OK(cudaMemsetAsync(args.prof, 0, 16 * sizeof(long long), s));
+    args.l2_hints = 1;
+    if (const char* env = getenv("CB200_DECODE_L2_HINTS")) args.l2_hints = atoi(env) != 0;
+    if (args.prof != nullptr) CB200_CUDA_OK(cudaMemsetAsync(args.prof, 0, 24 * sizeof(long long), s));
     return CB200_MEGA_DISPATCH(launch_mega, args, sm, ncl, s);
 }
 

@@ -44,15 +44,17 @@ for size in [v for v in impls if v != 1]:
     import ctypes
     names = ['embed', 'ln_1', 'c_attn', 'attention', 'barrier A', 'c_proj', 'barrier B', 'ln_2 + c_fc', 'barrier C',
              'mlp c_proj', 'barrier D', 'ln_f + logits', 'barrier E', 'sample', 'barrier F']
-    counters = torch.zeros(16, dtype=torch.int64, device='cuda')
+    counters = torch.zeros(24, dtype=torch.int64, device='cuda')
     _lib.call('cb200_set_decode_impl', 0, 0, size if size in (4, 8) else 0)
     _lib.call('cb200_set_decode_profile', ctypes.c_void_p(counters.data_ptr()))
     model.generate(prompt, N, temperature=1.0, seed=7)
     torch.cuda.synchronize()
     _lib.call('cb200_set_decode_profile', None)
     c = counters.cpu().tolist()
-    total = sum(c) or 1
+    total = sum(c[:15]) or 1
     print('phase profile, cluster size %s, over %d steps (cycles per step; per layer for block phases):' % (size or 'auto', N))
     for i, name in enumerate(names):
         per = c[i] / N / (L if 1 <= i <= 10 else 1)
         print('  %-14s %9.0f cyc  %5.1f%%' % (name, per, 100.0 * c[i] / total))
+    print('  thread 0 waited for its ring jobs (cyc per layer): c_attn %.0f, attention %.0f, c_proj %.0f, c_fc %.0f, mlp c_proj %.0f; logits %.0f per step'
+          % tuple([c[16 + k] / N / L for k in range(5)] + [c[21] / N]))
