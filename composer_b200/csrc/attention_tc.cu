@@ -52,7 +52,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     using C = TcbCfg<D>;
     constexpr int RB = C::RB, TILE = C::TILE, PBYTES = C::PBYTES, NBUF_Q = C::NBUF_Q, NBUF_P = C::NBUF_P;
     constexpr uint32_t LT = umma_layout_for_row_bytes(RB); // swizzle mode of the Q/K/V/dO tiles
-    constexpr uint32_t COL_S = 0, COL_DP = 128, COL_DQ = 256, COL_DK = 256 + D, COL_DV = 256 + 2 * D;
+    // dQ is double buffered (the drain of tile it - 1 runs under the MMAs of tile it)
+    constexpr uint32_t COL_S = 0, COL_DP = 128, COL_DQ = 256, COL_DK = 256 + 2 * D, COL_DV = 256 + 3 * D;
     static_assert(COL_DV + D <= 512, "TMEM budget");
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -69,9 +70,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     uint64_t* bar_s_full = bars + 4;          // S, dP complete in TMEM
     uint64_t* bar_sdp_free = bars + 5;        // S, dP pulled into registers by every softmax thread
     uint64_t* bar_p_full = bars + 6;          // P, dS' written to smem
-    uint64_t* bar_dq_full = bars + 7;         // dV, dK, dQ MMAs of the tile complete
-    uint64_t* bar_dq_free = bars + 8;         // dQ drained from TMEM
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+    // one barrier per dQ buffer: a waiter may then lag a whole tile behind without meeting the phase parity again
+    uint64_t* bar_dq_full = bars + 7;         // [2] dV, dK, dQ MMAs of the tile complete
+    uint64_t* bar_dq_free = bars + 9;         // [2] dQ buffer drained from TMEM
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
 
     const int E = H * D;
     const int kb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -89,8 +91,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         mbar_init(bar_s_full, 1);
         mbar_init(bar_sdp_free, TCB_SM_WARPS * 32);
         mbar_init(bar_p_full, TCB_SM_WARPS * 32);
-        mbar_init(bar_dq_full, 1);
-        mbar_init(bar_dq_free, 128);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bar_dq_full[i], 1);
+            mbar_init(&bar_dq_free[i], TCB_SM_WARPS * 32);
+        }
         mbar_fence_init();
     }
     if (warp == TCB_SM_WARPS + 1) tmem_alloc<512>(tmem_slot);
@@ -139,7 +143,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
             issue_s_dp(0);
             for (int it = 0; it < ntiles; ++it) {
                 // the ring slot of tile it + NBUF_Q - 1 was last read by the MMAs of tile it - 1
-                if (it >= 1) mbar_wait(bar_dq_full, (it - 1) & 1);
+                if (it >= 1) mbar_wait(&bar_dq_full[(it - 1) & 1], ((it - 1) >> 1) & 1);
                 if (it + NBUF_Q - 1 < ntiles) load_tile(it + NBUF_Q - 1);
                 if (it + 1 < ntiles) {
                     mbar_wait(bar_sdp_free, it & 1);       // S/dP(it) are in registers: TMEM columns reusable
@@ -148,8 +152,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
                 }
                 mbar_wait(bar_p_full, it & 1);
                 tc_fence_after();
-                if (it >= 1) {
-                    mbar_wait(bar_dq_free, (it - 1) & 1);  // previous dQ tile drained
+                if (it >= 2) {
+                    mbar_wait(&bar_dq_free[it & 1], ((it - 2) >> 1) & 1);  // tile it - 2 drained from this dQ buffer
                     tc_fence_after();
                 }
                 const int buf = it % NBUF_Q;
@@ -167,9 +171,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
                 // dQ = dS' K : A K-major (two 64-key halves of 16 KB), B = K tile MN-major
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks)
-                    umma_bf16(tmem + COL_DQ, umma_smem_desc(aS + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024, 2u),
+                    umma_bf16(tmem + COL_DQ + (it & 1) * D, umma_smem_desc(aS + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024, 2u),
                               umma_smem_desc(aK + ks * 16 * RB, 128 * RB, 8 * RB, LT), IDESC_Q, ks > 0 ? 1u : 0u);
-                umma_commit(bar_dq_full);
+                umma_commit(&bar_dq_full[it & 1]);
             }
         }
     } else if (warp < TCB_SM_WARPS) {
@@ -192,27 +196,28 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         }
         const float dq_scale = scale * ks_scale;
 
-        auto drain_dq = [&](int t) {                  // tile t's dQ rows of this band -> fp32 buffer
+        auto drain_dq = [&](int t) {                  // tile t's dQ: every warp reduces a quarter of the head's columns
+            constexpr int DC = D / 4;
             const int row_g = (kb + t) * TCB_TILE + r;
-            mbar_wait(bar_dq_full, t & 1);
+            const int buf = t & 1;
+            mbar_wait(&bar_dq_full[buf], (t >> 1) & 1);
             tc_fence_after();
+            uint32_t v[DC];
+            if (DC == 4) tmem_ld4(t_lane + COL_DQ + buf * D + cq * DC, reinterpret_cast<uint32_t(&)[4]>(v));
+            else if (DC == 8) tmem_ld8(t_lane + COL_DQ + buf * D + cq * DC, reinterpret_cast<uint32_t(&)[8]>(v));
+            else tmem_ld16(t_lane + COL_DQ + buf * D + cq * DC, reinterpret_cast<uint32_t(&)[16]>(v));
+            tmem_ld_wait();
+            if (row_g < T) {
+                float* dst = dqb + static_cast<size_t>(row_g) * E + cq * DC;
 #pragma unroll
-            for (int c0 = 0; c0 < D; c0 += 16) {
-                uint32_t v[16];
-                tmem_ld16(t_lane + COL_DQ + c0, v);
-                tmem_ld_wait();
-                if (row_g < T) {
-                    float* dst = dqb + static_cast<size_t>(row_g) * E + c0;
-#pragma unroll
-                    for (int j = 0; j < 16; j += 4)
-                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j),
-                                     "f"(__uint_as_float(v[j]) * dq_scale), "f"(__uint_as_float(v[j + 1]) * dq_scale),
-                                     "f"(__uint_as_float(v[j + 2]) * dq_scale), "f"(__uint_as_float(v[j + 3]) * dq_scale)
-                                     : "memory");
-                }
+                for (int j = 0; j < DC; j += 4)
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j),
+                                 "f"(__uint_as_float(v[j]) * dq_scale), "f"(__uint_as_float(v[j + 1]) * dq_scale),
+                                 "f"(__uint_as_float(v[j + 2]) * dq_scale), "f"(__uint_as_float(v[j + 3]) * dq_scale)
+                                 : "memory");
             }
             tc_fence_before();
-            mbar_arrive(bar_dq_free);
+            mbar_arrive(&bar_dq_free[buf]);
         };
 
         // per-row softmax statistics are fetched one tile ahead (a global-memory latency per tile otherwise)
@@ -227,7 +232,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
                 lse_next = ok ? glse[row_n] : INFINITY;
                 dl_next = ok ? gdelta[row_n] * inv_ks : 0.f;
             }
-            if (cq == 0 && it >= 1) drain_dq(it - 1);
             mbar_wait(bar_s_full, it & 1);
             tc_fence_after();
             const bool diagonal = (it == 0);
@@ -298,7 +302,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
                     if (partial) elements(std::true_type{});
                     else         elements(std::false_type{});
                 }
-                if (ch == 0 && NBUF_P == 1 && it >= 1) mbar_wait(bar_dq_full, (it - 1) & 1);   // single buffer: tile it-1's MMAs must be done
+                if (ch == 0 && NBUF_P == 1 && it >= 1) mbar_wait(&bar_dq_full[(it - 1) & 1], ((it - 1) >> 1) & 1);   // single buffer: tile it-1's MMAs must be done
                 // two 16-byte chunks of this row per tensor; chunk index XOR (row & 7) = SWIZZLE_128B
                 const uint32_t half_off = static_cast<uint32_t>((col0 >> 6) * 16384 + r * 128);
 #pragma unroll
@@ -310,10 +314,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
             }
             fence_proxy_async_smem();
             mbar_arrive(bar_p_full);
+            // dQ of the previous tile: its MMAs were issued a whole tile of softmax work ago
+            if (it >= 1) drain_dq(it - 1);
         }
         // ---- last dQ tile, then dK / dV of this key block (thread = key row) ----
+        drain_dq(ntiles - 1);
         if (cq == 0) {
-            drain_dq(ntiles - 1);
             const int key = k0 + r;
             const int ld = 3 * E;
             __nv_bfloat16* dkp = dqkv + (static_cast<size_t>(row_base) + key) * ld + E + h * D;
