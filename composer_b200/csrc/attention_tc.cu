@@ -222,15 +222,15 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
 
         // per-row softmax statistics are fetched one tile ahead (a global-memory latency per tile otherwise)
         float lse_next = (kb * TCB_TILE + r < T) ? glse[kb * TCB_TILE + r] : INFINITY;   // +inf => P = 0 past the end
-        float dl_next = (kb * TCB_TILE + r < T) ? gdelta[kb * TCB_TILE + r] * inv_ks : 0.f;
+        float dl_next = (kb * TCB_TILE + r < T) ? gdelta[kb * TCB_TILE + r] : 0.f;      // raw: scaled when it is used, a tile later
         for (int it = 0; it < ntiles; ++it) {
             const int row_g = (kb + it) * TCB_TILE + r;            // global query row
-            const float lse_r = lse_next, dl_r = dl_next;
+            const float lse_r = lse_next, dl_r = dl_next * inv_ks;
             {
                 const int row_n = row_g + TCB_TILE;
                 const bool ok = (it + 1 < ntiles) && row_n < T;
                 lse_next = ok ? glse[row_n] : INFINITY;
-                dl_next = ok ? gdelta[row_n] * inv_ks : 0.f;
+                dl_next = ok ? gdelta[row_n] : 0.f;
             }
             mbar_wait(bar_s_full, it & 1);
             tc_fence_after();

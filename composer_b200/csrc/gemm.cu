@@ -108,7 +108,8 @@ static int launch_variant(const GemmDesc& d, cudaStream_t stream) {
                               EPI == EPI_MUL_DGELU);
     constexpr int num_out = (EPI == EPI_BIAS_GELU) ? 2 : 1;
     constexpr int b_box_rows = (BN <= 256) ? BN : BN / 2;
-    constexpr size_t smem_bytes = size_t(STAGES) * L::STAGE_BYTES + (staging ? 2 * num_out * L::STAGING_BYTES : 0) +
+    constexpr bool aux_tma = (EPI == EPI_BIAS_DROP_RES || EPI == EPI_MUL_DGELU);
+    constexpr size_t smem_bytes = size_t(STAGES) * L::STAGE_BYTES + (staging ? (aux_tma ? 3 : 2) * num_out * L::STAGING_BYTES : 0) +
                                   256 /* barriers */ + 1024 /* alignment slack */;
     static_assert(smem_bytes <= 232448, "shared memory budget exceeded");
 
@@ -129,6 +130,11 @@ static int launch_variant(const GemmDesc& d, cudaStream_t stream) {
         if (num_out == 2) {
             CB200_REQUIRE(d.out1 != nullptr, "GELU epilogue needs out1");
             rc = make_tmap_bf16(&tmC1, d.out1, d.N, d.M, d.ld_out1, 64, GEMM_BM);
+            if (rc) return rc;
+        } else if (aux_tma) {
+            CB200_REQUIRE(d.aux != nullptr && d.ld_aux % 8 == 0 && (reinterpret_cast<uintptr_t>(d.aux) & 15) == 0,
+                          "epilogue needs a 16-byte aligned aux with ld %% 8 == 0");
+            rc = make_tmap_bf16(&tmC1, d.aux, d.N, d.M, d.ld_aux, 64, GEMM_BM);
             if (rc) return rc;
         } else {
             tmC1 = tmC0;
@@ -184,8 +190,8 @@ int gemm_launch(const GemmDesc& d, cudaStream_t stream) {
     switch (d.kind) {
         case GEMM_BIAS:       return launch_variant<256, false, false, EPI_BIAS_BF16, 4>(d, stream);
         case GEMM_BIAS_GELU:  return launch_variant<256, false, false, EPI_BIAS_GELU, 3>(d, stream);
-        case GEMM_BIAS_DROP_RES: return launch_variant<256, false, false, EPI_BIAS_DROP_RES, 4>(d, stream);
-        case GEMM_MUL_DGELU:  return launch_variant<256, false, false, EPI_MUL_DGELU, 4>(d, stream);
+        case GEMM_BIAS_DROP_RES: return launch_variant<256, false, false, EPI_BIAS_DROP_RES, 3>(d, stream);
+        case GEMM_MUL_DGELU:  return launch_variant<256, false, false, EPI_MUL_DGELU, 3>(d, stream);
         case GEMM_WGRAD:      return launch_variant<256, true, true, EPI_ATOMIC_F32, 4>(d, stream);
         case GEMM_CE:
             if (d.N <= 400) return launch_variant<400, false, false, EPI_CE, 3>(d, stream);

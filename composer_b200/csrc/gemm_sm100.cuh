@@ -91,6 +91,11 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     constexpr bool USES_STAGING = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU || EPI == EPI_BIAS_DROP_RES ||
                                    EPI == EPI_MUL_DGELU);
     constexpr int NUM_OUT = (EPI == EPI_BIAS_GELU) ? 2 : 1;
+    // The epilogues that read a second [M, N] operand (residual / pre-activation) fetch its 128 x 64 slab by TMA into
+    // the staging buffer the result is then written to (same swizzle, same thread, same 16 bytes), one slab ahead of
+    // its use; with thread = row, direct loads would touch 32 different lines per instruction.  tmC1 is its map.
+    constexpr bool AUX_TMA = (EPI == EPI_BIAS_DROP_RES || EPI == EPI_MUL_DGELU);
+    constexpr int STAGING_BUFS = AUX_TMA ? 3 : 2;
     constexpr int EPI_WARPS = (EPI == EPI_CE) ? 4 : 8;
     static_assert(BN % 16 == 0 && BN <= 512, "bad BN");
     static_assert(!(B_MN && BN > 256), "MN-major B with BN > 256 not supported");
@@ -99,13 +104,14 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // 1024-byte alignment is required by SWIZZLE_128B.
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* stage_base = smem;
-    uint8_t* staging = smem + STAGES * L::STAGE_BYTES;    // [2][NUM_OUT][16 KB] when USES_STAGING
-    uint64_t* bars = reinterpret_cast<uint64_t*>(staging + (USES_STAGING ? 2 * NUM_OUT * L::STAGING_BYTES : 0));
+    uint8_t* staging = smem + STAGES * L::STAGE_BYTES;    // [STAGING_BUFS][NUM_OUT][16 KB] when USES_STAGING
+    uint64_t* bars = reinterpret_cast<uint64_t*>(staging + (USES_STAGING ? STAGING_BUFS * NUM_OUT * L::STAGING_BYTES : 0));
     uint64_t* full_bar = bars;                       // [STAGES]
     uint64_t* empty_bar = bars + STAGES;             // [STAGES]
     uint64_t* tmem_full = bars + 2 * STAGES;         // [ACC_STAGES]
     uint64_t* tmem_empty = tmem_full + ACC_STAGES;   // [ACC_STAGES]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + ACC_STAGES);
+    uint64_t* aux_full = tmem_empty + ACC_STAGES;    // [3] aux slab landed (AUX_TMA)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_full + 3);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -115,7 +121,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tma_prefetch_desc(&tmB);
         if (USES_STAGING) {
             tma_prefetch_desc(&tmC0);
-            if (NUM_OUT == 2) tma_prefetch_desc(&tmC1);
+            if (NUM_OUT == 2 || AUX_TMA) tma_prefetch_desc(&tmC1);
         }
     }
     if (warp == 1 && lane == 0) {
@@ -127,6 +133,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             mbar_init(&tmem_full[s], 1);
             mbar_init(&tmem_empty[s], EPI_WARPS * 32);
         }
+        for (int s = 0; s < 3; ++s) mbar_init(&aux_full[s], 1);
         mbar_fence_init();
     }
     if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
@@ -230,6 +237,16 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         int acc = 0;
         uint32_t acc_phase = 0;
         int store_parity = 0;                        // which staging buffer pair to use next
+        int aux_seq = 0;                             // AUX_TMA: index of the next slab in this CTA's slab sequence
+        // AUX_TMA: requests the aux slab of (tile_, slab_) into staging buffer seq % 3 (one thread)
+        auto issue_aux = [&](int tile_, int slab_, int seq) {
+            const int mn_ = tile_ % tiles_mn;
+            const int m0_ = (mn_ / args.num_n_tiles) * GEMM_BM;
+            const int n0_ = (mn_ % args.num_n_tiles) * BN + slab_ * 64;
+            mbar_expect_tx(&aux_full[seq % 3], L::STAGING_BYTES);
+            tma_load_2d(staging + (seq % 3) * L::STAGING_BYTES, &tmC1, &aux_full[seq % 3], n0_, m0_);
+        };
+        if (AUX_TMA && epi_tid == 0 && static_cast<int>(blockIdx.x) < total_tiles) issue_aux(blockIdx.x, 0, 0);
 
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int split = tile / tiles_mn;
@@ -249,11 +266,24 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 for (int slab = 0; slab < BN / 64; ++slab) {
                     const int ncol0 = n0 + slab * 64;
                     if (ncol0 >= args.N) break;      // uniform across the CTA
-                    uint8_t* buf0 = staging + (store_parity * NUM_OUT) * L::STAGING_BYTES;
+                    uint8_t* buf0 = staging + ((AUX_TMA ? aux_seq % 3 : store_parity) * NUM_OUT) * L::STAGING_BYTES;
                     uint8_t* buf1 = buf0 + L::STAGING_BYTES;
-                    // the TMA store that last read this buffer pair must have drained
-                    if (epi_tid == 0) tma_store_wait_read<NUM_OUT>();
-                    epi_bar_sync();
+                    if (AUX_TMA) {
+                        if (epi_tid == 0) {
+                            // next slab of this CTA's sequence: its buffer was last read by the store two slabs ago
+                            int nt = tile, ns = slab + 1;
+                            if (ns >= BN / 64 || n0 + ns * 64 >= args.N) { nt = tile + gridDim.x; ns = 0; }
+                            if (nt < total_tiles) {
+                                tma_store_wait_read<1>();
+                                issue_aux(nt, ns, aux_seq + 1);
+                            }
+                        }
+                        mbar_wait(&aux_full[aux_seq % 3], (aux_seq / 3) & 1);
+                    } else {
+                        // the TMA store that last read this buffer pair must have drained
+                        if (epi_tid == 0) tma_store_wait_read<NUM_OUT>();
+                        epi_bar_sync();
+                    }
                     {
                         uint32_t v[32];
                         tmem_ld32(t_row + slab * 64 + half * 32, v);
@@ -282,9 +312,9 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                             const bool in_rows = row < args.M;
 #pragma unroll
                             for (int j = 0; j < 32; j += 8) {
-                                uint4 a4 = make_uint4(0, 0, 0, 0);
-                                if (in_rows && c0 + j < args.N)
-                                    a4 = __ldg(reinterpret_cast<const uint4*>(args.aux + static_cast<size_t>(row) * args.ld_aux + c0 + j));
+                                // rows / columns outside the tensor were zero-filled by the TMA load
+                                const uint4 a4 = *reinterpret_cast<const uint4*>(buf0 + sw128_offset(row_in_tile, half * 4 + (j >> 3)));
+                                (void)in_rows;
                                 const uint32_t aw[4] = {a4.x, a4.y, a4.z, a4.w};
                                 Philox4 rb{0, 0, 0, 0};
                                 if (EPI == EPI_BIAS_DROP_RES && args.drop.threshold16 != 0)
@@ -335,6 +365,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         }
                     }
                     store_parity ^= 1;
+                    ++aux_seq;
                 }
             } else if constexpr (EPI == EPI_ATOMIC_F32) {
                 if (has_work) {
