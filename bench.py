@@ -369,10 +369,13 @@ def dominant_kernel_roofline(model, B, T, peaks, peak_kind, step_seconds):
     summary_path = os.path.join(ROOT, 'profiles', 'ncu_summary.json')
     if os.path.exists(summary_path):
         with open(summary_path) as handle:
-            traffic = json.load(handle).get('attn_bwd_kernel', {}).get('dram_bytes_per_launch')
+            summary = json.load(handle)
+        for name, entry in summary.items():
+            if name.startswith('attn_bwd_tc_kernel'):
+                traffic = entry.get('dram_bytes_per_launch')
     achieved = bwd_flops / t_bwd / 1e12
     roofline = {
-        'kernel': 'attn_bwd_kernel<16,64> (+ delta and dq-store helpers), one decoder block',
+        'kernel': 'attn_bwd_tc_kernel<%d,1> (tcgen05 / TMEM; + delta and dq-store helpers), one decoder block' % D,
         'bound': 'tensor', 'achieved': achieved, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
         'frac': achieved / peaks['bf16_tflops'], 'traffic': traffic, 'peak_source': peak_kind + ' (burst)',
         'note': 'at d_h = 16 the kernel is bound by MUFU.EX2 / issue slots, not the tensor pipe: %.2f T '
