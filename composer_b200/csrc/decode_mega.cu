@@ -2,31 +2,34 @@
 // in ONE kernel launch.
 //
 // Sequences never interact while decoding, so the batch is split over thread
-// block clusters of 4 or 8 CTAs, each cluster owning up to 8 sequences (half the
-// M of an m16n8k16 MMA; the other rows are fed zeros) for the whole generation, and there is no grid-wide
-// synchronisation at all: the only barriers are hardware cluster barriers.
-// Inside a cluster every linear layer is split over the CTAs by output columns;
-// c_attn is split by heads, so a CTA computes q, k, v of its own heads, appends
-// k, v to the cache and attends for those heads without any exchange.  The
-// activations that the next layer needs in full (attention output, x2, gelu
-// output, block output: <= 8 rows each) are all-gathered by writing the CTA's
-// column slice into the shared memory of every peer (DSMEM), 4 cluster barriers
-// per decoder block.
+// block clusters of 4 or 8 CTAs, each cluster owning up to 8 sequences for the
+// whole generation, and there is no grid-wide synchronisation at all: the only
+// barriers are hardware cluster barriers.  Inside a cluster every linear layer
+// is split over the CTAs by output columns; c_attn is split by heads, so a CTA
+// computes q, k, v of its own heads, appends k, v to the cache and attends for
+// those heads without any exchange.  The activations that the next layer needs
+// in full (attention output, x2, gelu output, block output: <= 8 rows each) are
+// all-gathered by writing the CTA's column slice into the shared memory of
+// every peer (DSMEM), 4 cluster barriers per decoder block.
 //
-// Everything that comes from memory arrives through TMA bulk copies
-// (cp.async.bulk + mbarrier), issued far ahead of its use:
-//  * Weights.  A pack kernel re-lays the bf16 weights once per generation into
-//    the order in which each CTA consumes them: a stream of 4 KB slots (8 output
-//    columns x 256 of K, already in mma.sync B-fragment order, + the 8 biases).
-//    The stream runs through a ring of slots in shared memory; the warp that
-//    consumes slot s re-arms it with stream position s + ring size, so weights
-//    are always a whole ring (>= 10 slots, several phases) ahead and a GEMM
-//    phase never waits on L2.
-//  * KV cache, [L, B, H, t_max, 2, d_h] (k and v of a token adjacent): each warp
-//    owns one (sequence, head) pair at a time and streams it in 2-4 KB stages
-//    through a private ring; scores and P.V run on the tensor cores (q as the A
-//    operand, K rows / V rows as B through ldmatrix / ldmatrix.trans, the score
-//    accumulators re-used as the A operand of P.V), the softmax stays online.
+//  * Linear layers run transposed, out^T = W x^T: the 16 rows of an m16n8k16
+//    MMA are 16 output columns, its 8 columns are the 8 sequences.  A pack
+//    kernel re-lays the bf16 weights once per generation into the order in
+//    which each CTA consumes them: a stream of 4 KB slots (16 output columns x
+//    128 of K in A-fragment order, one 16-byte shared-memory read per MMA, +
+//    the 16 biases).
+//  * KV cache, [L, B, H, t_max, 2, d_h] (k and v of a token adjacent): a warp
+//    owns one (sequence, head) pair at a time and streams it in 4 KB stages;
+//    scores and P.V run on the tensor cores (q as the A operand, K rows / V
+//    rows as B through ldmatrix / ldmatrix.trans, the score accumulators
+//    re-used as the A operand of P.V), the softmax stays online.
+//  * Everything a warp reads from global memory on the hot path, weight slots
+//    and KV stages alike, is one static sequence of copy jobs in the warp's own
+//    program order (it depends on the step, not on data).  The warp owns 2-3
+//    ring stages; after consuming job k it issues job k + stages (16-byte
+//    cp.async by the whole warp, completion on an mbarrier), so the weights of
+//    a GEMM phase are requested while the previous phase or the attention is
+//    still running.  L2 eviction hints keep the weight stream resident.
 // The first CTA of each cluster draws the tokens (same Philox / inverse-CDF
 // rule as logits_sample_kernel) and broadcasts them.
 //
@@ -47,11 +50,8 @@ namespace cb200 {
 constexpr int MG_WARPS = 16;
 constexpr int MG_THREADS = MG_WARPS * 32;
 constexpr int MG_ROWS = 8;          // sequences per cluster: rows 0 .. 7 of the m16n8k16 MMAs (rows 8 .. 15 are fed zeros)
-#ifndef MG_CT16
-#define MG_CT16 64
-#endif
-// tokens per KV ring stage (one bulk copy of k|v records): 4 KB whatever the head size
-#define MG_CT(D) ((D) == 64 ? 16 : (D) == 32 ? 32 : MG_CT16)
+// tokens per KV ring stage (k|v records of one head): 4 KB whatever the head size
+#define MG_CT(D) ((D) == 64 ? 16 : (D) == 32 ? 32 : 64)
 constexpr int MG_SLOT_W = 4096;            // weight bytes of a slot: 16 output columns x 128 of K in A-fragment order
 constexpr int MG_SLOT = MG_SLOT_W + 64;    // + the 16 biases of those columns
 
@@ -67,10 +67,6 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank) {
     uint32_t r;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
     return r;
-}
-__device__ __forceinline__ void st_cluster_v4(uint32_t addr, const uint4& v) {
-    asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
-                 : "memory");
 }
 __device__ __forceinline__ void st_cluster_v2(uint32_t addr, uint32_t x, uint32_t y) {
     asm volatile("st.shared::cluster.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(x), "r"(y) : "memory");
@@ -108,11 +104,6 @@ __device__ __forceinline__ void cp_async_16_hint(uint32_t dst, const void* src, 
 __device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ uint4 ldg_nc_v4_keep(const void* p) {
-    uint4 r;
-    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-    return r;
-}
 __device__ __forceinline__ void mma_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
                                           uint32_t b1) {
     asm volatile(
@@ -124,7 +115,7 @@ __device__ __forceinline__ void mma_16816(float (&d)[4], uint32_t a0, uint32_t a
 
 struct MegaSmem {        // shared-memory layout and weight-stream plan (computed on the host, identical in every CTA)
     int pe, pf;          // row pitch of the [8, E] and [8, F] bf16 buffers (2E + 64, 2F + 64: conflict-free operand reads)
-    int buf0, buf1, bufn, bufg, qkv, red, zbuf, jobtab, ring, bars, toks, total;
+    int buf0, buf1, bufn, bufg, qkv, red, zbuf, jobtab, ring, bars, toks, prof, total;
     int nst;             // ring stages per warp ...
     int nst_extra;       // ... plus one more for the first nst_extra warps (whatever still fits)
     int zp;              // floats per row of the logits matrix (CTA 0)
@@ -171,7 +162,8 @@ struct JobCursor {
 struct JobRing {
     uint8_t* base;         // this warp's stages
     uint64_t* bars;        // this warp's mbarriers
-    uint32_t count;        // jobs consumed so far
+    int stage;             // stage of the next job to consume ...
+    uint32_t phase;        // ... and the parity of its mbarrier phase
     int nst;
     JobCursor cur;         // next job to issue (always `nst` jobs ahead of `count`)
     long long* wait_prof;  // diagnostic accumulator or null
@@ -222,85 +214,76 @@ __device__ __forceinline__ void job_issue(const JobPlan& p, JobCursor& c, uint8_
     cp_async_arrive(bar);
 }
 
-// Waits for the warp's next job and returns its stage.
+// Waits for the warp's next job and returns its stage.  (The stage index and the mbarrier phase are tracked
+// incrementally: an integer division by the runtime stage count costs more than the MMAs of a slot.)
 __device__ __forceinline__ uint8_t* ring_acquire(const JobRing& r) {
-    const uint32_t st = r.count % r.nst;
     if (r.wait_prof != nullptr) {                  // diagnostic: cycles this thread waits for its jobs
         const long long t0 = clock64();
-        mbar_wait(&r.bars[st], (r.count / r.nst) & 1);
+        mbar_wait(&r.bars[r.stage], r.phase);
         *r.wait_prof += clock64() - t0;
     } else {
-        mbar_wait(&r.bars[st], (r.count / r.nst) & 1);
+        mbar_wait(&r.bars[r.stage], r.phase);
     }
-    return r.base + st * MG_STAGE;
+    return r.base + r.stage * MG_STAGE;
 }
 
 // The warp is done with the stage of its current job: it is re-armed with the job NST ahead.
 template <int D>
 __device__ __forceinline__ void ring_release(JobRing& r, const JobPlan& p, int lane) {
     __syncwarp();
-    const uint32_t st = r.count % r.nst;
-    job_issue<D>(p, r.cur, r.base + st * MG_STAGE, &r.bars[st], lane);
-    ++r.count;
+    job_issue<D>(p, r.cur, r.base + r.stage * MG_STAGE, &r.bars[r.stage], lane);
+    if (++r.stage == r.nst) { r.stage = 0; r.phase ^= 1u; }
 }
 
 // acc (16 output columns x 8 sequences) += slot (16 x 128 weights, A operand, one 16-byte read per MMA) times
 // x^T: b0 points at (sequence g, first k of the slot + 8 * tig) of the activations (B operand: the k order inside
 // a 32-wide block is permuted identically on both sides).
 __device__ __forceinline__ void slot_mma(float (&acc)[4], const uint8_t* slot, const uint8_t* b0, int lane) {
+    // four independent accumulation chains (one per 32-wide k-block): a dependent mma.sync chain of 8 would expose
+    // the tensor-core latency 8 times per slot
+    float part[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const uint4 x = *reinterpret_cast<const uint4*>(b0 + i * 64);
         const uint4 wa = *reinterpret_cast<const uint4*>(slot + (2 * i * 32 + lane) * 16);
         const uint4 wb = *reinterpret_cast<const uint4*>(slot + ((2 * i + 1) * 32 + lane) * 16);
-        mma_16816(acc, wa.x, wa.y, wa.z, wa.w, x.x, x.y);
-        mma_16816(acc, wb.x, wb.y, wb.z, wb.w, x.z, x.w);
+        part[i][0] = part[i][1] = part[i][2] = part[i][3] = 0.f;
+        mma_16816(part[i], wa.x, wa.y, wa.z, wa.w, x.x, x.y);
+        mma_16816(part[i], wb.x, wb.y, wb.z, wb.w, x.z, x.w);
     }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[e] += (part[0][e] + part[1][e]) + (part[2][e] + part[3][e]);
 }
 
 // Runs this warp's units of `ph` on the activations X[8, K] (bf16 in shared memory, row pitch `pitch` bytes); the
 // weight slots are the warp's next jobs.  K-split partials meet in `red`.  The warp that owns K part 0 of a tile
 // calls epi(col, seq, lo, hi) once per lane with the complete sums (bias added) of sequence `seq` at output columns
 // (col, col + 1) = lo and (col + 8, col + 9) = hi, col relative to this CTA's slice.  All 16 warps must call this
-// (it may contain a __syncthreads).
+// (it may contain a __syncthreads).  There is one call site (the phase loop of the kernel): the kernel's code has
+// to stay within the instruction cache, a phase is only a few hundred instructions long.
 template <int D, typename Epi>
 __device__ __forceinline__ void run_phase(const Phase& ph, const uint8_t* X, int pitch, JobRing& ring, const JobPlan& plan,
                                           float* red, int warp, int lane, Epi epi) {
     const int g = lane >> 2, tig = lane & 3;
     const uint8_t* b0 = X + g * pitch + tig * 16;
-    auto finish = [&](int nt, float (&acc)[4], float bias_lo, float bias_hi) {
-        acc[0] += bias_lo; acc[1] += bias_lo; acc[2] += bias_hi; acc[3] += bias_hi;
-        // lanes g and g ^ 1 trade one sequence each: afterwards a lane holds two adjacent columns of one sequence
-        const bool odd = g & 1;
-        const float r0 = __shfl_xor_sync(0xffffffffu, odd ? acc[0] : acc[1], 4);
-        const float r1 = __shfl_xor_sync(0xffffffffu, odd ? acc[2] : acc[3], 4);
-        const float2 lo = odd ? make_float2(r0, acc[1]) : make_float2(acc[0], r0);
-        const float2 hi = odd ? make_float2(r1, acc[3]) : make_float2(acc[2], r1);
-        epi(nt * 16 + (g & ~1), 2 * tig + (odd ? 1 : 0), lo, hi);
-    };
     const int nunits = ph.ntiles * ph.ksplit;
-    if (nunits > MG_WARPS) {                       // several units per warp (then ksplit == 1)
-        for (int u = warp; u < nunits; u += MG_WARPS) {
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
-            float bias_lo = 0.f, bias_hi = 0.f;
-            for (int j = 0; j < ph.sub; ++j) {
-                const uint8_t* slot = ring_acquire(ring);
-                if (j == 0) {
-                    bias_lo = *reinterpret_cast<const float*>(slot + MG_SLOT_W + g * 4);
-                    bias_hi = *reinterpret_cast<const float*>(slot + MG_SLOT_W + (g + 8) * 4);
-                }
-                slot_mma(acc, slot, b0 + j * 256, lane);
-                ring_release<D>(ring, plan, lane);
-            }
-            finish(u, acc, bias_lo, bias_hi);
-        }
-        return;
-    }
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     float bias_lo = 0.f, bias_hi = 0.f;
-    const int nt = warp % ph.ntiles, ks = warp / ph.ntiles;
-    const bool active = warp < nunits;
-    if (active) {
+    int nt = 0;
+    bool owner = false;                            // this warp holds K part 0 of tile nt in acc
+    for (int u = warp; u < nunits; u += MG_WARPS) {
+        // with several units per warp (then ksplit == 1) the previous tile is finished first
+        if (owner) {
+            acc[0] += bias_lo; acc[1] += bias_lo; acc[2] += bias_hi; acc[3] += bias_hi;
+            const bool odd = g & 1;
+            const float r0 = __shfl_xor_sync(0xffffffffu, odd ? acc[0] : acc[1], 4);
+            const float r1 = __shfl_xor_sync(0xffffffffu, odd ? acc[2] : acc[3], 4);
+            epi(nt * 16 + (g & ~1), 2 * tig + (odd ? 1 : 0), odd ? make_float2(r0, acc[1]) : make_float2(acc[0], r0),
+                odd ? make_float2(r1, acc[3]) : make_float2(acc[2], r1));
+            acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+        }
+        nt = u % ph.ntiles;
+        const int ks = u / ph.ntiles;
         for (int j = 0; j < ph.sub; ++j) {
             const uint8_t* slot = ring_acquire(ring);
             if (j == 0) {
@@ -310,15 +293,25 @@ __device__ __forceinline__ void run_phase(const Phase& ph, const uint8_t* X, int
             slot_mma(acc, slot, b0 + (ks * ph.sub + j) * 256, lane);
             ring_release<D>(ring, plan, lane);
         }
+        owner = ks == 0;
         if (ks > 0) *reinterpret_cast<float4*>(red + (((ks - 1) * ph.ntiles + nt) * 32 + lane) * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
     }
-    if (ph.ksplit > 1) __syncthreads();
-    if (active && ks == 0) {
-        for (int k2 = 1; k2 < ph.ksplit; ++k2) {
-            const float4 p = *reinterpret_cast<const float4*>(red + (((k2 - 1) * ph.ntiles + nt) * 32 + lane) * 4);
-            acc[0] += p.x; acc[1] += p.y; acc[2] += p.z; acc[3] += p.w;
-        }
-        finish(nt, acc, bias_lo, bias_hi);
+    if (ph.ksplit > 1) {
+        __syncthreads();
+        if (owner)
+            for (int k2 = 1; k2 < ph.ksplit; ++k2) {
+                const float4 p = *reinterpret_cast<const float4*>(red + (((k2 - 1) * ph.ntiles + nt) * 32 + lane) * 4);
+                acc[0] += p.x; acc[1] += p.y; acc[2] += p.z; acc[3] += p.w;
+            }
+    }
+    if (owner) {
+        acc[0] += bias_lo; acc[1] += bias_lo; acc[2] += bias_hi; acc[3] += bias_hi;
+        // lanes g and g ^ 1 trade one sequence each: afterwards a lane holds two adjacent columns of one sequence
+        const bool odd = g & 1;
+        const float r0 = __shfl_xor_sync(0xffffffffu, odd ? acc[0] : acc[1], 4);
+        const float r1 = __shfl_xor_sync(0xffffffffu, odd ? acc[2] : acc[3], 4);
+        epi(nt * 16 + (g & ~1), 2 * tig + (odd ? 1 : 0), odd ? make_float2(r0, acc[1]) : make_float2(acc[0], r0),
+            odd ? make_float2(r1, acc[3]) : make_float2(acc[2], r1));
     }
 }
 
@@ -550,21 +543,25 @@ decode_mega_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ M
     const int first_stage = warp * NST + min(warp, sm.nst_extra);        // stages of the warps before this one
     jr.base = ring + first_stage * MG_STAGE;
     jr.bars = bars + first_stage;
-    jr.count = 0; jr.nst = NST + (warp < sm.nst_extra ? 1 : 0);
+    jr.stage = 0; jr.phase = 0; jr.nst = NST + (warp < sm.nst_extra ? 1 : 0);
     jr.cur = JobCursor{0, 0, 0, 0, 0};
     jr.wait_prof = nullptr;
     const bool wait_profiling = a.prof != nullptr && blockIdx.x == 0 && tid == 0;
-#define MG_WAIT_SLOT(k) if (wait_profiling) jr.wait_prof = a.prof + 16 + (k);
+#define MG_WAIT_SLOT(k) if (wait_profiling) jr.wait_prof = prof_acc + 16 + (k);
     for (int st = 0; st < jr.nst; ++st) job_issue<D>(plan, jr.cur, jr.base + st * MG_STAGE, &jr.bars[st], lane);
     cluster_sync_all();                            // every CTA of the cluster is resident before any DSMEM access
 
-    // optional phase profile (cluster 0, CTA 0, thread 0): cycles per phase, accumulated in global memory
+    // optional phase profile (cluster 0, CTA 0, thread 0): cycles per phase, accumulated in shared memory (a global
+    // read-modify-write per sample would cost more than most of the phases it measures) and written out at the end
     const bool profiling = a.prof != nullptr && blockIdx.x == 0 && tid == 0;
+    long long* prof_acc = reinterpret_cast<long long*>(smem + sm.prof);
+    if (profiling)
+        for (int i = 0; i < 24; ++i) prof_acc[i] = 0;
     long long prof_t = profiling ? clock64() : 0;
 #define MG_PROF(slot)                                                        \
     if (profiling) {                                                         \
         const long long now_ = clock64();                                    \
-        a.prof[slot] += now_ - prof_t;                                       \
+        prof_acc[slot] += now_ - prof_t;                                     \
         prof_t = now_;                                                       \
     }
     const float* P = a.params;
@@ -592,196 +589,183 @@ decode_mega_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ M
 
         uint8_t* X = bufU;                         // block input (full rows)
         uint8_t* Y = bufW;                         // the other full-row buffer
-        for (int l = 0; l < a.L; ++l) {
-            const MegaLayer& lw = a.layers[l];
-            // ---- P1: x1 = ln_1(x) ----
-            layernorm_rows(X, bufN, pe, E, lnf, a.eps, use_ln, warp, lane);
-            __syncthreads();
-            MG_PROF(1)
-            // ---- P2: q, k, v of this CTA's heads (bf16, local) ----
-            MG_WAIT_SLOT(0)
-            run_phase<D>(ph_attn, bufN, pe, jr, plan, red, warp, lane, [&](int col, int seq, float2 lo, float2 hi) {
-                uint8_t* dst = qkvs + (seq * 3 * HS + col) * 2;
-                *reinterpret_cast<uint32_t*>(dst) = pack_bf16(lo.x, lo.y);
-                *reinterpret_cast<uint32_t*>(dst + 16) = pack_bf16(hi.x, hi.y);
-            });
-            __syncthreads();
-            MG_PROF(2)
-            // ---- P3: append k, v; attention of (sequence, head) pairs on the tensor cores; all-gather into Y ----
-            {
-                MG_WAIT_SLOT(1)
-                __nv_bfloat16* cache_l = a.cache + static_cast<size_t>(l) * a.layer_stride;
-                const int npairs = G * HPC;
-                const int nmine = (npairs > warp) ? (npairs - warp + MG_WARPS - 1) / MG_WARPS : 0;
-                const int nchunks = (pos + CT - 1) / CT;
-                // ldmatrix row addresses of this lane inside a 16-token tile of k|v records
-                const int mi = lane >> 3, mr = lane & 7;
-                const uint32_t k_lane = static_cast<uint32_t>(((mi >> 1) * 8 + mr) * REC + (mi & 1) * 16);
-                const uint32_t v_lane = static_cast<uint32_t>(((mi & 1) * 8 + mr) * REC + 2 * D + (mi >> 1) * 16);
-                for (int pi = 0; pi < nmine; ++pi) {
-                    const int q = warp + MG_WARPS * pi;
-                    const int sl = q / HPC, hh = q % HPC;
-                    const int b = s0 + sl, h = crank * HPC + hh;
-                    const uint32_t* qw = reinterpret_cast<const uint32_t*>(qkvs + (sl * 3 * HS + hh * D) * 2);
-                    const uint32_t* kw = qw + HS / 2;
-                    const uint32_t* vw = qw + HS;
-                    // query as the A operand (every MMA row carries the same query), new token as the softmax seed
-                    uint32_t qa[D / 16][2];
-                    float snew = 0.f;
-#pragma unroll
-                    for (int ks = 0; ks < D / 16; ++ks) {
-                        qa[ks][0] = qw[ks * 8 + tig];
-                        qa[ks][1] = qw[ks * 8 + 4 + tig];
-                        const float2 q0 = unpack_bf16(qa[ks][0]), q1 = unpack_bf16(qa[ks][1]);
-                        const float2 k0 = unpack_bf16(kw[ks * 8 + tig]), k1 = unpack_bf16(kw[ks * 8 + 4 + tig]);
-                        snew += q0.x * k0.x + q0.y * k0.y + q1.x * k1.x + q1.y * k1.y;
-                    }
-                    snew += __shfl_xor_sync(0xffffffffu, snew, 1);
-                    snew += __shfl_xor_sync(0xffffffffu, snew, 2);
-                    float m = snew * a.scale_log2;                  // running maximum (log2 units)
-                    float lsum = (tig == 0) ? 1.f : 0.f;            // this lane's share of the denominator
-                    float o[NT_O][4];
-#pragma unroll
-                    for (int dt = 0; dt < NT_O; ++dt) {
-                        const float2 vn = unpack_bf16(vw[dt * 4 + tig]);
-                        o[dt][0] = vn.x; o[dt][1] = vn.y; o[dt][2] = 0.f; o[dt][3] = 0.f;
-                    }
-                    // append the k|v record to the global cache (read back by TMA in later steps)
-                    if (lane < 2 * CH) {
-                        const int part = lane % CH;
-                        const size_t off = ((static_cast<size_t>(b) * H + h) * a.t_max + pos) * (2 * D) + lane * 8;
-                        const uint4 val = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(lane < CH ? kw : vw) + part * 16);
-                        *reinterpret_cast<uint4*>(cache_l + off) = val;
-                        __threadfence_block();     // read back by cp.async of other lanes of this warp in a later job
-                    }
-                    __syncwarp();
-                    for (int c = 0; c < nchunks; ++c) {
-                        uint8_t* st = ring_acquire(jr);
-                        const int ntok = min(CT, pos - c * CT);
-                        // S = q K^T for CT tokens: K rows are the col-major B operand as they lie in shared memory
-                        float s[NT_S][4];
-#pragma unroll
-                        for (int n = 0; n < NT_S; ++n) { s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f; }
-                        const uint32_t sk_a = smem_u32(st) + k_lane, sv_a = smem_u32(st) + v_lane;
-#pragma unroll
-                        for (int jt = 0; jt < CT / 16; ++jt)
-#pragma unroll
-                            for (int ks = 0; ks < D / 16; ++ks) {
-                                uint32_t kb[4];
-                                ldmatrix_x4(kb, sk_a + jt * 16 * REC + ks * 32);
-                                mma_16816(s[2 * jt], qa[ks][0], qa[ks][0], qa[ks][1], qa[ks][1], kb[0], kb[1]);
-                                mma_16816(s[2 * jt + 1], qa[ks][0], qa[ks][0], qa[ks][1], qa[ks][1], kb[2], kb[3]);
-                            }
-                        if (ntok < CT) {
-#pragma unroll
-                            for (int n = 0; n < NT_S; ++n) {
-                                if (n * 8 + 2 * tig >= ntok) s[n][0] = -INFINITY;
-                                if (n * 8 + 2 * tig + 1 >= ntok) s[n][1] = -INFINITY;
-                            }
-                        }
-                        float mx = -INFINITY;
-#pragma unroll
-                        for (int n = 0; n < NT_S; ++n) mx = fmaxf(mx, fmaxf(s[n][0], s[n][1]));
-                        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-                        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-                        const float mn = fmaxf(m, mx * a.scale_log2);
-                        const float corr = fast_exp2(m - mn);
-                        m = mn;
-                        lsum *= corr;
-#pragma unroll
-                        for (int dt = 0; dt < NT_O; ++dt) { o[dt][0] *= corr; o[dt][1] *= corr; }
-#pragma unroll
-                        for (int n = 0; n < NT_S; ++n) {
-                            s[n][0] = fast_exp2(fmaf(s[n][0], a.scale_log2, -mn));
-                            s[n][1] = fast_exp2(fmaf(s[n][1], a.scale_log2, -mn));
-                            lsum += s[n][0] + s[n][1];
-                        }
-                        // O += P V: the score accumulators are already laid out as the A operand
-#pragma unroll
-                        for (int jt = 0; jt < CT / 16; ++jt) {
-                            const uint32_t p0 = pack_bf16(s[2 * jt][0], s[2 * jt][1]), p1 = pack_bf16(s[2 * jt + 1][0], s[2 * jt + 1][1]);
-#pragma unroll
-                            for (int dp = 0; dp < D / 16; ++dp) {
-                                uint32_t vb[4];
-                                ldmatrix_x4_trans(vb, sv_a + jt * 16 * REC + dp * 32);
-                                mma_16816(o[2 * dp], p0, 0u, p1, 0u, vb[0], vb[1]);
-                                mma_16816(o[2 * dp + 1], p0, 0u, p1, 0u, vb[2], vb[3]);
-                            }
-                        }
-                        ring_release<D>(jr, plan, lane);
-                    }
-                    lsum += __shfl_xor_sync(0xffffffffu, lsum, 1);
-                    lsum += __shfl_xor_sync(0xffffffffu, lsum, 2);
-                    const float inv = 1.0f / lsum;
-                    // every quad holds the same output row: quad g sends it to CTA g of the cluster
-                    if (g < CL) {
-                        const uint32_t dst = map_to_cta(smem_u32(Y + sl * pe + (h * D + 2 * tig) * 2), g);
-#pragma unroll
-                        for (int dt = 0; dt < NT_O; ++dt) st_cluster_u32(dst + dt * 16, pack_bf16(o[dt][0] * inv, o[dt][1] * inv));
-                    }
+        // One loop over the 4 L + 1 linear phases of a step (c_attn [+ attention], c_proj, c_fc, mlp c_proj per block,
+        // then the logits), so that every piece of code exists once: the kernel has to fit the instruction cache.
+        for (int p = 0; p <= 4 * a.L; ++p) {
+            const int l = p >> 2;
+            const int kind = (l == a.L) ? 4 : (p & 3);         // 0 c_attn, 1 c_proj, 2 c_fc, 3 mlp c_proj, 4 logits
+            const MegaLayer& lw = a.layers[l < a.L ? l : 0];
+            // ---- LayerNorm in front of c_attn (ln_1), c_fc (ln_2) and the logits (ln_f) ----
+            if (kind == 0 || kind == 2 || kind == 4) {
+                layernorm_rows(X, bufN, pe, E, lnf, a.eps, use_ln, warp, lane);
+                if (use_ln && kind != 0) {         // (ln_2's parameters are fetched after the attention)
+                    const bool more = kind == 2 && l + 1 < a.L;          // next: ln_1 of the next block, else ln_f / ln_1 of block 0
+                    const MegaLayer& nx = a.layers[more ? l + 1 : 0];
+                    if (kind == 2 && !more) ln_prefetch(lnf, P + a.lnf_g, P + a.lnf_b, E, lane);
+                    else ln_prefetch(lnf, P + nx.ln1_g, P + nx.ln1_b, E, lane);
                 }
+                __syncthreads();
+                MG_PROF(kind == 0 ? 1 : 15)
             }
-            if (use_ln) ln_prefetch(lnf, P + lw.ln2_g, P + lw.ln2_b, E, lane);
-            MG_PROF(3)
-            cluster_sync_all();                    // A: attention output of all heads is in Y everywhere
-            MG_PROF(4)
-            // ---- P4: x2 = x1 + c_proj(att) for this CTA's columns, all-gathered into X ----
-            MG_WAIT_SLOT(2)
-            run_phase<D>(ph_proj, Y, pe, jr, plan, red, warp, lane, [&](int col, int seq, float2 lo, float2 hi) {
-                const int off = seq * pe + (crank * HS + col) * 2;
-                const float2 r0 = unpack_bf16(*reinterpret_cast<const uint32_t*>(bufN + off));
-                const float2 r1 = unpack_bf16(*reinterpret_cast<const uint32_t*>(bufN + off + 16));
-                broadcast_u32<CL>(X + off, pack_bf16(lo.x + r0.x, lo.y + r0.y), seq < G);
-                broadcast_u32<CL>(X + off + 16, pack_bf16(hi.x + r1.x, hi.y + r1.y), seq < G);
-            });
-            MG_PROF(5)
-            cluster_sync_all();                    // B: x2 is in X everywhere
-            MG_PROF(6)
-            // ---- P5: m = ln_2(x2);  P6: gelu(c_fc(m)) for this CTA's columns, all-gathered into bufG ----
-            layernorm_rows(X, bufN, pe, E, lnf, a.eps, use_ln, warp, lane);
-            if (use_ln) {
-                if (l + 1 < a.L) ln_prefetch(lnf, P + a.layers[l + 1].ln1_g, P + a.layers[l + 1].ln1_b, E, lane);
-                else ln_prefetch(lnf, P + a.lnf_g, P + a.lnf_b, E, lane);
-            }
-            __syncthreads();
-            MG_WAIT_SLOT(3)
-            run_phase<D>(ph_fc, bufN, pe, jr, plan, red, warp, lane, [&](int col, int seq, float2 lo, float2 hi) {
-                const int off = seq * pf + (crank * FS + col) * 2;
-                broadcast_u32<CL>(bufG + off, pack_bf16(gelu_tanh(lo.x), gelu_tanh(lo.y)), seq < G);
-                broadcast_u32<CL>(bufG + off + 16, pack_bf16(gelu_tanh(hi.x), gelu_tanh(hi.y)), seq < G);
-            });
-            MG_PROF(7)
-            cluster_sync_all();                    // C: gelu output is in bufG everywhere
-            MG_PROF(8)
-            // ---- P7: out = x2 + c_proj(gelu) for this CTA's columns, all-gathered into Y ----
-            MG_WAIT_SLOT(4)
-            run_phase<D>(ph_proj2, bufG, pf, jr, plan, red, warp, lane, [&](int col, int seq, float2 lo, float2 hi) {
-                const int off = seq * pe + (crank * HS + col) * 2;
-                const float2 r0 = unpack_bf16(*reinterpret_cast<const uint32_t*>(X + off));
-                const float2 r1 = unpack_bf16(*reinterpret_cast<const uint32_t*>(X + off + 16));
-                broadcast_u32<CL>(Y + off, pack_bf16(lo.x + r0.x, lo.y + r0.y), seq < G);
-                broadcast_u32<CL>(Y + off + 16, pack_bf16(hi.x + r1.x, hi.y + r1.y), seq < G);
-            });
-            MG_PROF(9)
-            cluster_sync_all();                    // D: the block output is in Y everywhere
-            MG_PROF(10)
-            uint8_t* t = X; X = Y; Y = t;
-        }
-
-        // ---- ln_f, tied logits for this CTA's vocabulary rows -> Z of CTA 0 ----
-        {
-            layernorm_rows(X, bufN, pe, E, lnf, a.eps, use_ln, warp, lane);
-            if (use_ln) ln_prefetch(lnf, P + a.layers[0].ln1_g, P + a.layers[0].ln1_b, E, lane);
-            __syncthreads();
+            // ---- the linear layer: this CTA's output columns for all sequences ----
+            const Phase ph = kind == 0 ? ph_attn : kind == 1 ? ph_proj : kind == 2 ? ph_fc : kind == 3 ? ph_proj2 : ph_logits;
+            const uint8_t* src = (kind == 1) ? Y : (kind == 3) ? bufG : bufN;      // x1 | attention output | ln_2(x2) | gelu
+            const int src_pitch = (kind == 3) ? pf : pe;
+            // epilogue: where the result goes (all-gathered into every CTA but for q, k, v), what is added to it
+            uint8_t* dst = (kind == 1) ? X : (kind == 2) ? bufG : Y;
+            const uint8_t* res = (kind == 1) ? bufN : X;                             // residual stream: x1, then x2
+            const int dst_pitch = (kind == 2) ? pf : pe;
+            const int col0 = crank * ((kind == 2) ? FS : HS);
             const uint32_t zbase = map_to_cta(smem_u32(Z), 0);
-            MG_WAIT_SLOT(5)
-            run_phase<D>(ph_logits, bufN, pe, jr, plan, red, warp, lane, [&](int col, int seq, float2 lo, float2 hi) {
-                const uint32_t dst = zbase + (seq * sm.zp + crank * VS + col) * 4;
-                if (seq < G) {
-                    st_cluster_v2(dst, __float_as_uint(lo.x), __float_as_uint(lo.y));
-                    st_cluster_v2(dst + 32, __float_as_uint(hi.x), __float_as_uint(hi.y));
+            MG_WAIT_SLOT(kind == 0 ? 0 : kind + 1)
+            run_phase<D>(ph, src, src_pitch, jr, plan, red, warp, lane, [&](int col, int seq, float2 lo, float2 hi) {
+                if (kind == 0) {                   // q, k, v of this CTA's heads (bf16, local)
+                    uint8_t* q = qkvs + (seq * 3 * HS + col) * 2;
+                    *reinterpret_cast<uint32_t*>(q) = pack_bf16(lo.x, lo.y);
+                    *reinterpret_cast<uint32_t*>(q + 16) = pack_bf16(hi.x, hi.y);
+                } else if (kind == 4) {            // logits -> CTA 0 (fp32)
+                    const uint32_t z = zbase + (seq * sm.zp + crank * VS + col) * 4;
+                    if (seq < G) {
+                        st_cluster_v2(z, __float_as_uint(lo.x), __float_as_uint(lo.y));
+                        st_cluster_v2(z + 32, __float_as_uint(hi.x), __float_as_uint(hi.y));
+                    }
+                } else {
+                    const int off = seq * dst_pitch + (col0 + col) * 2;
+                    if (kind == 2) {               // gelu(c_fc)
+                        lo.x = gelu_tanh(lo.x); lo.y = gelu_tanh(lo.y); hi.x = gelu_tanh(hi.x); hi.y = gelu_tanh(hi.y);
+                    } else {                       // x2 = x1 + c_proj(att)  |  out = x2 + c_proj(gelu)
+                        const float2 r0 = unpack_bf16(*reinterpret_cast<const uint32_t*>(res + off));
+                        const float2 r1 = unpack_bf16(*reinterpret_cast<const uint32_t*>(res + off + 16));
+                        lo.x += r0.x; lo.y += r0.y; hi.x += r1.x; hi.y += r1.y;
+                    }
+                    broadcast_u32<CL>(dst + off, pack_bf16(lo.x, lo.y), seq < G);
+                    broadcast_u32<CL>(dst + off + 16, pack_bf16(hi.x, hi.y), seq < G);
                 }
             });
+            if (kind == 4) break;                  // the step ends with the sampling below
+            if (kind == 0) {
+                __syncthreads();
+                MG_PROF(2)
+                // ---- P3: append k, v; attention of (sequence, head) pairs on the tensor cores; all-gather into Y ----
+                {
+                    MG_WAIT_SLOT(1)
+                    __nv_bfloat16* cache_l = a.cache + static_cast<size_t>(l) * a.layer_stride;
+                    const int npairs = G * HPC;
+                    const int nmine = (npairs > warp) ? (npairs - warp + MG_WARPS - 1) / MG_WARPS : 0;
+                    const int nchunks = (pos + CT - 1) / CT;
+                    // ldmatrix row addresses of this lane inside a 16-token tile of k|v records
+                    const int mi = lane >> 3, mr = lane & 7;
+                    const uint32_t k_lane = static_cast<uint32_t>(((mi >> 1) * 8 + mr) * REC + (mi & 1) * 16);
+                    const uint32_t v_lane = static_cast<uint32_t>(((mi & 1) * 8 + mr) * REC + 2 * D + (mi >> 1) * 16);
+                    for (int pi = 0; pi < nmine; ++pi) {
+                        const int q = warp + MG_WARPS * pi;
+                        const int sl = q / HPC, hh = q % HPC;
+                        const int b = s0 + sl, h = crank * HPC + hh;
+                        const uint32_t* qw = reinterpret_cast<const uint32_t*>(qkvs + (sl * 3 * HS + hh * D) * 2);
+                        const uint32_t* kw = qw + HS / 2;
+                        const uint32_t* vw = qw + HS;
+                        // query as the A operand (every MMA row carries the same query), new token as the softmax seed
+                        uint32_t qa[D / 16][2];
+                        float snew = 0.f;
+    #pragma unroll
+                        for (int ks = 0; ks < D / 16; ++ks) {
+                            qa[ks][0] = qw[ks * 8 + tig];
+                            qa[ks][1] = qw[ks * 8 + 4 + tig];
+                            const float2 q0 = unpack_bf16(qa[ks][0]), q1 = unpack_bf16(qa[ks][1]);
+                            const float2 k0 = unpack_bf16(kw[ks * 8 + tig]), k1 = unpack_bf16(kw[ks * 8 + 4 + tig]);
+                            snew += q0.x * k0.x + q0.y * k0.y + q1.x * k1.x + q1.y * k1.y;
+                        }
+                        snew += __shfl_xor_sync(0xffffffffu, snew, 1);
+                        snew += __shfl_xor_sync(0xffffffffu, snew, 2);
+                        float m = snew * a.scale_log2;                  // running maximum (log2 units)
+                        float lsum = (tig == 0) ? 1.f : 0.f;            // this lane's share of the denominator
+                        float o[NT_O][4];
+    #pragma unroll
+                        for (int dt = 0; dt < NT_O; ++dt) {
+                            const float2 vn = unpack_bf16(vw[dt * 4 + tig]);
+                            o[dt][0] = vn.x; o[dt][1] = vn.y; o[dt][2] = 0.f; o[dt][3] = 0.f;
+                        }
+                        // append the k|v record to the global cache (read back by TMA in later steps)
+                        if (lane < 2 * CH) {
+                            const int part = lane % CH;
+                            const size_t off = ((static_cast<size_t>(b) * H + h) * a.t_max + pos) * (2 * D) + lane * 8;
+                            const uint4 val = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(lane < CH ? kw : vw) + part * 16);
+                            *reinterpret_cast<uint4*>(cache_l + off) = val;
+                            __threadfence_block();     // read back by cp.async of other lanes of this warp in a later job
+                        }
+                        __syncwarp();
+                        for (int c = 0; c < nchunks; ++c) {
+                            uint8_t* st = ring_acquire(jr);
+                            const int ntok = min(CT, pos - c * CT);
+                            // S = q K^T for CT tokens: K rows are the col-major B operand as they lie in shared memory
+                            float s[NT_S][4];
+    #pragma unroll
+                            for (int n = 0; n < NT_S; ++n) { s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f; }
+                            const uint32_t sk_a = smem_u32(st) + k_lane, sv_a = smem_u32(st) + v_lane;
+    #pragma unroll
+                            for (int jt = 0; jt < CT / 16; ++jt)
+    #pragma unroll
+                                for (int ks = 0; ks < D / 16; ++ks) {
+                                    uint32_t kb[4];
+                                    ldmatrix_x4(kb, sk_a + jt * 16 * REC + ks * 32);
+                                    mma_16816(s[2 * jt], qa[ks][0], qa[ks][0], qa[ks][1], qa[ks][1], kb[0], kb[1]);
+                                    mma_16816(s[2 * jt + 1], qa[ks][0], qa[ks][0], qa[ks][1], qa[ks][1], kb[2], kb[3]);
+                                }
+                            if (ntok < CT) {
+    #pragma unroll
+                                for (int n = 0; n < NT_S; ++n) {
+                                    if (n * 8 + 2 * tig >= ntok) s[n][0] = -INFINITY;
+                                    if (n * 8 + 2 * tig + 1 >= ntok) s[n][1] = -INFINITY;
+                                }
+                            }
+                            float mx = -INFINITY;
+    #pragma unroll
+                            for (int n = 0; n < NT_S; ++n) mx = fmaxf(mx, fmaxf(s[n][0], s[n][1]));
+                            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+                            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+                            const float mn = fmaxf(m, mx * a.scale_log2);
+                            const float corr = fast_exp2(m - mn);
+                            m = mn;
+                            lsum *= corr;
+    #pragma unroll
+                            for (int dt = 0; dt < NT_O; ++dt) { o[dt][0] *= corr; o[dt][1] *= corr; }
+    #pragma unroll
+                            for (int n = 0; n < NT_S; ++n) {
+                                s[n][0] = fast_exp2(fmaf(s[n][0], a.scale_log2, -mn));
+                                s[n][1] = fast_exp2(fmaf(s[n][1], a.scale_log2, -mn));
+                                lsum += s[n][0] + s[n][1];
+                            }
+                            // O += P V: the score accumulators are already laid out as the A operand
+    #pragma unroll
+                            for (int jt = 0; jt < CT / 16; ++jt) {
+                                const uint32_t p0 = pack_bf16(s[2 * jt][0], s[2 * jt][1]), p1 = pack_bf16(s[2 * jt + 1][0], s[2 * jt + 1][1]);
+    #pragma unroll
+                                for (int dp = 0; dp < D / 16; ++dp) {
+                                    uint32_t vb[4];
+                                    ldmatrix_x4_trans(vb, sv_a + jt * 16 * REC + dp * 32);
+                                    mma_16816(o[2 * dp], p0, 0u, p1, 0u, vb[0], vb[1]);
+                                    mma_16816(o[2 * dp + 1], p0, 0u, p1, 0u, vb[2], vb[3]);
+                                }
+                            }
+                            ring_release<D>(jr, plan, lane);
+                        }
+                        lsum += __shfl_xor_sync(0xffffffffu, lsum, 1);
+                        lsum += __shfl_xor_sync(0xffffffffu, lsum, 2);
+                        const float inv = 1.0f / lsum;
+                        // every quad holds the same output row: quad g sends it to CTA g of the cluster
+                        if (g < CL) {
+                            const uint32_t dst = map_to_cta(smem_u32(Y + sl * pe + (h * D + 2 * tig) * 2), g);
+    #pragma unroll
+                            for (int dt = 0; dt < NT_O; ++dt) st_cluster_u32(dst + dt * 16, pack_bf16(o[dt][0] * inv, o[dt][1] * inv));
+                        }
+                    }
+                }
+                if (use_ln) ln_prefetch(lnf, P + lw.ln2_g, P + lw.ln2_b, E, lane);
+            }
+            MG_PROF(kind == 0 ? 3 : 2 * kind + 3)
+            cluster_sync_all();                    // the all-gathered activation is complete in every CTA
+            MG_PROF(2 * kind + 4)
+            if (kind == 3) { uint8_t* t = X; X = Y; Y = t; }        // the block output becomes the next block's input
         }
         MG_PROF(11)
         cluster_sync_all();                        // E: all logits are in CTA 0
@@ -809,6 +793,8 @@ decode_mega_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ M
         cluster_sync_all();                        // F: next tokens are everywhere
         MG_PROF(14)
     }
+    if (profiling)
+        for (int i = 0; i < 24; ++i) a.prof[i] = prof_acc[i];
 #undef MG_PROF
 #undef MG_WAIT_SLOT
 }
@@ -897,6 +883,7 @@ static MegaSmem mega_smem_layout(int E, int F, int V, int D, int CL, int nst, in
     s.ring = take((MG_WARPS * nst + nst_extra) * MG_STAGE);
     s.bars = take((MG_WARPS * nst + nst_extra) * 8);
     s.toks = take(MG_ROWS * 4);
+    s.prof = take(24 * 8);
     s.total = off;
     return s;
 }

@@ -51,10 +51,11 @@ for size in [v for v in impls if v != 1]:
     torch.cuda.synchronize()
     _lib.call('cb200_set_decode_profile', None)
     c = counters.cpu().tolist()
-    total = sum(c[:15]) or 1
+    total = sum(c[:16]) or 1
     print('phase profile, cluster size %s, over %d steps (cycles per step; per layer for block phases):' % (size or 'auto', N))
     for i, name in enumerate(names):
         per = c[i] / N / (L if 1 <= i <= 10 else 1)
         print('  %-14s %9.0f cyc  %5.1f%%' % (name, per, 100.0 * c[i] / total))
+    print('  (ln_2 alone, up to its __syncthreads: %.0f cyc per layer)' % (c[15] / N / L))
     print('  thread 0 waited for its ring jobs (cyc per layer): c_attn %.0f, attention %.0f, c_proj %.0f, c_fc %.0f, mlp c_proj %.0f; logits %.0f per step'
           % tuple([c[16 + k] / N / L for k in range(5)] + [c[21] / N]))
