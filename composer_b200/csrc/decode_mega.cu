@@ -143,6 +143,17 @@ struct Phase {
 // ---------------------------------------------------------------------------
 constexpr int MG_STAGE = MG_SLOT;          // >= the 4 KB of a KV stage
 
+// Byte offset of 16-byte piece `c` of token `t` inside a KV stage.  A k|v record is 4 D bytes (4, 8 or 16 pieces);
+// ldmatrix reads one piece of 8 consecutive tokens, which would land in 2 (d_h 16) or 1 (d_h >= 32) of the 8
+// 16-byte bank groups, a 4- or 8-way conflict that made shared memory the limiter of the attention phase.  The
+// piece index is XOR-ed with token bits so that those 8 reads cover all 8 groups; cp.async writes the pieces there.
+template <int D>
+__device__ __forceinline__ uint32_t kv_piece_off(int t, int c) {
+    constexpr int REC = 4 * D;
+    const int sw = (D == 16) ? ((t >> 1) & 3) : (t & 7);
+    return static_cast<uint32_t>(t * REC + ((c ^ sw) << 4));
+}
+
 struct JobPlan {           // what the cursor needs to enumerate this warp's jobs (uniform per warp)
     const uint8_t* wsrc;   // this CTA's weight stream (one step; it repeats every step)
     const __nv_bfloat16* cache;
@@ -204,10 +215,13 @@ __device__ __forceinline__ void job_issue(const JobPlan& p, JobCursor& c, uint8_
         const size_t off = ((static_cast<size_t>(b) * p.H + h) * p.t_max + static_cast<size_t>(c.c) * CT) * (2 * D);
         const int pieces = min(CT, c.step - c.c * CT) * (4 * D / 16);             // 16-byte pieces that exist
         const uint8_t* src = reinterpret_cast<const uint8_t*>(p.cache + static_cast<size_t>(c.l) * p.layer_stride + off);
+        constexpr int PR = D / 4;                   // 16-byte pieces per k|v record
+        const uint32_t st0 = smem_u32(stage);
 #pragma unroll
         for (int i = 0; i < CT * 4 * D / 512; ++i) {
             const int idx = i * 32 + lane;
-            cp_async_16_hint(dst + i * 512, src + (idx < pieces ? idx * 16 : 0), idx < pieces, p.kv_policy);
+            cp_async_16_hint(st0 + kv_piece_off<D>(idx / PR, idx % PR), src + (idx < pieces ? idx * 16 : 0), idx < pieces,
+                             p.kv_policy);
         }
         if (++c.c == (c.step + CT - 1) / CT) { c.c = 0; ++c.pi; }
     }
@@ -653,10 +667,17 @@ decode_mega_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ M
                     const int npairs = G * HPC;
                     const int nmine = (npairs > warp) ? (npairs - warp + MG_WARPS - 1) / MG_WARPS : 0;
                     const int nchunks = (pos + CT - 1) / CT;
-                    // ldmatrix row addresses of this lane inside a 16-token tile of k|v records
+                    // ldmatrix row addresses of this lane inside a 16-token tile of k|v records: the K rows are the A
+                    // operand of the score MMA (16 tokens x d_h), the V rows the B operand of P.V (transposed load)
+                    // (pieces are swizzled, see kv_piece_off; the swizzle of a lane's row does not depend on the tile)
                     const int mi = lane >> 3, mr = lane & 7;
-                    const uint32_t k_lane = static_cast<uint32_t>(((mi >> 1) * 8 + mr) * REC + (mi & 1) * 16);
-                    const uint32_t v_lane = static_cast<uint32_t>(((mi & 1) * 8 + mr) * REC + 2 * D + (mi >> 1) * 16);
+                    constexpr int PR = D / 4;
+                    uint32_t k_lane[D / 16], v_lane[D / 16];
+    #pragma unroll
+                    for (int ks = 0; ks < D / 16; ++ks) {
+                        k_lane[ks] = kv_piece_off<D>((mi & 1) * 8 + mr, ks * 2 + (mi >> 1));
+                        v_lane[ks] = kv_piece_off<D>((mi & 1) * 8 + mr, PR / 2 + ks * 2 + (mi >> 1));
+                    }
                     for (int pi = 0; pi < nmine; ++pi) {
                         const int q = warp + MG_WARPS * pi;
                         const int sl = q / HPC, hh = q % HPC;
@@ -664,28 +685,31 @@ decode_mega_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ M
                         const uint32_t* qw = reinterpret_cast<const uint32_t*>(qkvs + (sl * 3 * HS + hh * D) * 2);
                         const uint32_t* kw = qw + HS / 2;
                         const uint32_t* vw = qw + HS;
-                        // query as the A operand (every MMA row carries the same query), new token as the softmax seed
-                        uint32_t qa[D / 16][2];
+                        // Scores as K q: the 16 tokens of a tile are the MMA rows and the query is column 0 of the B
+                        // operand (only the lanes of quad 0 hold it), so a lane with tig == 0 gets the scores of tokens
+                        // g and g + 8 and nothing is computed 8 times over.  New token = the softmax seed.
+                        uint32_t qb[D / 16][2];
                         float snew = 0.f;
     #pragma unroll
                         for (int ks = 0; ks < D / 16; ++ks) {
-                            qa[ks][0] = qw[ks * 8 + tig];
-                            qa[ks][1] = qw[ks * 8 + 4 + tig];
-                            const float2 q0 = unpack_bf16(qa[ks][0]), q1 = unpack_bf16(qa[ks][1]);
+                            const uint32_t q0w = qw[ks * 8 + tig], q1w = qw[ks * 8 + 4 + tig];
+                            qb[ks][0] = (g == 0) ? q0w : 0u;
+                            qb[ks][1] = (g == 0) ? q1w : 0u;
+                            const float2 q0 = unpack_bf16(q0w), q1 = unpack_bf16(q1w);
                             const float2 k0 = unpack_bf16(kw[ks * 8 + tig]), k1 = unpack_bf16(kw[ks * 8 + 4 + tig]);
                             snew += q0.x * k0.x + q0.y * k0.y + q1.x * k1.x + q1.y * k1.y;
                         }
                         snew += __shfl_xor_sync(0xffffffffu, snew, 1);
                         snew += __shfl_xor_sync(0xffffffffu, snew, 2);
-                        float m = snew * a.scale_log2;                  // running maximum (log2 units)
-                        float lsum = (tig == 0) ? 1.f : 0.f;            // this lane's share of the denominator
-                        float o[NT_O][4];
+                        float m = snew * a.scale_log2;                  // running maximum (log2 units), warp-uniform
+                        float lsum = (lane == 0) ? 1.f : 0.f;           // this lane's share of the denominator
+                        float o[NT_O][4];                               // row 0 of P.V; every quad carries a copy
     #pragma unroll
                         for (int dt = 0; dt < NT_O; ++dt) {
                             const float2 vn = unpack_bf16(vw[dt * 4 + tig]);
                             o[dt][0] = vn.x; o[dt][1] = vn.y; o[dt][2] = 0.f; o[dt][3] = 0.f;
                         }
-                        // append the k|v record to the global cache (read back by TMA in later steps)
+                        // append the k|v record to the global cache
                         if (lane < 2 * CH) {
                             const int part = lane % CH;
                             const size_t off = ((static_cast<size_t>(b) * H + h) * a.t_max + pos) * (2 * D) + lane * 8;
@@ -697,58 +721,62 @@ decode_mega_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ M
                         for (int c = 0; c < nchunks; ++c) {
                             uint8_t* st = ring_acquire(jr);
                             const int ntok = min(CT, pos - c * CT);
-                            // S = q K^T for CT tokens: K rows are the col-major B operand as they lie in shared memory
-                            float s[NT_S][4];
+                            const uint32_t st_a = smem_u32(st);
+                            // S^T = K q: s[j][0] = token 16 j + g, s[j][2] = token 16 j + 8 + g (lanes with tig == 0)
+                            float s[CT / 16][4];
     #pragma unroll
-                            for (int n = 0; n < NT_S; ++n) { s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f; }
-                            const uint32_t sk_a = smem_u32(st) + k_lane, sv_a = smem_u32(st) + v_lane;
-    #pragma unroll
-                            for (int jt = 0; jt < CT / 16; ++jt)
+                            for (int jt = 0; jt < CT / 16; ++jt) {
+                                s[jt][0] = s[jt][1] = s[jt][2] = s[jt][3] = 0.f;
     #pragma unroll
                                 for (int ks = 0; ks < D / 16; ++ks) {
-                                    uint32_t kb[4];
-                                    ldmatrix_x4(kb, sk_a + jt * 16 * REC + ks * 32);
-                                    mma_16816(s[2 * jt], qa[ks][0], qa[ks][0], qa[ks][1], qa[ks][1], kb[0], kb[1]);
-                                    mma_16816(s[2 * jt + 1], qa[ks][0], qa[ks][0], qa[ks][1], qa[ks][1], kb[2], kb[3]);
-                                }
-                            if (ntok < CT) {
-    #pragma unroll
-                                for (int n = 0; n < NT_S; ++n) {
-                                    if (n * 8 + 2 * tig >= ntok) s[n][0] = -INFINITY;
-                                    if (n * 8 + 2 * tig + 1 >= ntok) s[n][1] = -INFINITY;
+                                    uint32_t ka[4];
+                                    ldmatrix_x4(ka, st_a + jt * 16 * REC + k_lane[ks]);
+                                    mma_16816(s[jt], ka[0], ka[1], ka[2], ka[3], qb[ks][0], qb[ks][1]);
                                 }
                             }
                             float mx = -INFINITY;
     #pragma unroll
-                            for (int n = 0; n < NT_S; ++n) mx = fmaxf(mx, fmaxf(s[n][0], s[n][1]));
-                            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-                            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+                            for (int jt = 0; jt < CT / 16; ++jt) {
+                                // the other lanes hold columns 2, 4, 6 of the product (zeros): keep them out of the maximum
+                                if (tig != 0 || jt * 16 + g >= ntok) s[jt][0] = -INFINITY;
+                                if (tig != 0 || jt * 16 + 8 + g >= ntok) s[jt][2] = -INFINITY;
+                                mx = fmaxf(mx, fmaxf(s[jt][0], s[jt][2]));
+                            }
+                            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+                            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+                            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+                            mx = __shfl_sync(0xffffffffu, mx, 0);        // lanes with tig != 0 only saw -inf
                             const float mn = fmaxf(m, mx * a.scale_log2);
                             const float corr = fast_exp2(m - mn);
                             m = mn;
                             lsum *= corr;
     #pragma unroll
                             for (int dt = 0; dt < NT_O; ++dt) { o[dt][0] *= corr; o[dt][1] *= corr; }
-    #pragma unroll
-                            for (int n = 0; n < NT_S; ++n) {
-                                s[n][0] = fast_exp2(fmaf(s[n][0], a.scale_log2, -mn));
-                                s[n][1] = fast_exp2(fmaf(s[n][1], a.scale_log2, -mn));
-                                lsum += s[n][0] + s[n][1];
-                            }
-                            // O += P V: the score accumulators are already laid out as the A operand
+                            // O += P V: the probabilities of 16 tokens travel to the A-operand layout (row 0 = p over k)
+                            // as bf16 pairs: lane (g, tig) needs tokens 2 tig, 2 tig + 1 (from lanes 8 tig, 8 tig + 4)
     #pragma unroll
                             for (int jt = 0; jt < CT / 16; ++jt) {
-                                const uint32_t p0 = pack_bf16(s[2 * jt][0], s[2 * jt][1]), p1 = pack_bf16(s[2 * jt + 1][0], s[2 * jt + 1][1]);
+                                const float p_lo = fast_exp2(fmaf(s[jt][0], a.scale_log2, -mn));
+                                const float p_hi = fast_exp2(fmaf(s[jt][2], a.scale_log2, -mn));
+                                lsum += p_lo + p_hi;
+                                const uint32_t pk = pack_bf16(p_lo, p_hi);            // {token g, token g + 8} of this tile
+                                const uint32_t y0 = __shfl_sync(0xffffffffu, pk, 8 * tig);
+                                const uint32_t y1 = __shfl_sync(0xffffffffu, pk, 8 * tig + 4);
+                                const uint32_t a0 = __byte_perm(y0, y1, 0x5410);      // tokens 2 tig, 2 tig + 1
+                                const uint32_t a2 = __byte_perm(y0, y1, 0x7632);      // tokens 2 tig + 8, 2 tig + 9
     #pragma unroll
                                 for (int dp = 0; dp < D / 16; ++dp) {
                                     uint32_t vb[4];
-                                    ldmatrix_x4_trans(vb, sv_a + jt * 16 * REC + dp * 32);
-                                    mma_16816(o[2 * dp], p0, 0u, p1, 0u, vb[0], vb[1]);
-                                    mma_16816(o[2 * dp + 1], p0, 0u, p1, 0u, vb[2], vb[3]);
+                                    ldmatrix_x4_trans(vb, st_a + jt * 16 * REC + v_lane[dp]);
+                                    mma_16816(o[2 * dp], a0, 0u, a2, 0u, vb[0], vb[1]);
+                                    mma_16816(o[2 * dp + 1], a0, 0u, a2, 0u, vb[2], vb[3]);
                                 }
                             }
                             ring_release<D>(jr, plan, lane);
                         }
+                        lsum += __shfl_xor_sync(0xffffffffu, lsum, 4);
+                        lsum += __shfl_xor_sync(0xffffffffu, lsum, 8);
+                        lsum += __shfl_xor_sync(0xffffffffu, lsum, 16);
                         lsum += __shfl_xor_sync(0xffffffffu, lsum, 1);
                         lsum += __shfl_xor_sync(0xffffffffu, lsum, 2);
                         const float inv = 1.0f / lsum;
@@ -1015,6 +1043,10 @@ int decode_mega(MegaArgs args, int D, int max_clusters, int cluster_size, uint8_
     CB200_REQUIRE(mega_shape_ok(args.E, args.H, D, args.V, args.L, CL), "cluster size %d does not fit this shape", CL);
     const int resident = decode_mega_capacity(args.E, args.H, args.V, D, args.L, CL);
     CB200_REQUIRE(resident >= 1, "the cluster decode kernel does not fit on this device");
+    if (const char* env = getenv("CB200_DECODE_MAX_CLUSTERS")) {       // tuning knob
+        const int v = atoi(env);
+        if (v > 0 && (max_clusters == 0 || v < max_clusters)) max_clusters = v;
+    }
     const int ncl = mega_cluster_count(args.B, resident, max_clusters);
     const MegaSmem sm = mega_smem_fit(args.E, args.V, D, CL, args.L);
     // ---- pack the weight stream ----
