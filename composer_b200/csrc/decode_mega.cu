@@ -20,16 +20,20 @@
 //    the 16 biases).
 //  * KV cache, [L, B, H, t_max, 2, d_h] (k and v of a token adjacent): a warp
 //    owns one (sequence, head) pair at a time and streams it in 4 KB stages;
-//    scores and P.V run on the tensor cores (q as the A operand, K rows / V
-//    rows as B through ldmatrix / ldmatrix.trans, the score accumulators
-//    re-used as the A operand of P.V), the softmax stays online.
+//    scores and P.V run on the tensor cores (scores as K q: the 16 tokens of a
+//    tile are the MMA rows, the query is one column of the B operand; the
+//    probabilities travel to the A-operand layout of P.V with two shuffles per
+//    tile; V rows through ldmatrix.trans), the softmax stays online.
 //  * Everything a warp reads from global memory on the hot path, weight slots
 //    and KV stages alike, is one static sequence of copy jobs in the warp's own
 //    program order (it depends on the step, not on data).  The warp owns 2-3
-//    ring stages; after consuming job k it issues job k + stages (16-byte
-//    cp.async by the whole warp, completion on an mbarrier), so the weights of
-//    a GEMM phase are requested while the previous phase or the attention is
-//    still running.  L2 eviction hints keep the weight stream resident.
+//    ring stages; after consuming job k it issues job k + stages (one TMA bulk
+//    copy of 4 KB by one lane, completion on an mbarrier), so the weights of a
+//    GEMM phase are requested while the previous phase or the attention is
+//    still running.  L2 eviction hints keep the weight stream resident.  The
+//    16-byte pieces of a cached record are XOR-swizzled (in global memory, so
+//    that a chunk stays one linear copy): ldmatrix on the stage is then free of
+//    bank conflicts, which were what bounded the attention phase before.
 // The first CTA of each cluster draws the tokens (same Philox / inverse-CDF
 // rule as logits_sample_kernel) and broadcasts them.
 //
@@ -74,11 +78,9 @@ __device__ __forceinline__ void st_cluster_v2(uint32_t addr, uint32_t x, uint32_
 __device__ __forceinline__ void st_cluster_u32(uint32_t addr, uint32_t v) {
     asm volatile("st.shared::cluster.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
-// Copies global -> shared are 16-byte cp.async (LDGSTS) issued by the whole warp, 512 contiguous bytes per
-// instruction, completion reported to an mbarrier: measured here, one SM ingests ~3x more through this path than
-// through cp.async.bulk (whose per-SM engine moved ~22 B/clk whatever the copy size or the source, L2 or HBM).
-// L2 eviction policies: the KV cache is streamed once per step (evict first), the weight stream is re-read by every
-// cluster every step (evict last), so that 1 GB of cache reads per step does not push the 13 MB of weights out.
+// L2 eviction policies of the copies: the KV cache is streamed once per step (evict first), the weight stream is
+// re-read by every cluster every step (evict last), so that 1 GB of cache reads per step does not push the 13 MB of
+// weights out of L2.
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {
     uint64_t p;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
@@ -94,15 +96,11 @@ __device__ __forceinline__ uint64_t l2_policy_evict_last() {
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
-__device__ __forceinline__ void cp_async_16_hint(uint32_t dst, const void* src, bool valid, uint64_t policy) {
-    const int src_bytes = valid ? 16 : 0;          // src-size 0 => the 16 bytes are zero-filled
-    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;" ::"r"(dst), "l"(src), "r"(src_bytes),
-                 "l"(policy)
+// TMA bulk copy global -> shared (one instruction, one thread), completion as transaction bytes on an mbarrier.
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
                  : "memory");
-}
-// The mbarrier receives one arrival from this thread once all its cp.async issued so far have landed.
-__device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mma_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
                                           uint32_t b1) {
@@ -131,6 +129,7 @@ struct MegaSmem {        // shared-memory layout and weight-stream plan (compute
 // consecutive slots (128 of K each) of the weight stream.
 struct Phase {
     int ntiles, ksplit, sub;
+    int nt0, ks0;        // this warp's unit when the K is split (unit = warp): tile and K part
 };
 
 // ---------------------------------------------------------------------------
@@ -182,13 +181,11 @@ struct JobRing {
 
 __device__ __forceinline__ int units_of(int warp, int n) { return n > warp ? (n - warp + MG_WARPS - 1) / MG_WARPS : 0; }
 
-// Issues the job at the cursor into `stage` (the whole warp: 8 x 512 bytes + completion arrival on `bar`, whose
-// phase needs 32 arrivals) and advances the cursor.  D selects the KV geometry.  A KV stage is zero-filled beyond
-// its tokens, so stale rows never reach an MMA.
+// Issues the job at the cursor into `stage` and advances the cursor (all lanes advance it, lane 0 copies).  D selects
+// the KV geometry.
 template <int D>
 __device__ __forceinline__ void job_issue(const JobPlan& p, JobCursor& c, uint8_t* stage, uint64_t* bar, int lane) {
     constexpr int CT = MG_CT(D);
-    const uint32_t dst = smem_u32(stage) + lane * 16;
     int wpos = -1;                                  // weight job: stream position
     for (;;) {
         if (c.step >= p.steps) return;
@@ -204,28 +201,24 @@ __device__ __forceinline__ void job_issue(const JobPlan& p, JobCursor& c, uint8_
             ++c.step; c.l = 0; c.k = 0; c.pi = 0; c.c = 0;
         }
     }
+    // one TMA bulk copy per job, issued by lane 0: a weight slot, or a whole chunk of a head's k|v records (the cache
+    // is zero-filled before the generation, so the tokens of the chunk that are not cached yet read as zeros)
     if (wpos >= 0) {
-        const uint8_t* src = p.wsrc + static_cast<size_t>(wpos) * MG_SLOT + lane * 16;
-#pragma unroll
-        for (int i = 0; i < MG_SLOT_W / 512; ++i) cp_async_16_hint(dst + i * 512, src + i * 512, true, p.w_policy);
-        if (lane < (MG_SLOT - MG_SLOT_W) / 16) cp_async_16_hint(dst + MG_SLOT_W, src + MG_SLOT_W, true, p.w_policy);
+        if (lane == 0) {
+            mbar_expect_tx(bar, MG_SLOT);
+            bulk_g2s(smem_u32(stage), p.wsrc + static_cast<size_t>(wpos) * MG_SLOT, MG_SLOT, bar, p.w_policy);
+        }
     } else {
+        constexpr int CHUNK_BYTES = CT * 4 * D;
         const int q = p.warp + MG_WARPS * c.pi;
         const int b = p.s0 + (q >> p.hpc_shift), h = p.crank * p.HPC + (q & (p.HPC - 1));
         const size_t off = ((static_cast<size_t>(b) * p.H + h) * p.t_max + static_cast<size_t>(c.c) * CT) * (2 * D);
-        const int pieces = min(CT, c.step - c.c * CT) * (4 * D / 16);             // 16-byte pieces that exist
-        const uint8_t* src = reinterpret_cast<const uint8_t*>(p.cache + static_cast<size_t>(c.l) * p.layer_stride + off);
-        constexpr int PR = D / 4;                   // 16-byte pieces per k|v record
-        const uint32_t st0 = smem_u32(stage);
-#pragma unroll
-        for (int i = 0; i < CT * 4 * D / 512; ++i) {
-            const int idx = i * 32 + lane;
-            cp_async_16_hint(st0 + kv_piece_off<D>(idx / PR, idx % PR), src + (idx < pieces ? idx * 16 : 0), idx < pieces,
-                             p.kv_policy);
+        if (lane == 0) {
+            mbar_expect_tx(bar, CHUNK_BYTES);
+            bulk_g2s(smem_u32(stage), p.cache + static_cast<size_t>(c.l) * p.layer_stride + off, CHUNK_BYTES, bar, p.kv_policy);
         }
         if (++c.c == (c.step + CT - 1) / CT) { c.c = 0; ++c.pi; }
     }
-    cp_async_arrive(bar);
 }
 
 // Waits for the warp's next job and returns its stage.  (The stage index and the mbarrier phase are tracked
@@ -296,8 +289,8 @@ __device__ __forceinline__ void run_phase(const Phase& ph, const uint8_t* X, int
                 odd ? make_float2(r1, acc[3]) : make_float2(acc[2], r1));
             acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
         }
-        nt = u % ph.ntiles;
-        const int ks = u / ph.ntiles;
+        nt = (ph.ksplit == 1) ? u : ph.nt0;          // (no division here: it would cost as much as the MMAs of a slot)
+        const int ks = (ph.ksplit == 1) ? 0 : ph.ks0;
         for (int j = 0; j < ph.sub; ++j) {
             const uint8_t* slot = ring_acquire(ring);
             if (j == 0) {
@@ -514,17 +507,23 @@ decode_mega_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ M
 
     // ---- one-time setup ----
     for (int i = tid * 16; i < sm.bars; i += MG_THREADS * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
-    if (tid < MG_WARPS * NST + sm.nst_extra) mbar_init(&bars[tid], 32);
+    if (tid < MG_WARPS * NST + sm.nst_extra) mbar_init(&bars[tid], 1);
     if (tid < MG_ROWS) toks[tid] = (tid < G) ? a.first[s0 + tid] : 0;
     mbar_fence_init();
     __syncthreads();
 
     // phases of a decoder block and of the head as this CTA sees them (16-column tiles, K split, slots per unit)
-    const Phase ph_attn{3 * HS / 16, sm.ks_attn, E / 128 / sm.ks_attn};
-    const Phase ph_proj{HS / 16, sm.ks_proj, E / 128 / sm.ks_proj};
-    const Phase ph_fc{FS / 16, sm.ks_fc, E / 128 / sm.ks_fc};
-    const Phase ph_proj2{HS / 16, sm.ks_proj2, a.F / 128 / sm.ks_proj2};
-    const Phase ph_logits{VS / 16, sm.ks_logits, E / 128 / sm.ks_logits};
+    auto make_phase = [&](int ntiles, int ksplit, int K) {
+        Phase ph;
+        ph.ntiles = ntiles; ph.ksplit = ksplit; ph.sub = K / 128 / ksplit;
+        ph.nt0 = warp % ntiles; ph.ks0 = warp / ntiles;
+        return ph;
+    };
+    const Phase ph_attn = make_phase(3 * HS / 16, sm.ks_attn, E);
+    const Phase ph_proj = make_phase(HS / 16, sm.ks_proj, E);
+    const Phase ph_fc = make_phase(FS / 16, sm.ks_fc, E);
+    const Phase ph_proj2 = make_phase(HS / 16, sm.ks_proj2, a.F);
+    const Phase ph_logits = make_phase(VS / 16, sm.ks_logits, E);
 
     // this warp's weight jobs in the order it consumes them (stream positions relative to the block / to the head)
     uint16_t* tab = reinterpret_cast<uint16_t*>(smem + sm.jobtab) + warp * MG_TAB;
@@ -712,10 +711,11 @@ decode_mega_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ M
                         // append the k|v record to the global cache
                         if (lane < 2 * CH) {
                             const int part = lane % CH;
-                            const size_t off = ((static_cast<size_t>(b) * H + h) * a.t_max + pos) * (2 * D) + lane * 8;
+                            // (the pieces of a record are stored swizzled, so that a chunk is a linear image of a stage)
+                            const size_t rec = ((static_cast<size_t>(b) * H + h) * a.t_max + pos) * (2 * D);
                             const uint4 val = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(lane < CH ? kw : vw) + part * 16);
-                            *reinterpret_cast<uint4*>(cache_l + off) = val;
-                            __threadfence_block();     // read back by cp.async of other lanes of this warp in a later job
+                            *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(cache_l + rec) + kv_piece_off<D>(pos % CT, lane) - (pos % CT) * REC) = val;
+                            asm volatile("fence.proxy.async.global;" ::: "memory");    // read back by TMA in a later job
                         }
                         __syncwarp();
                         for (int c = 0; c < nchunks; ++c) {

@@ -564,7 +564,8 @@ static int generate_on(Engine& e, bf16* cache, int t_max, uint8_t* ws, int64_t w
     CB200_CUDA_OK(cudaGetLastError());
     note_launch(1);
     int rc;
-    const bool mega = g_decode_impl == 0 && decode_mega_supported(e.E, e.H, e.D, e.V, e.L);
+    // (the cluster kernel copies whole 64-token chunks of the cache: t_max must be a multiple of the chunk)
+    const bool mega = g_decode_impl == 0 && t_max % 64 == 0 && decode_mega_supported(e.E, e.H, e.D, e.V, e.L);
     if (mega) {
         // the whole generation (all steps, all layers) is one persistent cluster kernel
         MegaArgs m{};
@@ -593,6 +594,8 @@ static int generate_on(Engine& e, bf16* cache, int t_max, uint8_t* ws, int64_t w
             w.attn_w = static_cast<uint32_t>(e.shT_attn[l]); w.proj_w = static_cast<uint32_t>(e.shT_proj[l]);
             w.fc_w = static_cast<uint32_t>(e.shT_fc[l]); w.proj2_w = static_cast<uint32_t>(e.shT_proj2[l]);
         }
+        // chunks are copied whole: positions that are not cached yet must read as zeros (V rows enter an MMA)
+        CB200_CUDA_OK(cudaMemsetAsync(cache, 0, sizeof(bf16) * static_cast<size_t>(m.layer_stride) * e.L, s));
         if ((rc = decode_mega(m, e.D, g_decode_max_clusters, g_decode_cluster_size, d.mega_stream, d.mega_stream_bytes, s))) return rc;
     } else {
     // step 0 runs eagerly (also configures kernel attributes outside of capture); the rest replays a graph
