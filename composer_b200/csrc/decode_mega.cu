@@ -369,8 +369,10 @@ __device__ __forceinline__ void layernorm_rows(const uint8_t* src, uint8_t* dst,
         }
         return;
     }
+    // sum and sum of squares in one pass and one butterfly (fp32; the inputs are bf16 values of a few units, the
+    // cancellation error is far below the bf16 rounding of the output): half the dependent shuffle rounds
     float v[2][8];
-    float sum = 0.f;
+    float sum = 0.f, sq = 0.f;
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
         const int ch = lane + 32 * i;
@@ -378,21 +380,21 @@ __device__ __forceinline__ void layernorm_rows(const uint8_t* src, uint8_t* dst,
             const uint4 raw = *reinterpret_cast<const uint4*>(s + ch * 16);
             const float2 a = unpack_bf16(raw.x), b = unpack_bf16(raw.y), c = unpack_bf16(raw.z), e = unpack_bf16(raw.w);
             v[i][0] = a.x; v[i][1] = a.y; v[i][2] = b.x; v[i][3] = b.y; v[i][4] = c.x; v[i][5] = c.y; v[i][6] = e.x; v[i][7] = e.y;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) sum += v[i][k];
+            sum += ((v[i][0] + v[i][1]) + (v[i][2] + v[i][3])) + ((v[i][4] + v[i][5]) + (v[i][6] + v[i][7]));
+            sq += ((v[i][0] * v[i][0] + v[i][1] * v[i][1]) + (v[i][2] * v[i][2] + v[i][3] * v[i][3])) +
+                  ((v[i][4] * v[i][4] + v[i][5] * v[i][5]) + (v[i][6] * v[i][6] + v[i][7] * v[i][7]));
         } else {
 #pragma unroll
             for (int k = 0; k < 8; ++k) v[i][k] = 0.f;
         }
     }
-    const float mean = warp_sum(sum) / E;
-    float sq = 0.f;
 #pragma unroll
-    for (int i = 0; i < 2; ++i)
-        if (lane + 32 * i < nchunk)
-#pragma unroll
-            for (int k = 0; k < 8; ++k) { const float t = v[i][k] - mean; sq += t * t; }
-    const float rstd = rsqrtf(warp_sum(sq) / E + eps);
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    }
+    const float mean = sum / E;
+    const float rstd = rsqrtf(fmaxf(sq / E - mean * mean, 0.f) + eps);
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
         const int ch = lane + 32 * i;
@@ -684,16 +686,17 @@ decode_mega_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ M
                         const uint32_t* qw = reinterpret_cast<const uint32_t*>(qkvs + (sl * 3 * HS + hh * D) * 2);
                         const uint32_t* kw = qw + HS / 2;
                         const uint32_t* vw = qw + HS;
-                        // Scores as K q: the 16 tokens of a tile are the MMA rows and the query is column 0 of the B
-                        // operand (only the lanes of quad 0 hold it), so a lane with tig == 0 gets the scores of tokens
-                        // g and g + 8 and nothing is computed 8 times over.  New token = the softmax seed.
+                        // Scores as K q: the 16 tokens of a tile are the MMA rows and every column of the B operand is
+                        // the query, so lane (g, tig) gets the scores of tokens g and g + 8 (the same in its 4 tig
+                        // lanes: the softmax below runs on 16 distinct values per tile, not on 8 copies of the row).
+                        // New token = the softmax seed.
                         uint32_t qb[D / 16][2];
                         float snew = 0.f;
     #pragma unroll
                         for (int ks = 0; ks < D / 16; ++ks) {
                             const uint32_t q0w = qw[ks * 8 + tig], q1w = qw[ks * 8 + 4 + tig];
-                            qb[ks][0] = (g == 0) ? q0w : 0u;
-                            qb[ks][1] = (g == 0) ? q1w : 0u;
+                            qb[ks][0] = q0w;
+                            qb[ks][1] = q1w;
                             const float2 q0 = unpack_bf16(q0w), q1 = unpack_bf16(q1w);
                             const float2 k0 = unpack_bf16(kw[ks * 8 + tig]), k1 = unpack_bf16(kw[ks * 8 + 4 + tig]);
                             snew += q0.x * k0.x + q0.y * k0.y + q1.x * k1.x + q1.y * k1.y;
@@ -701,7 +704,7 @@ decode_mega_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ M
                         snew += __shfl_xor_sync(0xffffffffu, snew, 1);
                         snew += __shfl_xor_sync(0xffffffffu, snew, 2);
                         float m = snew * a.scale_log2;                  // running maximum (log2 units), warp-uniform
-                        float lsum = (lane == 0) ? 1.f : 0.f;           // this lane's share of the denominator
+                        float lsum = (lane < 4) ? 1.f : 0.f;            // this lane's share of 4 x the denominator (4 tig copies)
                         float o[NT_O][4];                               // row 0 of P.V; every quad carries a copy
     #pragma unroll
                         for (int dt = 0; dt < NT_O; ++dt) {
@@ -734,18 +737,19 @@ decode_mega_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ M
                                     mma_16816(s[jt], ka[0], ka[1], ka[2], ka[3], qb[ks][0], qb[ks][1]);
                                 }
                             }
+                            if (ntok < CT) {       // last, partial chunk of the pair: tokens that are not cached yet
+    #pragma unroll
+                                for (int jt = 0; jt < CT / 16; ++jt) {
+                                    if (jt * 16 + g >= ntok) s[jt][0] = -INFINITY;
+                                    if (jt * 16 + 8 + g >= ntok) s[jt][2] = -INFINITY;
+                                }
+                            }
                             float mx = -INFINITY;
     #pragma unroll
-                            for (int jt = 0; jt < CT / 16; ++jt) {
-                                // the other lanes hold columns 2, 4, 6 of the product (zeros): keep them out of the maximum
-                                if (tig != 0 || jt * 16 + g >= ntok) s[jt][0] = -INFINITY;
-                                if (tig != 0 || jt * 16 + 8 + g >= ntok) s[jt][2] = -INFINITY;
-                                mx = fmaxf(mx, fmaxf(s[jt][0], s[jt][2]));
-                            }
+                            for (int jt = 0; jt < CT / 16; ++jt) mx = fmaxf(mx, fmaxf(s[jt][0], s[jt][2]));
                             mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
                             mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
                             mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
-                            mx = __shfl_sync(0xffffffffu, mx, 0);        // lanes with tig != 0 only saw -inf
                             const float mn = fmaxf(m, mx * a.scale_log2);
                             const float corr = fast_exp2(m - mn);
                             m = mn;
@@ -779,7 +783,7 @@ decode_mega_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ M
                         lsum += __shfl_xor_sync(0xffffffffu, lsum, 16);
                         lsum += __shfl_xor_sync(0xffffffffu, lsum, 1);
                         lsum += __shfl_xor_sync(0xffffffffu, lsum, 2);
-                        const float inv = 1.0f / lsum;
+                        const float inv = 4.0f / lsum;                  // lsum counted every token in its 4 tig lanes
                         // every quad holds the same output row: quad g sends it to CTA g of the cluster
                         if (g < CL) {
                             const uint32_t dst = map_to_cta(smem_u32(Y + sl * pe + (h * D + 2 * tig) * 2), g);
