@@ -235,8 +235,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
             mbar_wait(bar_s_full, it & 1);
             tc_fence_after();
             const bool diagonal = (it == 0);
-            uint8_t* bp = sP + (it % NBUF_P) * PBYTES;
-            uint8_t* bs = sdS + (it % NBUF_P) * PBYTES;
+            const uint32_t bp_a = smem_u32(sP) + (it % NBUF_P) * PBYTES;
+            const uint32_t bs_a = smem_u32(sdS) + (it % NBUF_P) * PBYTES;
             uint32_t xs[4] = {0, 0, 0, 0};
             // 16 columns at a time keep the live register set small
 #pragma unroll
@@ -308,8 +308,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
 #pragma unroll
                 for (int c2 = 0; c2 < 2; ++c2) {
                     const uint32_t off = half_off + (((((col0 & 63) >> 3) + c2) ^ (r & 7)) << 4);
-                    *reinterpret_cast<uint4*>(bp + off) = make_uint4(pk[4 * c2], pk[4 * c2 + 1], pk[4 * c2 + 2], pk[4 * c2 + 3]);
-                    *reinterpret_cast<uint4*>(bs + off) = make_uint4(dk_[4 * c2], dk_[4 * c2 + 1], dk_[4 * c2 + 2], dk_[4 * c2 + 3]);
+                    // explicit shared-space stores with 32-bit addresses (the aligned base pointer went through an
+                    // integer cast, so a plain store would be a generic ST with 64-bit address arithmetic)
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(bp_a + off), "r"(pk[4 * c2]), "r"(pk[4 * c2 + 1]),
+                                 "r"(pk[4 * c2 + 2]), "r"(pk[4 * c2 + 3]) : "memory");
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(bs_a + off), "r"(dk_[4 * c2]), "r"(dk_[4 * c2 + 1]),
+                                 "r"(dk_[4 * c2 + 2]), "r"(dk_[4 * c2 + 3]) : "memory");
                 }
             }
             fence_proxy_async_smem();
