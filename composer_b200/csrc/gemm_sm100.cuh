@@ -68,6 +68,17 @@ struct GemmSmem {
     static constexpr int STAGING_BYTES = GEMM_BM * 128;                 // one 64-column bf16 slab
 };
 
+// Shared-space accesses with 32-bit addresses: the staging pointers come from an integer-aligned base, so a plain
+// dereference compiles to generic LD / ST with 64-bit address arithmetic.
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // Byte offset of 16-byte chunk `chunk` (0..7) of row `row` inside a
@@ -313,7 +324,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
                             for (int j = 0; j < 32; j += 8) {
                                 // rows / columns outside the tensor were zero-filled by the TMA load
-                                const uint4 a4 = *reinterpret_cast<const uint4*>(buf0 + sw128_offset(row_in_tile, half * 4 + (j >> 3)));
+                                const uint4 a4 = lds128(smem_u32(buf0) + sw128_offset(row_in_tile, half * 4 + (j >> 3)));
                                 (void)in_rows;
                                 const uint32_t aw[4] = {a4.x, a4.y, a4.z, a4.w};
                                 Philox4 rb{0, 0, 0, 0};
@@ -345,12 +356,12 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                             uint4 o;
                             o.x = pack_bf16(f[j], f[j + 1]); o.y = pack_bf16(f[j + 2], f[j + 3]);
                             o.z = pack_bf16(f[j + 4], f[j + 5]); o.w = pack_bf16(f[j + 6], f[j + 7]);
-                            *reinterpret_cast<uint4*>(buf0 + sw128_offset(row_in_tile, chunk)) = o;
+                            sts128(smem_u32(buf0) + sw128_offset(row_in_tile, chunk), o);
                             if (EPI == EPI_BIAS_GELU) {
                                 uint4 o1;
                                 o1.x = pack_bf16(g[j], g[j + 1]); o1.y = pack_bf16(g[j + 2], g[j + 3]);
                                 o1.z = pack_bf16(g[j + 4], g[j + 5]); o1.w = pack_bf16(g[j + 6], g[j + 7]);
-                                *reinterpret_cast<uint4*>(buf1 + sw128_offset(row_in_tile, chunk)) = o1;
+                                sts128(smem_u32(buf1) + sw128_offset(row_in_tile, chunk), o1);
                             }
                         }
                     }
