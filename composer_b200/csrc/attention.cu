@@ -122,7 +122,7 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
 #pragma unroll
         for (int t = 0; t < NT_O; ++t) { o[mt][t][0] = o[mt][t][1] = o[mt][t][2] = o[mt][t][3] = 0.f; }
     }
-    uint32_t seed_base = 0;
+    AttnStream seed_base{0u, 1u};
     if (DROP) seed_base = attn_stream_base(drop, b * H + h, lane);
 
     // keys 0 .. min(T, q0 + BR) - 1 are visible to this CTA
@@ -390,7 +390,7 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
         for (int t = 0; t < NT_D; ++t)
 #pragma unroll
             for (int e = 0; e < 4; ++e) { dk[m][t][e] = 0.f; dv[m][t][e] = 0.f; }
-    uint32_t seed_base = 0;
+    AttnStream seed_base{0u, 1u};
     if (DROP) seed_base = attn_stream_base(drop, b * H + h, lane);
 
     const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8, a_chunk = lane >> 4;               // A fragments (Q, dO)

@@ -188,11 +188,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         const float* gdelta = delta + (static_cast<size_t>(b) * H + h) * T;
         float* dqb = dq_acc + static_cast<size_t>(b) * T * E + h * D;
         // dropout: this thread's row meets 4 lanes' streams (tig = 0..3) of the m16n8k16 ownership map
-        uint32_t base4[4] = {0, 0, 0, 0};
+        uint32_t stream_base = 0, mult4[4] = {1u, 1u, 1u, 1u};
         const int g = r & 7, hi = (r >> 3) & 1;
         if (DROP) {
 #pragma unroll
-            for (int tig = 0; tig < 4; ++tig) base4[tig] = attn_stream_base(drop, b * H + h, 4 * g + tig);
+            for (int tig = 0; tig < 4; ++tig) mult4[tig] = attn_lane_mult(drop, 4 * g + tig);
+            stream_base = attn_stream_base(drop, b * H + h, 0).base;
         }
         const float dq_scale = scale * ks_scale;
 
@@ -266,11 +267,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
                         // (re)seed at the thread's first chunk and at every new 64-key dropout block.  The stream is
                         // parked two positions before element idx = 4*t + 2*hi (t = first 8-key group of the chunk),
                         // so that every pair below advances by A^3 then A.
+                        // One hash per (16-row group, 64-key block), then this thread's four lane multipliers.
                         const uint32_t park = ((col0 & 32) ? mcg_mul_pow(16) : 1u) * (hi ? 1u : mcg_inv_pow(2));
+                        const uint32_t hash = attn_block_hash(stream_base, static_cast<uint32_t>(row_g) >> 4,
+                                                              static_cast<uint32_t>((k0 + col0) >> 6)) * park;
 #pragma unroll
-                        for (int tig = 0; tig < 4; ++tig)
-                            xs[tig] = attn_stream_seed(base4[tig], static_cast<uint32_t>(row_g) >> 4,
-                                                       static_cast<uint32_t>((k0 + col0) >> 6)) * park;
+                        for (int tig = 0; tig < 4; ++tig) xs[tig] = hash * mult4[tig];
                     }
                     // two copies of the element loop: only chunks that straddle the diagonal pay for the mask
                     auto elements = [&](auto masked) {

@@ -194,14 +194,35 @@ __host__ __device__ __forceinline__ uint32_t fmix32(uint32_t h) {
     return h;
 }
 
-// Per-(batch*head, lane) part of the seed; computed once per thread.
-__host__ __device__ __forceinline__ uint32_t attn_stream_base(const AttnDropKey& key, uint32_t bh, uint32_t lane) {
-    return fmix32(fmix32(bh ^ key.k0) + lane * 0x9E3779B9u + key.k1);
+// The stream of lane `lane` for block (i16, jb) of (batch * head) starts at
+//     seed = (fmix32(base ^ block coordinates) | 1) * mult(lane)          (odd times odd: odd, a valid MCG state)
+// with base hashed from (batch * head) and mult(lane) an odd multiplier hashed from the lane, both computed once
+// per thread.  One hash per block serves every lane's stream: the tcgen05 backward kernel, whose threads own a
+// query row and therefore meet four lanes' streams per block, pays one hash and four multiplies instead of four
+// hashes (which were 2.5 of its ~15 instructions per score element).
+struct AttnStream {
+    uint32_t base;   // per (batch * head)
+    uint32_t mult;   // per lane, odd
+};
+
+__host__ __device__ __forceinline__ uint32_t attn_lane_mult(const AttnDropKey& key, uint32_t lane) {
+    return fmix32(lane * 0x9E3779B9u + key.k1) | 1u;
 }
 
-// (i16 < 2^13, jb < 2^11: injective for T <= 2^17); fmix32 is a bijection, so distinct blocks get distinct seeds.
-__host__ __device__ __forceinline__ uint32_t attn_stream_seed(uint32_t base, uint32_t i16, uint32_t jb) {
+__host__ __device__ __forceinline__ AttnStream attn_stream_base(const AttnDropKey& key, uint32_t bh, uint32_t lane) {
+    AttnStream s;
+    s.base = fmix32(bh ^ key.k0) + key.k1;
+    s.mult = attn_lane_mult(key, lane);
+    return s;
+}
+
+// (i16 < 2^13, jb < 2^11: injective for T <= 2^17); fmix32 is a bijection, so distinct blocks get distinct hashes.
+__host__ __device__ __forceinline__ uint32_t attn_block_hash(uint32_t base, uint32_t i16, uint32_t jb) {
     return fmix32(base ^ ((i16 << 11) | jb)) | 1u;
+}
+
+__host__ __device__ __forceinline__ uint32_t attn_stream_seed(const AttnStream& s, uint32_t i16, uint32_t jb) {
+    return attn_block_hash(s.base, i16, jb) * s.mult;
 }
 
 __host__ __device__ __forceinline__ AttnDropKey make_attn_drop_key(const DropoutParams& p, uint32_t layer) {
