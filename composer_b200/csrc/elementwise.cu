@@ -308,26 +308,40 @@ bias_grad_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (my_lane < lanes) {
         const int grp = group0 + my_group;
-        for (int row = r0 + my_lane; row < r1; row += lanes) {
-            const size_t off = static_cast<size_t>(row) * N + grp * 8;
-            const uint4 raw = *reinterpret_cast<const uint4*>(dy + off);
-            const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
-            float f[8];
+        // 4 rows per pass: the loads of a pass are issued together (one load in flight per thread left the kernel
+        // latency-bound at ~3.5 TB/s)
+        constexpr int U = 4;
+        for (int row0 = r0 + my_lane; row0 < r1; row0 += U * lanes) {
+            uint4 raw[U];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) { const float2 p = unpack_bf16(w[e]); f[2 * e] = p.x; f[2 * e + 1] = p.y; }
-            if (drop.threshold16 != 0) {
-                const Philox4 r = drop_bits_rowmajor(drop, site, layer, row, grp);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] = (drop_u16(r, e) < drop.threshold16) ? 0.f : f[e] * drop.keep_scale;
-                if (g_out != nullptr) {
-                    uint4 o;
-                    o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]);
-                    o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
-                    *reinterpret_cast<uint4*>(g_out + off) = o;
-                }
+            for (int u = 0; u < U; ++u) {
+                const int row = row0 + u * lanes;
+                raw[u] = make_uint4(0, 0, 0, 0);
+                if (row < r1) raw[u] = *reinterpret_cast<const uint4*>(dy + static_cast<size_t>(row) * N + grp * 8);
             }
 #pragma unroll
-            for (int e = 0; e < 8; ++e) acc[e] += f[e];
+            for (int u = 0; u < U; ++u) {
+                const int row = row0 + u * lanes;
+                if (row >= r1) break;
+                const size_t off = static_cast<size_t>(row) * N + grp * 8;
+                const uint32_t w[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
+                float f[8];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { const float2 p = unpack_bf16(w[e]); f[2 * e] = p.x; f[2 * e + 1] = p.y; }
+                if (drop.threshold16 != 0) {
+                    const Philox4 r = drop_bits_rowmajor(drop, site, layer, row, grp);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) f[e] = (drop_u16(r, e) < drop.threshold16) ? 0.f : f[e] * drop.keep_scale;
+                    if (g_out != nullptr) {
+                        uint4 o;
+                        o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]);
+                        o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+                        *reinterpret_cast<uint4*>(g_out + off) = o;
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[e] += f[e];
+            }
         }
 #pragma unroll
         for (int e = 0; e < 8; ++e) atomicAdd(&red[my_group * 8 + e], acc[e]);
