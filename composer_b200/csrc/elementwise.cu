@@ -184,11 +184,16 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy_a, const __nv_bfloat16
                      const __nv_bfloat16* __restrict__ x, const float* __restrict__ stats,
                      const float* __restrict__ gamma, const __nv_bfloat16* __restrict__ dres,
                      __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                     int rows, int E) {
+                     int rows, int E, LnBwdTail tail) {
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int warps_total = gridDim.x * (blockDim.x >> 5);
     float gam[VPL][8], pg[VPL][8], pb[VPL][8];
+    float pt[VPL][8];      // column sums of the tail's g = dropout_bwd(dx)
+#pragma unroll
+    for (int v = 0; v < VPL; ++v)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) pt[v][e] = 0.f;
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
         const int c = (v * 32 + lane) * 8;
@@ -242,11 +247,29 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy_a, const __nv_bfloat16
             out.x = pack_bf16(o[0], o[1]); out.y = pack_bf16(o[2], o[3]);
             out.z = pack_bf16(o[4], o[5]); out.w = pack_bf16(o[6], o[7]);
             *reinterpret_cast<uint4*>(dx + off) = out;
+            if (tail.dbias != nullptr) {
+                // what bias_grad would do with dx as its input: the bf16-rounded values, the same keep mask
+                const uint32_t wo[4] = {out.x, out.y, out.z, out.w};
+                float f[8];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { const float2 p = unpack_bf16(wo[e]); f[2 * e] = p.x; f[2 * e + 1] = p.y; }
+                if (tail.drop.threshold16 != 0) {
+                    const Philox4 r = drop_bits_rowmajor(tail.drop, tail.site, tail.layer, row, v * 32 + lane);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) f[e] = (drop_u16(r, e) < tail.drop.threshold16) ? 0.f : f[e] * tail.drop.keep_scale;
+                    uint4 g;
+                    g.x = pack_bf16(f[0], f[1]); g.y = pack_bf16(f[2], f[3]);
+                    g.z = pack_bf16(f[4], f[5]); g.w = pack_bf16(f[6], f[7]);
+                    *reinterpret_cast<uint4*>(tail.g_out + off) = g;
+                }
+#pragma unroll
+                for (int e = 0; e < 8; ++e) pt[v][e] += f[e];
+            }
         }
     }
-    // cross-warp reduction of the dgamma / dbeta partials through shared memory
-    extern __shared__ float red[];   // [2][E]
-    for (int i = threadIdx.x; i < 2 * E; i += blockDim.x) red[i] = 0.f;
+    // cross-warp reduction of the dgamma / dbeta (/ tail bias) partials through shared memory
+    extern __shared__ float red[];   // [3][E]
+    for (int i = threadIdx.x; i < 3 * E; i += blockDim.x) red[i] = 0.f;
     __syncthreads();
 #pragma unroll
     for (int v = 0; v < VPL; ++v)
@@ -255,28 +278,39 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy_a, const __nv_bfloat16
             const int c = (v * 32 + lane) * 8 + e;
             atomicAdd(&red[c], pg[v][e]);
             atomicAdd(&red[E + c], pb[v][e]);
+            if (tail.dbias != nullptr) atomicAdd(&red[2 * E + c], pt[v][e]);
         }
     __syncthreads();
     for (int i = threadIdx.x; i < E; i += blockDim.x) {
         atomicAdd(&dgamma[i], red[i]);
         atomicAdd(&dbeta[i], red[E + i]);
+        if (tail.dbias != nullptr) atomicAdd(&tail.dbias[i], red[2 * E + i]);
     }
 }
 
 int layernorm_bwd(const __nv_bfloat16* dy_a, const __nv_bfloat16* dy_b, const __nv_bfloat16* x, const float* stats,
                   const float* gamma, const __nv_bfloat16* dres, __nv_bfloat16* dx, float* dgamma, float* dbeta,
                   int rows, int E, cudaStream_t s) {
+    LnBwdTail none{};
+    return layernorm_bwd_tail(dy_a, dy_b, x, stats, gamma, dres, dx, dgamma, dbeta, rows, E, none, s);
+}
+
+int layernorm_bwd_tail(const __nv_bfloat16* dy_a, const __nv_bfloat16* dy_b, const __nv_bfloat16* x, const float* stats,
+                       const float* gamma, const __nv_bfloat16* dres, __nv_bfloat16* dx, float* dgamma, float* dbeta,
+                       int rows, int E, const LnBwdTail& tail, cudaStream_t s) {
+    CB200_REQUIRE(tail.dbias == nullptr || tail.drop.threshold16 == 0 || tail.g_out != nullptr,
+                  "the fused dropout-backward tail needs an output buffer");
     CB200_REQUIRE(E % 256 == 0 && E <= 1024, "LayerNorm backward needs E %% 256 == 0 and E <= 1024, got %d", E);
     if (rows == 0) return 0;
     int grid = (rows + 7) / 8;
     const int cap = 2 * device_sm_count_ew();
     if (grid > cap) grid = cap;
-    const size_t smem = 2 * E * sizeof(float);
+    const size_t smem = 3 * E * sizeof(float);
     switch (E / 256) {
-        case 1: layernorm_bwd_kernel<1><<<grid, 256, smem, s>>>(dy_a, dy_b, x, stats, gamma, dres, dx, dgamma, dbeta, rows, E); break;
-        case 2: layernorm_bwd_kernel<2><<<grid, 256, smem, s>>>(dy_a, dy_b, x, stats, gamma, dres, dx, dgamma, dbeta, rows, E); break;
-        case 3: layernorm_bwd_kernel<3><<<grid, 256, smem, s>>>(dy_a, dy_b, x, stats, gamma, dres, dx, dgamma, dbeta, rows, E); break;
-        case 4: layernorm_bwd_kernel<4><<<grid, 256, smem, s>>>(dy_a, dy_b, x, stats, gamma, dres, dx, dgamma, dbeta, rows, E); break;
+        case 1: layernorm_bwd_kernel<1><<<grid, 256, smem, s>>>(dy_a, dy_b, x, stats, gamma, dres, dx, dgamma, dbeta, rows, E, tail); break;
+        case 2: layernorm_bwd_kernel<2><<<grid, 256, smem, s>>>(dy_a, dy_b, x, stats, gamma, dres, dx, dgamma, dbeta, rows, E, tail); break;
+        case 3: layernorm_bwd_kernel<3><<<grid, 256, smem, s>>>(dy_a, dy_b, x, stats, gamma, dres, dx, dgamma, dbeta, rows, E, tail); break;
+        case 4: layernorm_bwd_kernel<4><<<grid, 256, smem, s>>>(dy_a, dy_b, x, stats, gamma, dres, dx, dgamma, dbeta, rows, E, tail); break;
         default: set_error("unsupported embedding size %d for LayerNorm backward", E); return -1;
     }
     CB200_CUDA_OK(cudaGetLastError());

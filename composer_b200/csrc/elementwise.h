@@ -17,6 +17,17 @@ int embed_bwd(const int32_t* ids, const __nv_bfloat16* dh, float* dwte, float* d
               int vocab, const DropoutParams& drop, cudaStream_t s);
 int layernorm_fwd(const __nv_bfloat16* x, const float* gamma, const float* beta, __nv_bfloat16* y, float* stats,
                   int rows, int E, float eps, cudaStream_t s);
+// Optional tail of layernorm_bwd: what bias_grad would do next with dx as its input, i.e. g = dropout_bwd(dx)
+// (written to g_out when dropout is on) and dbias += column sums of g, without a second pass over dx.
+struct LnBwdTail {
+    __nv_bfloat16* g_out;     // [rows, E]; may be null when drop.threshold16 == 0
+    float* dbias;             // [E]; null = no tail
+    DropoutParams drop;
+    uint32_t site, layer;
+};
+int layernorm_bwd_tail(const __nv_bfloat16* dy_a, const __nv_bfloat16* dy_b, const __nv_bfloat16* x, const float* stats,
+                       const float* gamma, const __nv_bfloat16* dres, __nv_bfloat16* dx, float* dgamma, float* dbeta,
+                       int rows, int E, const LnBwdTail& tail, cudaStream_t s);
 int layernorm_bwd(const __nv_bfloat16* dy_a, const __nv_bfloat16* dy_b, const __nv_bfloat16* x, const float* stats,
                   const float* gamma, const __nv_bfloat16* dres, __nv_bfloat16* dx, float* dgamma, float* dbeta,
                   int rows, int E, cudaStream_t s);

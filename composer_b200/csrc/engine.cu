@@ -320,8 +320,10 @@ static int backward_head(Engine& e, cudaStream_t s) {
         if ((rc = gemm_launch(d, s))) return rc;
     }
     const bf16* x_last = e.lb[e.L - 1].x3;
-    return layernorm_bwd(e.bufQ, nullptr, x_last, e.lnf_stats, e.params + e.lay.lnf_g, nullptr, e.bufP,
-                         G + e.lay.lnf_g, G + e.lay.lnf_b, M, E, s);
+    // d x3 of the last block, and in the same pass what its MLP needs first: g = dropout_bwd(d x3), d b_proj2
+    const LnBwdTail tail{e.bufG, G + e.lay.layers[e.L - 1].proj2_b, e.drop_res, SITE_MLP, static_cast<uint32_t>(e.L)};
+    return layernorm_bwd_tail(e.bufQ, nullptr, x_last, e.lnf_stats, e.params + e.lay.lnf_g, nullptr, e.bufP,
+                              G + e.lay.lnf_g, G + e.lay.lnf_b, M, E, tail, s);
 }
 
 __global__ void add3_kernel(const bf16* a, const bf16* b, const bf16* c, bf16* out, size_t n8) {
@@ -371,8 +373,9 @@ static int backward_layer(Engine& e, int l, cudaStream_t s) {
     int rc;
 
     // ---- MLP ----
-    // g = dropout_bwd(d x3); d b_proj2 += colsum(g)
-    if ((rc = bias_grad(e.bufP, e.bufG, G + o.proj2_b, M, E, e.drop_res, SITE_MLP, layer, s))) return rc;
+    // g = dropout_bwd(d x3); d b_proj2 += colsum(g): done by the kernel that produced d x3 (ln_f backward for the last
+    // block, ln_1 backward of the block above otherwise) unless the model runs without LayerNorm
+    if (!ln && (rc = bias_grad(e.bufP, e.bufG, G + o.proj2_b, M, E, e.drop_res, SITE_MLP, layer, s))) return rc;
     const bf16* g_mlp = dropping ? e.bufG : e.bufP;
     {   // du = (g W2^T) * gelu'(u)
         GemmDesc d = gemm_desc(GEMM_MUL_DGELU, M, F, E, g_mlp, E, S + o.proj2_w, E);
@@ -397,12 +400,14 @@ static int backward_layer(Engine& e, int l, cudaStream_t s) {
     }
     // d x2 = LN2_bwd(d mln) + d x3
     if (ln) {
-        if ((rc = layernorm_bwd(e.bufQ, nullptr, x.x2, x.ln2_stats, P + o.ln2_g, e.bufP, e.bufR, G + o.ln2_g, G + o.ln2_b, M, E, s))) return rc;
+        // ... and g = dropout_bwd(d x2), d b_proj for the attention projection in the same pass
+        const LnBwdTail tail{e.bufG, G + o.proj_b, e.drop_res, SITE_ATTN_RESID, layer};
+        if ((rc = layernorm_bwd_tail(e.bufQ, nullptr, x.x2, x.ln2_stats, P + o.ln2_g, e.bufP, e.bufR, G + o.ln2_g, G + o.ln2_b, M, E, tail, s))) return rc;
     } else {
         if ((rc = add3(e.bufQ, e.bufP, nullptr, e.bufR, static_cast<size_t>(M) * E, s))) return rc;
+        if ((rc = bias_grad(e.bufR, e.bufG, G + o.proj_b, M, E, e.drop_res, SITE_ATTN_RESID, layer, s))) return rc;
     }
     // ---- attention ----
-    if ((rc = bias_grad(e.bufR, e.bufG, G + o.proj_b, M, E, e.drop_res, SITE_ATTN_RESID, layer, s))) return rc;
     const bf16* g_att = dropping ? e.bufG : e.bufR;
     {   // d att = g Wproj^T
         GemmDesc d = gemm_desc(GEMM_BIAS, M, E, E, g_att, E, S + o.proj_w, E);
@@ -430,7 +435,10 @@ static int backward_layer(Engine& e, int l, cudaStream_t s) {
     // d x_in = LN1_bwd(d x2 + d x1_attn): ln_1 overwrote the residual stream (transformer.py:583-587),
     // so the block input is reached only through ln_1.
     if (ln) {
-        if ((rc = layernorm_bwd(e.bufR, e.bufQ, x_in, x.ln1_stats, P + o.ln1_g, nullptr, e.bufP, G + o.ln1_g, G + o.ln1_b, M, E, s))) return rc;
+        // (for l > 0 also the MLP tail of the block below: g = dropout_bwd(d x3), d b_proj2)
+        LnBwdTail tail{};
+        if (l > 0) tail = LnBwdTail{e.bufG, G + e.lay.layers[l - 1].proj2_b, e.drop_res, SITE_MLP, static_cast<uint32_t>(l)};
+        if ((rc = layernorm_bwd_tail(e.bufR, e.bufQ, x_in, x.ln1_stats, P + o.ln1_g, nullptr, e.bufP, G + o.ln1_g, G + o.ln1_b, M, E, tail, s))) return rc;
     } else {
         if ((rc = add3(e.bufR, e.bufQ, nullptr, e.bufP, static_cast<size_t>(M) * E, s))) return rc;
     }
