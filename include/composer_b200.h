@@ -109,15 +109,18 @@ int cb200_adam_step(void* engine, float learning_rate, float beta_1, float beta_
 /* ---- generation -------------------------------------------------------------
  * KV-cache decoding through the model's `past=` semantics (transformer.py:423-437,
  * 735-770) with the CLI's sampling rule (cli.py:663-676).
- * cache: device bf16 [L, 2, B, H, t_max, d_h]; see cb200_kv_cache_elems.
+ * cache: device bf16 scratch of cb200_kv_cache_elems(engine, B, t_max) elements.  Its layout is private to the call
+ * (a generation always starts from an empty cache): [L, B, H, t_max, 2, d_h] with swizzled 16-byte pieces for the
+ * persistent cluster kernel, which is used when t_max is a multiple of 64 and the shape allows it (see
+ * cb200_set_decode_impl), [L, 2, B, H, t_max, d_h] for the per-step kernels.
  * prompt: device int32 [B, prompt_len] (every sequence has the same prompt length).
  * out_ids: device int32 [B, n_new].  temperature <= 0 selects argmax.
  * seq_index_base: global index of sequence 0 (keys the Philox stream so that
  * results do not depend on the sharding).  uniforms_out (device fp32 [B, prompt_len-1+n_new],
  * may be NULL) receives the uniform draw used at every step (for parity tests).
  * last_logits (device fp32 [B, vocab], may be NULL) receives the logits of the
- * final step.  The call replays a CUDA graph of one step on `stream` and
- * synchronises the stream before returning. */
+ * final step.  The call runs the whole generation (one persistent kernel, or a CUDA graph of one step replayed)
+ * and synchronises the stream before returning. */
 int64_t cb200_kv_cache_elems(void* engine, int B, int t_max);
 int64_t cb200_decode_workspace_bytes(void* engine, int B);
 int cb200_generate(void* engine, void* cache, int t_max, void* workspace, int64_t workspace_bytes,
