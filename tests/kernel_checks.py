@@ -506,21 +506,22 @@ def check_engine_adam_step(B=2, T=64):
     return _finish(results)
 
 
-def check_generate(B=4, prompt_len=5, length=40, impl=0, max_clusters=0, embedding=256, heads=16, cluster_size=0):
+def check_generate(B=4, prompt_len=5, length=40, impl=0, max_clusters=0, embedding=256, heads=16, cluster_size=0,
+                   window=64):
     '''impl 0 = persistent cluster kernel (decode_mega.cu), 1 = per-step kernels replayed as a CUDA graph.'''
     _lib.call('cb200_set_decode_impl', impl, max_clusters, cluster_size)
     try:
-        return _check_generate(B, prompt_len, length, embedding, heads)
+        return _check_generate(B, prompt_len, length, embedding, heads, window)
     finally:
         _lib.call('cb200_set_decode_impl', 0, 0, 0)
 
 
-def check_generate_impls_agree(B=19, prompt_len=3, length=50, embedding=256, heads=16):
+def check_generate_impls_agree(B=19, prompt_len=3, length=50, embedding=256, heads=16, window=64):
     '''The two decode implementations share every rounding point: same tokens (greedy and sampled) and the
     same final logits up to accumulation order.'''
     import numpy as np
 
-    model, cfg, _ = _small_model(3, embedding, heads, window=64)
+    model, cfg, _ = _small_model(3, embedding, heads, window=window)
     rng = np.random.default_rng(21)
     prompt = rng.integers(0, cfg.vocab_size, size=(B, prompt_len))
     outs = {}
@@ -558,11 +559,11 @@ def check_generate_impls_agree(B=19, prompt_len=3, length=50, embedding=256, hea
     return _finish(results)
 
 
-def _check_generate(B, prompt_len, length, embedding, heads):
+def _check_generate(B, prompt_len, length, embedding, heads, window=64):
     import numpy as np
     from oracle import transformer_oracle as oracle
 
-    model, cfg, weights = _small_model(2, embedding, heads, window=64)
+    model, cfg, weights = _small_model(2, embedding, heads, window=window)
     rng = np.random.default_rng(9)
     prompt = rng.integers(0, cfg.vocab_size, size=(B, prompt_len))
     results = []
@@ -629,5 +630,10 @@ GROUPS['generate'] = [check_generate, lambda: check_generate(impl=1),
                       lambda: check_generate(B=3, prompt_len=2, length=36, embedding=256, heads=4, cluster_size=4),
                       lambda: check_generate(B=5, prompt_len=4, length=24, embedding=512, heads=8),
                       lambda: check_generate(B=3, prompt_len=4, length=24, embedding=512, heads=16, impl=1),
+                      # contexts beyond one 64-token chunk of the cluster kernel's KV ring (several chunks per pair,
+                      # a partial last chunk, ring stages re-used within a layer), 8- and 4-CTA clusters
+                      lambda: check_generate(B=3, prompt_len=70, length=90, window=192),
+                      lambda: check_generate(B=10, prompt_len=2, length=140, window=192, cluster_size=4),
+                      lambda: check_generate_impls_agree(B=6, prompt_len=2, length=250, window=256),
                       check_generate_impls_agree,
                       lambda: check_generate_impls_agree(B=33, embedding=512, heads=16)]
