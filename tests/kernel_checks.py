@@ -622,7 +622,10 @@ def _check_generate(B, prompt_len, length, embedding, heads, window=64):
 
 
 GROUPS['engine'] = [check_engine_forward_backward, check_engine_adam_step,
-                    lambda: check_engine_forward_backward(B=1, T=256, layers=3)]
+                    lambda: check_engine_forward_backward(B=1, T=256, layers=3),
+                    # the head sizes of the scaled configuration (d_h 64) and of an intermediate one (d_h 32)
+                    lambda: check_engine_forward_backward(B=2, T=130, layers=2, embedding=1024, heads=16),
+                    lambda: check_engine_forward_backward(B=1, T=200, layers=2, embedding=512, heads=16)]
 GROUPS['generate'] = [check_generate, lambda: check_generate(impl=1),
                       lambda: check_generate(B=21, prompt_len=2, length=30, max_clusters=1),
                       lambda: check_generate(B=9, prompt_len=3, length=40, cluster_size=4),
