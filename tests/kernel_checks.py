@@ -633,6 +633,8 @@ GROUPS['generate'] = [check_generate, lambda: check_generate(impl=1),
                       lambda: check_generate(B=3, prompt_len=2, length=36, embedding=256, heads=4, cluster_size=4),
                       lambda: check_generate(B=5, prompt_len=4, length=24, embedding=512, heads=8),
                       lambda: check_generate(B=3, prompt_len=4, length=24, embedding=512, heads=16, impl=1),
+                      # the scaled configuration's width and head size (d_model 1024, d_h 64: per-step kernels)
+                      lambda: check_generate(B=4, prompt_len=4, length=32, embedding=1024, heads=16),
                       # contexts beyond one 64-token chunk of the cluster kernel's KV ring (several chunks per pair,
                       # a partial last chunk, ring stages re-used within a layer), 8- and 4-CTA clusters
                       lambda: check_generate(B=3, prompt_len=70, length=90, window=192),
