@@ -44,6 +44,8 @@ struct MegaArgs {
     long long* prof;               // 24 cycle counters (phase profile of cluster 0: 15 phases, then ring waits per phase), or null
     long long layer_stride;        // elements per layer of the cache
     int B, E, H, F, V, L, t_max, steps, use_ln, greedy, seq_base;
+    int kv_split_log2;             // a pair's KV chunks go to up to 1 << this warps when the CTA has few pairs (set by decode_mega)
+    int kv_prefetch;               // KV chunks per warp and attention phase requested into L2 during the GEMM phases (set by decode_mega)
     int l2_hints;                  // 1: cache reads evict-first, weight stream evict-last (set by decode_mega)
     float eps, scale_log2, inv_temperature;
     uint32_t seed_lo, seed_hi;

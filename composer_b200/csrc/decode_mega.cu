@@ -162,11 +162,14 @@ struct JobPlan {           // what the cursor needs to enumerate this warp's job
                            // after it (c_proj, c_fc, mlp c_proj), then the logits slots; relative stream positions
     int n_pre, n_post, n_logit;
     int warp, steps, L, s0, nmine, hpc_shift, HPC, H, crank, t_max, per_layer;
+    int ss, split;         // a pair's chunks are dealt to 1 << ss adjacent warps; this warp takes chunks = split mod 2^ss
 };
 constexpr int MG_TAB = 32;                 // table entries per warp: [0, 8) pre, [8, 24) post, [24, 32) logits
 
 struct JobCursor {
-    int step, l, k, pi, c;                 // k: weight jobs of this block issued so far; (pi, c): next KV job
+    int step, l, k, pi;                    // k: weight jobs of this block issued so far; pi: next KV item
+    int kv_left;                           // chunks of the current KV item still to issue, the next one at kv_ptr
+    const uint8_t* kv_ptr;
 };
 
 struct JobRing {
@@ -186,39 +189,71 @@ __device__ __forceinline__ int units_of(int warp, int n) { return n > warp ? (n 
 template <int D>
 __device__ __forceinline__ void job_issue(const JobPlan& p, JobCursor& c, uint8_t* stage, uint64_t* bar, int lane) {
     constexpr int CT = MG_CT(D);
-    int wpos = -1;                                  // weight job: stream position
-    for (;;) {
-        if (c.step >= p.steps) return;
-        if (c.l < p.L) {
-            if (c.k < p.n_pre) { wpos = c.l * p.per_layer + p.tab[c.k]; ++c.k; break; }
-            const int nchunks = (c.step + CT - 1) / CT;
-            if (c.pi < p.nmine && nchunks > 0) break;          // KV job (pi, c)
-            const int kk = c.k - p.n_pre;
-            if (kk < p.n_post) { wpos = c.l * p.per_layer + p.tab[8 + kk]; ++c.k; break; }
-            ++c.l; c.k = 0; c.pi = 0; c.c = 0;
-        } else {
-            if (c.k < p.n_logit) { wpos = p.L * p.per_layer + p.tab[24 + c.k]; ++c.k; break; }
-            ++c.step; c.l = 0; c.k = 0; c.pi = 0; c.c = 0;
+    constexpr uint32_t CHUNK_BYTES = CT * 4 * D;
+    const uint8_t* src;
+    bool kv = true;
+    if (c.kv_left > 0) {                            // the common case: the next chunk of the current (sequence, head) item
+        src = c.kv_ptr;
+        --c.kv_left;
+    } else {
+        for (;;) {
+            if (c.step >= p.steps) return;
+            if (c.l < p.L) {
+                if (c.k < p.n_pre) { src = p.wsrc + static_cast<size_t>(c.l * p.per_layer + p.tab[c.k]) * MG_SLOT; ++c.k; kv = false; break; }
+                if (c.pi < p.nmine) {
+                    // chunks of an item of this warp in this step: split, split + S, ... (the same for all its items)
+                    const int nchunks = (c.step + CT - 1) / CT;
+                    const int nck = nchunks > p.split ? (nchunks - p.split + (1 << p.ss) - 1) >> p.ss : 0;
+                    if (nck > 0) {
+                        const int q = (p.warp + MG_WARPS * c.pi) >> p.ss;
+                        const int b = p.s0 + (q >> p.hpc_shift), h = p.crank * p.HPC + (q & (p.HPC - 1));
+                        const size_t off = ((static_cast<size_t>(b) * p.H + h) * p.t_max + static_cast<size_t>(p.split) * CT) * (2 * D);
+                        src = reinterpret_cast<const uint8_t*>(p.cache + static_cast<size_t>(c.l) * p.layer_stride + off);
+                        ++c.pi;
+                        c.kv_left = nck - 1;
+                        break;
+                    }
+                    c.pi = p.nmine;
+                }
+                const int kk = c.k - p.n_pre;
+                if (kk < p.n_post) { src = p.wsrc + static_cast<size_t>(c.l * p.per_layer + p.tab[8 + kk]) * MG_SLOT; ++c.k; kv = false; break; }
+                ++c.l; c.k = 0; c.pi = 0;
+            } else {
+                if (c.k < p.n_logit) { src = p.wsrc + static_cast<size_t>(p.L * p.per_layer + p.tab[24 + c.k]) * MG_SLOT; ++c.k; kv = false; break; }
+                ++c.step; c.l = 0; c.k = 0; c.pi = 0;
+            }
         }
     }
     // one TMA bulk copy per job, issued by lane 0: a weight slot, or a whole chunk of a head's k|v records (the cache
     // is zero-filled before the generation, so the tokens of the chunk that are not cached yet read as zeros)
-    if (wpos >= 0) {
-        if (lane == 0) {
-            mbar_expect_tx(bar, MG_SLOT);
-            bulk_g2s(smem_u32(stage), p.wsrc + static_cast<size_t>(wpos) * MG_SLOT, MG_SLOT, bar, p.w_policy);
-        }
-    } else {
-        constexpr int CHUNK_BYTES = CT * 4 * D;
-        const int q = p.warp + MG_WARPS * c.pi;
-        const int b = p.s0 + (q >> p.hpc_shift), h = p.crank * p.HPC + (q & (p.HPC - 1));
-        const size_t off = ((static_cast<size_t>(b) * p.H + h) * p.t_max + static_cast<size_t>(c.c) * CT) * (2 * D);
-        if (lane == 0) {
-            mbar_expect_tx(bar, CHUNK_BYTES);
-            bulk_g2s(smem_u32(stage), p.cache + static_cast<size_t>(c.l) * p.layer_stride + off, CHUNK_BYTES, bar, p.kv_policy);
-        }
-        if (++c.c == (c.step + CT - 1) / CT) { c.c = 0; ++c.pi; }
+    if (kv) c.kv_ptr = src + (static_cast<size_t>(CHUNK_BYTES) << p.ss);
+    const uint32_t bytes = kv ? CHUNK_BYTES : static_cast<uint32_t>(MG_SLOT);
+    if (lane == 0) {
+        mbar_expect_tx(bar, bytes);
+        bulk_g2s(smem_u32(stage), src, bytes, bar, kv ? p.kv_policy : p.w_policy);
     }
+}
+
+// L2 prefetch of this warp's KV jobs [lo, hi) of the attention phase of (`step`, `layer`), one job per lane.  The
+// attention phase streams the cache at HBM speed while the GEMM phases leave HBM idle (their weights come from L2)
+// and the rings hold only the next few jobs, so the GEMM phases ask L2 for the first chunks of the coming attention
+// phase: its TMA copies of those chunks then hit L2 and HBM serves the rest meanwhile.
+template <int D>
+__device__ __forceinline__ void kv_prefetch_l2(const JobPlan& p, int layer, int step, int lo, int hi, int lane) {
+    constexpr int CT = MG_CT(D);
+    constexpr int CHUNK_BYTES = CT * 4 * D;
+    const int nchunks = (step + CT - 1) / CT;
+    const int nck = nchunks > p.split ? (nchunks - p.split + (1 << p.ss) - 1) >> p.ss : 0;    // chunks per item of this warp
+    int n = lo + lane;
+    if (nck == 0 || n >= hi) return;
+    int pi = 0;
+    while (pi < p.nmine && n >= nck) { n -= nck; ++pi; }
+    if (pi >= p.nmine) return;
+    const int q = (p.warp + MG_WARPS * pi) >> p.ss;
+    const int b = p.s0 + (q >> p.hpc_shift), h = p.crank * p.HPC + (q & (p.HPC - 1));
+    const size_t off = ((static_cast<size_t>(b) * p.H + h) * p.t_max + static_cast<size_t>(p.split + (n << p.ss)) * CT) * (2 * D);
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.cache + static_cast<size_t>(layer) * p.layer_stride + off), "r"(CHUNK_BYTES)
+                 : "memory");
 }
 
 // Waits for the warp's next job and returns its stage.  (The stage index and the mbarrier phase are tracked
@@ -551,7 +586,13 @@ decode_mega_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ M
     plan.w_policy = a.l2_hints ? l2_policy_evict_last() : l2_policy_evict_normal();
     plan.kv_policy = a.l2_hints ? l2_policy_evict_first() : l2_policy_evict_normal();
     plan.tab = tab; plan.n_pre = n_pre; plan.n_post = n_post; plan.n_logit = n_logit;
-    plan.warp = warp; plan.steps = a.steps; plan.L = a.L; plan.s0 = s0; plan.nmine = units_of(warp, G * HPC);
+    // With few (sequence, head) pairs in the CTA (small batches) the chunks of a pair are dealt to 2, 4 or 8 adjacent
+    // warps, which merge their partial softmax states through shared memory: the attention phase is a serial walk
+    // over the context, so its length is what the split shortens.
+    int kv_ss = 0;
+    while (kv_ss < a.kv_split_log2 && ((G * HPC) << (kv_ss + 1)) <= MG_WARPS) ++kv_ss;
+    plan.ss = kv_ss; plan.split = warp & ((1 << kv_ss) - 1);
+    plan.warp = warp; plan.steps = a.steps; plan.L = a.L; plan.s0 = s0; plan.nmine = units_of(warp, (G * HPC) << kv_ss);
     plan.hpc_shift = 31 - __clz(HPC); plan.HPC = HPC; plan.H = H; plan.crank = crank; plan.t_max = a.t_max;
     plan.per_layer = sm.per_layer;
     JobRing jr;
@@ -559,7 +600,7 @@ decode_mega_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ M
     jr.base = ring + first_stage * MG_STAGE;
     jr.bars = bars + first_stage;
     jr.stage = 0; jr.phase = 0; jr.nst = NST + (warp < sm.nst_extra ? 1 : 0);
-    jr.cur = JobCursor{0, 0, 0, 0, 0};
+    jr.cur = JobCursor{0, 0, 0, 0, 0, nullptr};
     jr.wait_prof = nullptr;
     const bool wait_profiling = a.prof != nullptr && blockIdx.x == 0 && tid == 0;
 #define MG_WAIT_SLOT(k) if (wait_profiling) jr.wait_prof = prof_acc + 16 + (k);
@@ -632,6 +673,12 @@ decode_mega_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ M
             const int dst_pitch = (kind == 2) ? pf : pe;
             const int col0 = crank * ((kind == 2) ? FS : HS);
             const uint32_t zbase = map_to_cta(smem_u32(Z), 0);
+            if (a.kv_prefetch > 0 && kind >= 1 && kind <= 3) {          // a third of the budget in front of each GEMM phase
+                const bool wrap = l + 1 == a.L;
+                if (!wrap || step + 1 < a.steps)
+                    kv_prefetch_l2<D>(plan, wrap ? 0 : l + 1, wrap ? step + 1 : step, jr.nst + (kind - 1) * a.kv_prefetch / 3,
+                                      jr.nst + kind * a.kv_prefetch / 3, lane);      // (the first jobs of the phase are fetched by the ring itself)
+            }
             MG_WAIT_SLOT(kind == 0 ? 0 : kind + 1)
             run_phase<D>(ph, src, src_pitch, jr, plan, red, warp, lane, [&](int col, int seq, float2 lo, float2 hi) {
                 if (kind == 0) {                   // q, k, v of this CTA's heads (bf16, local)
@@ -665,9 +712,10 @@ decode_mega_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ M
                 {
                     MG_WAIT_SLOT(1)
                     __nv_bfloat16* cache_l = a.cache + static_cast<size_t>(l) * a.layer_stride;
-                    const int npairs = G * HPC;
-                    const int nmine = (npairs > warp) ? (npairs - warp + MG_WARPS - 1) / MG_WARPS : 0;
+                    const int nmine = plan.nmine;
                     const int nchunks = (pos + CT - 1) / CT;
+                    const int ss = plan.ss;
+                    const bool lead = plan.split == 0;             // appends k|v, seeds the softmax, writes the output
                     // ldmatrix row addresses of this lane inside a 16-token tile of k|v records: the K rows are the A
                     // operand of the score MMA (16 tokens x d_h), the V rows the B operand of P.V (transposed load)
                     // (pieces are swizzled, see kv_piece_off; the swizzle of a lane's row does not depend on the tile)
@@ -680,7 +728,7 @@ decode_mega_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ M
                         v_lane[ks] = kv_piece_off<D>((mi & 1) * 8 + mr, PR / 2 + ks * 2 + (mi >> 1));
                     }
                     for (int pi = 0; pi < nmine; ++pi) {
-                        const int q = warp + MG_WARPS * pi;
+                        const int q = (warp + MG_WARPS * pi) >> ss;
                         const int sl = q / HPC, hh = q % HPC;
                         const int b = s0 + sl, h = crank * HPC + hh;
                         const uint32_t* qw = reinterpret_cast<const uint32_t*>(qkvs + (sl * 3 * HS + hh * D) * 2);
@@ -703,16 +751,16 @@ decode_mega_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ M
                         }
                         snew += __shfl_xor_sync(0xffffffffu, snew, 1);
                         snew += __shfl_xor_sync(0xffffffffu, snew, 2);
-                        float m = snew * a.scale_log2;                  // running maximum (log2 units), warp-uniform
-                        float lsum = (lane < 4) ? 1.f : 0.f;            // this lane's share of 4 x the denominator (4 tig copies)
+                        float m = lead ? snew * a.scale_log2 : -INFINITY;        // running maximum (log2 units), warp-uniform
+                        float lsum = (lead && lane < 4) ? 1.f : 0.f;    // this lane's share of 4 x the denominator (4 tig copies)
                         float o[NT_O][4];                               // row 0 of P.V; every quad carries a copy
     #pragma unroll
                         for (int dt = 0; dt < NT_O; ++dt) {
                             const float2 vn = unpack_bf16(vw[dt * 4 + tig]);
-                            o[dt][0] = vn.x; o[dt][1] = vn.y; o[dt][2] = 0.f; o[dt][3] = 0.f;
+                            o[dt][0] = lead ? vn.x : 0.f; o[dt][1] = lead ? vn.y : 0.f; o[dt][2] = 0.f; o[dt][3] = 0.f;
                         }
                         // append the k|v record to the global cache
-                        if (lane < 2 * CH) {
+                        if (lead && lane < 2 * CH) {
                             const int part = lane % CH;
                             // (the pieces of a record are stored swizzled, so that a chunk is a linear image of a stage)
                             const size_t rec = ((static_cast<size_t>(b) * H + h) * a.t_max + pos) * (2 * D);
@@ -721,7 +769,7 @@ decode_mega_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ M
                             asm volatile("fence.proxy.async.global;" ::: "memory");    // read back by TMA in a later job
                         }
                         __syncwarp();
-                        for (int c = 0; c < nchunks; ++c) {
+                        for (int c = plan.split; c < nchunks; c += 1 << ss) {
                             uint8_t* st = ring_acquire(jr);
                             const int ntok = min(CT, pos - c * CT);
                             const uint32_t st_a = smem_u32(st);
@@ -783,9 +831,42 @@ decode_mega_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ M
                         lsum += __shfl_xor_sync(0xffffffffu, lsum, 16);
                         lsum += __shfl_xor_sync(0xffffffffu, lsum, 1);
                         lsum += __shfl_xor_sync(0xffffffffu, lsum, 2);
+                        if (ss > 0) {                                   // merge the partial states of the pair's warps
+                            constexpr int PW = 68;                      // floats per warp: m, l, -, -, o[D]
+                            float* part = red + warp * PW;
+                            const uint32_t bar_id = 1 + (warp >> ss), bar_n = 32u << ss;
+                            if (!lead) {
+                                if (lane == 0) { part[0] = m; part[1] = lsum; }
+                                if (lane < 4) {
+    #pragma unroll
+                                    for (int dt = 0; dt < NT_O; ++dt) *reinterpret_cast<float2*>(part + 4 + dt * 8 + 2 * tig) = make_float2(o[dt][0], o[dt][1]);
+                                }
+                            }
+                            asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_n) : "memory");
+                            if (lead) {
+                                float mm = m;
+                                for (int j = 1; j < (1 << ss); ++j) mm = fmaxf(mm, part[j * PW]);
+                                const float w0 = fast_exp2(m - mm);
+                                lsum *= w0;
+    #pragma unroll
+                                for (int dt = 0; dt < NT_O; ++dt) { o[dt][0] *= w0; o[dt][1] *= w0; }
+                                for (int j = 1; j < (1 << ss); ++j) {
+                                    const float* pj = part + j * PW;
+                                    const float wj = fast_exp2(pj[0] - mm);
+                                    lsum = fmaf(wj, pj[1], lsum);
+    #pragma unroll
+                                    for (int dt = 0; dt < NT_O; ++dt) {
+                                        const float2 oj = *reinterpret_cast<const float2*>(pj + 4 + dt * 8 + 2 * tig);
+                                        o[dt][0] = fmaf(wj, oj.x, o[dt][0]);
+                                        o[dt][1] = fmaf(wj, oj.y, o[dt][1]);
+                                    }
+                                }
+                            }
+                            asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_n) : "memory");      // the slots are free again
+                        }
                         const float inv = 4.0f / lsum;                  // lsum counted every token in its 4 tig lanes
                         // every quad holds the same output row: quad g sends it to CTA g of the cluster
-                        if (g < CL) {
+                        if (lead && g < CL) {
                             const uint32_t dst = map_to_cta(smem_u32(Y + sl * pe + (h * D + 2 * tig) * 2), g);
     #pragma unroll
                             for (int dt = 0; dt < NT_O; ++dt) st_cluster_u32(dst + dt * 16, pack_bf16(o[dt][0] * inv, o[dt][1] * inv));
@@ -1083,8 +1164,14 @@ int decode_mega(MegaArgs args, int D, int max_clusters, int cluster_size, uint8_
     CB200_CUDA_OK(cudaGetLastError());
     note_launch(1);
     args.wstream = stream_ws;
+    args.kv_split_log2 = 2;
+    if (const char* env = getenv("CB200_DECODE_KV_SPLIT")) args.kv_split_log2 = std::min(3, std::max(0, atoi(env)));      // tuning knob
     args.l2_hints = 1;
     if (const char* env = getenv("CB200_DECODE_L2_HINTS")) args.l2_hints = atoi(env) != 0;
+    // L2 prefetch budget of an attention phase, dealt evenly to the warps of all CTAs as whole 4 KB chunks
+    int prefetch_mb = 0;          // (measured: no gain, the attention phase is issue-bound rather than HBM-bound)
+    if (const char* env = getenv("CB200_DECODE_KV_PREFETCH_MB")) prefetch_mb = std::max(0, atoi(env));                  // tuning knob
+    args.kv_prefetch = static_cast<int>(std::min<long long>(30, (static_cast<long long>(prefetch_mb) << 20) / (static_cast<long long>(ncl) * CL * MG_WARPS * MG_STAGE)));
     if (args.prof != nullptr) CB200_CUDA_OK(cudaMemsetAsync(args.prof, 0, 24 * sizeof(long long), s));
     return CB200_MEGA_DISPATCH(launch_mega, args, sm, ncl, s);
 }
