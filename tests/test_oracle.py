@@ -111,3 +111,41 @@ def test_sampling_distribution_rows_sum_to_one():
     p = oracle.next_token_distribution(np.array([[0.0, 1.0, -2.0]]), 0.7)
     np.testing.assert_allclose(p.sum(axis=-1), 1.0)
     assert p[0, 1] > p[0, 0] > p[0, 2]
+
+
+def test_oracle_matches_tf_reference():
+    '''
+    Pins the oracle to outputs of the reference itself when ``tests/golden/tf_reference.npz`` exists (written by
+    ``tools/dump_tf_reference.py`` where TensorFlow and the reference are available; neither is in this image, hence
+    the skip).  Tolerances: fp32 TensorFlow against the fp64 oracle.
+    '''
+    import os
+    import pytest
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'tf_reference.npz')
+    if not os.path.exists(path):
+        pytest.skip('no TensorFlow dump of the reference (tools/dump_tf_reference.py has to run where TensorFlow exists)')
+    data = np.load(path)
+    vocab, embedding, window, layers, heads = (int(v) for v in data['config'])
+    cfg = oracle.OracleConfig(vocab_size=vocab, embedding_size=embedding, window_size=window, decoder_layers_count=layers,
+                              attention_head_count=heads, attention_dropout_rate=0.0, residual_dropout_rate=0.0)
+    weights = {k[len('param/'):]: data[k] for k in data.files if k.startswith('param/')}
+    weights = type(oracle.init_parameters(cfg))((k, weights[k]) for k in oracle.parameter_shapes(cfg))
+    x, y = data['x'], data['y']
+    loss, _, logits, grads = oracle.loss_and_gradients(weights, x, y, cfg)
+    np.testing.assert_allclose(logits, data['logits'], rtol=2e-4, atol=2e-4)
+    assert abs(loss - float(data['loss'])) < 1e-4
+    for name in weights:
+        np.testing.assert_allclose(grads[name], data['grad/' + name], rtol=2e-3, atol=2e-6, err_msg=name)
+    adam = oracle.AdamState(weights)
+    updated = adam.apply({k: v.copy() for k, v in weights.items()}, grads)
+    for name in weights:
+        np.testing.assert_allclose(updated[name], data['adam/' + name], rtol=1e-4, atol=2e-5, err_msg=name)
+    steps = data['decode_ids'].shape[1]
+    ids, step_logits = oracle.generate(weights, x[:, :1], steps, cfg, greedy=True)
+    np.testing.assert_allclose(step_logits, data['decode_logits'], rtol=2e-4, atol=2e-4)
+    # greedy ids must agree wherever the reference's top-2 margin is not within rounding
+    top2 = np.sort(data['decode_logits'], axis=-1)[..., -2:]
+    decided = (top2[..., 1] - top2[..., 0]) > 1e-3
+    first_undecided = np.where(~decided.all(axis=0))[0]
+    upto = int(first_undecided[0]) if first_undecided.size else steps
+    assert (ids[:, :upto] == data['decode_ids'][:, :upto]).all()
