@@ -143,13 +143,20 @@ struct Phase {
 constexpr int MG_STAGE = MG_SLOT;          // >= the 4 KB of a KV stage
 
 // Byte offset of 16-byte piece `c` of token `t` inside a KV stage.  A k|v record is 4 D bytes (4, 8 or 16 pieces);
-// ldmatrix reads one piece of 8 consecutive tokens, which would land in 2 (d_h 16) or 1 (d_h >= 32) of the 8
-// 16-byte bank groups, a 4- or 8-way conflict that made shared memory the limiter of the attention phase.  The
-// piece index is XOR-ed with token bits so that those 8 reads cover all 8 groups; cp.async writes the pieces there.
+// ldmatrix reads one piece of 8 tokens, which would land in 2 (d_h 16) or 1 (d_h >= 32) of the 8 16-byte bank
+// groups, a 4- or 8-way conflict that made shared memory the limiter of the attention phase.  The piece position
+// is XOR-ed with token bits so that both row sets the attention reads cover all 8 groups: 8 consecutive tokens (K,
+// the score MMA) and tokens {j, j + 8 : j even} or {j, j + 8 : j odd} of a 16-token tile (V, in the order the
+// probabilities come out of the softmax).  d_h 16: two records share a 128-byte line and the XOR runs over the 8
+// positions of the line.  The appended records are written to the cache in this form.
 template <int D>
 __device__ __forceinline__ uint32_t kv_piece_off(int t, int c) {
     constexpr int REC = 4 * D;
-    const int sw = (D == 16) ? ((t >> 1) & 3) : (t & 7);
+    if (D == 16) {
+        const int pos = (((t & 1) << 2) | c) ^ (((t >> 1) & 3) | (((t >> 3) & 1) << 2));
+        return static_cast<uint32_t>((t >> 1) * (2 * REC) + (pos << 4));
+    }
+    const int sw = (t ^ ((t >> 3) & 1)) & 7;       // (bit 3 only: the same for every 16-token tile of the stage)
     return static_cast<uint32_t>(t * REC + ((c ^ sw) << 4));
 }
 
@@ -725,7 +732,10 @@ decode_mega_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ M
     #pragma unroll
                     for (int ks = 0; ks < D / 16; ++ks) {
                         k_lane[ks] = kv_piece_off<D>((mi & 1) * 8 + mr, ks * 2 + (mi >> 1));
-                        v_lane[ks] = kv_piece_off<D>((mi & 1) * 8 + mr, PR / 2 + ks * 2 + (mi >> 1));
+                        // (V rows in the order the probabilities arrive in: k = 2t, 2t + 1, 2t + 8, 2t + 9 of the P.V MMA are
+                        // tokens 2t, 2t + 8, 2t + 1, 2t + 9 of the tile, so that a lane's packed pair {token g, token g + 8}
+                        // is an A-operand register as it stands)
+                        v_lane[ks] = kv_piece_off<D>((mr & ~1) + (mi & 1) + (mr & 1) * 8, PR / 2 + ks * 2 + (mi >> 1));
                     }
                     for (int pi = 0; pi < nmine; ++pi) {
                         const int q = (warp + MG_WARPS * pi) >> ss;
@@ -792,9 +802,14 @@ decode_mega_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ M
                                     if (jt * 16 + 8 + g >= ntok) s[jt][2] = -INFINITY;
                                 }
                             }
-                            float mx = -INFINITY;
+                            float tm[CT / 16];                 // (a tree: the chain of dependent maxima was on the critical path)
     #pragma unroll
-                            for (int jt = 0; jt < CT / 16; ++jt) mx = fmaxf(mx, fmaxf(s[jt][0], s[jt][2]));
+                            for (int jt = 0; jt < CT / 16; ++jt) tm[jt] = fmaxf(s[jt][0], s[jt][2]);
+    #pragma unroll
+                            for (int w = CT / 32; w > 0; w >>= 1)
+    #pragma unroll
+                                for (int jt = 0; jt < w; ++jt) tm[jt] = fmaxf(tm[jt], tm[jt + w]);
+                            float mx = tm[0];
                             mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
                             mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
                             mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
@@ -812,10 +827,8 @@ decode_mega_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ M
                                 const float p_hi = fast_exp2(fmaf(s[jt][2], a.scale_log2, -mn));
                                 lsum += p_lo + p_hi;
                                 const uint32_t pk = pack_bf16(p_lo, p_hi);            // {token g, token g + 8} of this tile
-                                const uint32_t y0 = __shfl_sync(0xffffffffu, pk, 8 * tig);
-                                const uint32_t y1 = __shfl_sync(0xffffffffu, pk, 8 * tig + 4);
-                                const uint32_t a0 = __byte_perm(y0, y1, 0x5410);      // tokens 2 tig, 2 tig + 1
-                                const uint32_t a2 = __byte_perm(y0, y1, 0x7632);      // tokens 2 tig + 8, 2 tig + 9
+                                const uint32_t a0 = __shfl_sync(0xffffffffu, pk, 8 * tig);        // tokens 2 tig, 2 tig + 8
+                                const uint32_t a2 = __shfl_sync(0xffffffffu, pk, 8 * tig + 4);    // tokens 2 tig + 1, 2 tig + 9
     #pragma unroll
                                 for (int dp = 0; dp < D / 16; ++dp) {
                                     uint32_t vb[4];

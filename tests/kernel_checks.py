@@ -507,11 +507,13 @@ def check_engine_adam_step(B=2, T=64):
 
 
 def check_generate(B=4, prompt_len=5, length=40, impl=0, max_clusters=0, embedding=256, heads=16, cluster_size=0,
-                   window=64):
-    '''impl 0 = persistent cluster kernel (decode_mega.cu), 1 = per-step kernels replayed as a CUDA graph.'''
+                   window=64, sharp=False):
+    '''impl 0 = persistent cluster kernel (decode_mega.cu), 1 = per-step kernels replayed as a CUDA graph.
+    ``sharp`` scales the query / key projections so that the attention concentrates on a few cached tokens: with
+    the initialiser's weights it is nearly uniform and a k|v row read from the wrong place hardly shows.'''
     _lib.call('cb200_set_decode_impl', impl, max_clusters, cluster_size)
     try:
-        return _check_generate(B, prompt_len, length, embedding, heads, window)
+        return _check_generate(B, prompt_len, length, embedding, heads, window, sharp)
     finally:
         _lib.call('cb200_set_decode_impl', 0, 0, 0)
 
@@ -559,11 +561,17 @@ def check_generate_impls_agree(B=19, prompt_len=3, length=50, embedding=256, hea
     return _finish(results)
 
 
-def _check_generate(B, prompt_len, length, embedding, heads, window=64):
+def _check_generate(B, prompt_len, length, embedding, heads, window=64, sharp=False):
     import numpy as np
     from oracle import transformer_oracle as oracle
 
     model, cfg, weights = _small_model(2, embedding, heads, window=window)
+    if sharp:
+        for name in weights:
+            if name.endswith('attn/c_attn/weight'):
+                weights[name] = weights[name].copy()
+                weights[name][:, :2 * embedding] *= 6.0
+        model.set_weights(weights)
     rng = np.random.default_rng(9)
     prompt = rng.integers(0, cfg.vocab_size, size=(B, prompt_len))
     results = []
@@ -609,6 +617,10 @@ def _check_generate(B, prompt_len, length, embedding, heads, window=64):
             # a draw within tolerance of a CDF edge may legitimately fall either side
             edge = np.abs(cdf - u[:, None]).min(axis=-1)
             near += int(((chosen != out_s[:, step]) & (edge < 5e-3)).sum())
+            if step == length - 1:
+                # logits of the last step: every cached token of every layer has been read by then
+                results.append(_stats('last-step logits vs oracle%s' % (' (sharp attention)' if sharp else ''),
+                                      last_logits.float().cpu(), torch.from_numpy(logits[:, -1].numpy()).float(), 3e-2))
             ids = np.concatenate([ids, out_s[:, step:step + 1]], axis=1)
     results.append({'name': 'sampled decode agreement %d/%d (+%d at CDF edges)' % (agree, total, near),
                     'rel': total - agree - near, 'tol': 0, 'nan': False, 'ok': agree + near == total})
@@ -640,5 +652,12 @@ GROUPS['generate'] = [check_generate, lambda: check_generate(impl=1),
                       lambda: check_generate(B=3, prompt_len=70, length=90, window=192),
                       lambda: check_generate(B=10, prompt_len=2, length=140, window=192, cluster_size=4),
                       lambda: check_generate_impls_agree(B=6, prompt_len=2, length=250, window=256),
+                      # sharp attention (see check_generate): d_h 16 with 8- and 4-CTA clusters and split pairs, d_h 32,
+                      # the per-step kernels, and d_h 64
+                      lambda: check_generate(B=3, prompt_len=40, length=150, window=192, sharp=True),
+                      lambda: check_generate(B=40, prompt_len=2, length=100, window=128, cluster_size=4, sharp=True),
+                      lambda: check_generate(B=5, prompt_len=30, length=70, embedding=512, heads=16, window=128, sharp=True),
+                      lambda: check_generate(B=3, prompt_len=30, length=70, window=128, impl=1, sharp=True),
+                      lambda: check_generate(B=3, prompt_len=20, length=40, embedding=1024, heads=16, sharp=True),
                       check_generate_impls_agree,
                       lambda: check_generate_impls_agree(B=33, embedding=512, heads=16)]
