@@ -67,6 +67,11 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+__device__ __forceinline__ float warp_max_f32(float v) {        // sm_100a: warp-wide fp32 maximum in one instruction
+    float r;
+    asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+    return r;
+}
 __device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank) {
     uint32_t r;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
@@ -810,9 +815,7 @@ decode_mega_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ M
     #pragma unroll
                                 for (int jt = 0; jt < w; ++jt) tm[jt] = fmaxf(tm[jt], tm[jt + w]);
                             float mx = tm[0];
-                            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
-                            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
-                            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+                            mx = warp_max_f32(mx);              // one CREDUX instead of three shuffle + max rounds
                             const float mn = fmaxf(m, mx * a.scale_log2);
                             const float corr = fast_exp2(m - mn);
                             m = mn;
@@ -1182,7 +1185,7 @@ int decode_mega(MegaArgs args, int D, int max_clusters, int cluster_size, uint8_
     args.l2_hints = 1;
     if (const char* env = getenv("CB200_DECODE_L2_HINTS")) args.l2_hints = atoi(env) != 0;
     // L2 prefetch budget of an attention phase, dealt evenly to the warps of all CTAs as whole 4 KB chunks
-    int prefetch_mb = 0;          // (measured: no gain, the attention phase is issue-bound rather than HBM-bound)
+    int prefetch_mb = 0;          // (measured: a net loss, the prefetch traffic slows the GEMM phases by more than its hits save)
     if (const char* env = getenv("CB200_DECODE_KV_PREFETCH_MB")) prefetch_mb = std::max(0, atoi(env));                  // tuning knob
     args.kv_prefetch = static_cast<int>(std::min<long long>(30, (static_cast<long long>(prefetch_mb) << 20) / (static_cast<long long>(ncl) * CL * MG_WARPS * MG_STAGE)));
     if (args.prof != nullptr) CB200_CUDA_OK(cudaMemsetAsync(args.prof, 0, 24 * sizeof(long long), s));
