@@ -246,10 +246,10 @@ __device__ __forceinline__ void job_issue(const JobPlan& p, JobCursor& c, uint8_
     }
 }
 
-// L2 prefetch of this warp's KV jobs [lo, hi) of the attention phase of (`step`, `layer`), one job per lane.  The
-// attention phase streams the cache at HBM speed while the GEMM phases leave HBM idle (their weights come from L2)
-// and the rings hold only the next few jobs, so the GEMM phases ask L2 for the first chunks of the coming attention
-// phase: its TMA copies of those chunks then hit L2 and HBM serves the rest meanwhile.
+// L2 prefetch of this warp's KV jobs [lo, hi) of the attention phase of (`step`, `layer`), one job per lane: the
+// attention phase streams the cache at HBM speed while the GEMM phases leave HBM idle, so the GEMM phases can ask L2
+// for the first chunks of the coming attention phase.  OFF by default (CB200_DECODE_KV_PREFETCH_MB): measured, the
+// hits save less than the prefetch traffic costs the L2-resident weight slots the GEMM phases wait for.
 template <int D>
 __device__ __forceinline__ void kv_prefetch_l2(const JobPlan& p, int layer, int step, int lo, int hi, int lane) {
     constexpr int CT = MG_CT(D);
