@@ -2,6 +2,7 @@
 // creation (cuTensorMapEncodeTiled through the runtime's driver entry point,
 // so libcuda is not a link-time dependency) and template dispatch.
 #include "gemm.h"
+#include <cstdlib>
 
 #include <cstdio>
 #include <cstring>
@@ -101,7 +102,7 @@ int device_sm_count() {
     return sms;
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI, int STAGES>
+template <int BN, bool A_MN, bool B_MN, int EPI, int STAGES, int KRES = 0>
 static int launch_variant(const GemmDesc& d, cudaStream_t stream) {
     using L = GemmSmem<BN>;
     constexpr bool staging = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU || EPI == EPI_BIAS_DROP_RES ||
@@ -109,7 +110,7 @@ static int launch_variant(const GemmDesc& d, cudaStream_t stream) {
     constexpr int num_out = (EPI == EPI_BIAS_GELU) ? 2 : 1;
     constexpr int b_box_rows = (BN <= 256) ? BN : BN / 2;
     constexpr bool aux_tma = (EPI == EPI_BIAS_DROP_RES || EPI == EPI_MUL_DGELU);
-    constexpr size_t smem_bytes = size_t(STAGES) * L::STAGE_BYTES + (staging ? (aux_tma ? 3 : 2) * num_out * L::STAGING_BYTES : 0) +
+    constexpr size_t smem_bytes = size_t(KRES) * L::B_BYTES + size_t(STAGES) * (KRES ? L::A_BYTES : L::STAGE_BYTES) + (staging ? (aux_tma ? 3 : 2) * num_out * L::STAGING_BYTES : 0) +
                                   256 /* barriers */ + 1024 /* alignment slack */;
     static_assert(smem_bytes <= 232448, "shared memory budget exceeded");
 
@@ -172,26 +173,40 @@ static int launch_variant(const GemmDesc& d, cudaStream_t stream) {
     if (EPI == EPI_ATOMIC_F32) CB200_REQUIRE(d.outf != nullptr && d.ld_outf % 4 == 0 && d.N % 4 == 0, "atomic epilogue needs outf, ld %% 4 == 0");
     if (d.bias != nullptr) CB200_REQUIRE(d.N % 4 == 0 && (reinterpret_cast<uintptr_t>(d.bias) & 15) == 0, "bias must be 16-byte aligned, N %% 4 == 0");
 
-    auto kernel = gemm_sm100_kernel<BN, A_MN, B_MN, EPI, STAGES>;
+    if (KRES > 0) CB200_REQUIRE(a.k_blocks_total == KRES && a.k_splits == 1, "resident-B GEMM needs K = %d", KRES * GEMM_BK);
+    auto kernel = gemm_sm100_kernel<BN, A_MN, B_MN, EPI, STAGES, KRES>;
     static bool configured = false;
     if (!configured) {
         CB200_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
         configured = true;
     }
     const int total_tiles = a.num_m_tiles * a.num_n_tiles * a.k_splits;
-    const int grid = total_tiles < sms ? total_tiles : sms;
+    int grid = total_tiles < sms ? total_tiles : sms;
+    if (KRES > 0 && grid % a.num_n_tiles != 0) grid -= grid % a.num_n_tiles;       // one column tile per CTA (see the kernel)
     kernel<<<grid, GEMM_THREADS, smem_bytes, stream>>>(tmA, tmB, tmC0, tmC1, a);
     CB200_CUDA_OK(cudaGetLastError());
     note_launch(1);
     return 0;
 }
 
+// K = 256 (the model width of the benchmark configurations): keep B resident.  CB200_GEMM_BRES=0 disables it (A/B).
+static bool resident_b(const GemmDesc& d) {
+    static const bool enabled = [] { const char* e = getenv("CB200_GEMM_BRES"); return e == nullptr || atoi(e) != 0; }();
+    return enabled && d.K == 4 * GEMM_BK;
+}
+
 int gemm_launch(const GemmDesc& d, cudaStream_t stream) {
     switch (d.kind) {
-        case GEMM_BIAS:       return launch_variant<256, false, false, EPI_BIAS_BF16, 4>(d, stream);
+        case GEMM_BIAS:
+            if (resident_b(d)) return launch_variant<256, false, false, EPI_BIAS_BF16, 4, 4>(d, stream);
+            return launch_variant<256, false, false, EPI_BIAS_BF16, 4>(d, stream);
         case GEMM_BIAS_GELU:  return launch_variant<256, false, false, EPI_BIAS_GELU, 3>(d, stream);
-        case GEMM_BIAS_DROP_RES: return launch_variant<256, false, false, EPI_BIAS_DROP_RES, 3>(d, stream);
-        case GEMM_MUL_DGELU:  return launch_variant<256, false, false, EPI_MUL_DGELU, 3>(d, stream);
+        case GEMM_BIAS_DROP_RES:
+            if (resident_b(d)) return launch_variant<256, false, false, EPI_BIAS_DROP_RES, 3, 4>(d, stream);
+            return launch_variant<256, false, false, EPI_BIAS_DROP_RES, 3>(d, stream);
+        case GEMM_MUL_DGELU:
+            if (resident_b(d)) return launch_variant<256, false, false, EPI_MUL_DGELU, 3, 4>(d, stream);
+            return launch_variant<256, false, false, EPI_MUL_DGELU, 3>(d, stream);
         case GEMM_WGRAD:      return launch_variant<256, true, true, EPI_ATOMIC_F32, 4>(d, stream);
         case GEMM_CE:
             if (d.N <= 400) return launch_variant<400, false, false, EPI_CE, 3>(d, stream);
