@@ -23,7 +23,10 @@
 //    scores and P.V run on the tensor cores (scores as K q: the 16 tokens of a
 //    tile are the MMA rows, the query is one column of the B operand; the
 //    probabilities travel to the A-operand layout of P.V with two shuffles per
-//    tile; V rows through ldmatrix.trans), the softmax stays online.
+//    tile; V rows through ldmatrix.trans, in the order the packed pairs arrive
+//    in), the softmax stays online.  With few (sequence, head) pairs per CTA
+//    (small batches) a pair's chunks are dealt to 2-4 warps whose partial
+//    softmax states are merged through shared memory.
 //  * Everything a warp reads from global memory on the hot path, weight slots
 //    and KV stages alike, is one static sequence of copy jobs in the warp's own
 //    program order (it depends on the step, not on data).  The warp owns 2-3
