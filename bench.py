@@ -421,7 +421,8 @@ def generation_benchmark(model, world, rank, device, dist):
                             device=device, seed=0)
     rng = np.random.default_rng(99)
     prompt = rng.integers(0, VOCAB, size=(total, 1))[rank * per_rank:(rank + 1) * per_rank]
-    gen_model.generate(prompt, 16, temperature=1.0, seed=7, sequence_index_base=rank * per_rank)   # warm-up
+    # warm-up at the timed shape: the KV cache and workspace are allocated here, not inside the timed region
+    gen_model.generate(prompt, length, temperature=1.0, seed=7, sequence_index_base=rank * per_rank)
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
