@@ -288,6 +288,113 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy_a, const __nv_bfloat16
     }
 }
 
+// The same for wide rows (E = 256 WPR): WPR warps share a row, each owning 256 columns, so that the per-column
+// partial sums stay at 8 per lane and kind (24 registers instead of 96 at E = 1024, where the one-warp-per-row kernel
+// ran at 1 block per SM and 1.8 TB/s).  The warps of a row exchange their two partial row sums through shared memory
+// behind a named barrier; the exchange slots alternate between rows, so one barrier per row is enough.
+template <int WPR>
+__global__ void __launch_bounds__(256)
+layernorm_bwd_split_kernel(const __nv_bfloat16* __restrict__ dy_a, const __nv_bfloat16* __restrict__ dy_b,
+                           const __nv_bfloat16* __restrict__ x, const float* __restrict__ stats,
+                           const float* __restrict__ gamma, const __nv_bfloat16* __restrict__ dres,
+                           __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                           int rows, int E, LnBwdTail tail) {
+    constexpr int GROUPS = 8 / WPR;
+    __shared__ float part[GROUPS][2][WPR][2];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int group = warp / WPR, w = warp % WPR;
+    const int col = (w * 32 + lane) * 8;              // this lane's 8 columns
+    float gam[8], pg[8], pb[8], pt[8];
+    {
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + col)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + col + 4));
+        gam[0] = g0.x; gam[1] = g0.y; gam[2] = g0.z; gam[3] = g0.w; gam[4] = g1.x; gam[5] = g1.y; gam[6] = g1.z; gam[7] = g1.w;
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { pg[e] = 0.f; pb[e] = 0.f; pt[e] = 0.f; }
+    int buf = 0;
+    const float inv_e = 1.0f / E;
+    for (int row = blockIdx.x * GROUPS + group; row < rows; row += gridDim.x * GROUPS) {
+        const float mean = stats[2 * static_cast<size_t>(row)], rstd = stats[2 * static_cast<size_t>(row) + 1];
+        const size_t off = static_cast<size_t>(row) * E + col;
+        const uint4 ra = *reinterpret_cast<const uint4*>(dy_a + off);
+        const uint4 rx = *reinterpret_cast<const uint4*>(x + off);
+        uint4 rb = make_uint4(0, 0, 0, 0);
+        if (dy_b != nullptr) rb = *reinterpret_cast<const uint4*>(dy_b + off);
+        uint4 rr = make_uint4(0, 0, 0, 0);
+        if (dres != nullptr) rr = *reinterpret_cast<const uint4*>(dres + off);
+        const uint32_t wa[4] = {ra.x, ra.y, ra.z, ra.w}, wx[4] = {rx.x, rx.y, rx.z, rx.w}, wb[4] = {rb.x, rb.y, rb.z, rb.w};
+        float dyv[8], xh[8];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 a = unpack_bf16(wa[e]), b = unpack_bf16(wb[e]), xx = unpack_bf16(wx[e]);
+            dyv[2 * e] = a.x + b.x; dyv[2 * e + 1] = a.y + b.y;
+            xh[2 * e] = (xx.x - mean) * rstd; xh[2 * e + 1] = (xx.y - mean) * rstd;
+        }
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float g = dyv[e] * gam[e];
+            s1 += g; s2 += g * xh[e];
+            pg[e] += dyv[e] * xh[e];
+            pb[e] += dyv[e];
+        }
+        s1 = warp_sum(s1);
+        s2 = warp_sum(s2);
+        if (lane == 0) { part[group][buf][w][0] = s1; part[group][buf][w][1] = s2; }
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(32 * WPR) : "memory");
+        s1 = 0.f; s2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < WPR; ++k) { s1 += part[group][buf][k][0]; s2 += part[group][buf][k][1]; }
+        buf ^= 1;
+        s1 *= inv_e; s2 *= inv_e;
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = rstd * (dyv[e] * gam[e] - s1 - xh[e] * s2);
+        if (dres != nullptr) {
+            const uint32_t wr[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { const float2 r = unpack_bf16(wr[e]); o[2 * e] += r.x; o[2 * e + 1] += r.y; }
+        }
+        uint4 out;
+        out.x = pack_bf16(o[0], o[1]); out.y = pack_bf16(o[2], o[3]);
+        out.z = pack_bf16(o[4], o[5]); out.w = pack_bf16(o[6], o[7]);
+        *reinterpret_cast<uint4*>(dx + off) = out;
+        if (tail.dbias != nullptr) {
+            const uint32_t wo[4] = {out.x, out.y, out.z, out.w};
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { const float2 p = unpack_bf16(wo[e]); f[2 * e] = p.x; f[2 * e + 1] = p.y; }
+            if (tail.drop.threshold16 != 0) {
+                const Philox4 r = drop_bits_rowmajor(tail.drop, tail.site, tail.layer, row, w * 32 + lane);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] = (drop_u16(r, e) < tail.drop.threshold16) ? 0.f : f[e] * tail.drop.keep_scale;
+                uint4 g;
+                g.x = pack_bf16(f[0], f[1]); g.y = pack_bf16(f[2], f[3]);
+                g.z = pack_bf16(f[4], f[5]); g.w = pack_bf16(f[6], f[7]);
+                *reinterpret_cast<uint4*>(tail.g_out + off) = g;
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) pt[e] += f[e];
+        }
+    }
+    extern __shared__ float red[];   // [3][E]
+    for (int i = threadIdx.x; i < 3 * E; i += blockDim.x) red[i] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        atomicAdd(&red[col + e], pg[e]);
+        atomicAdd(&red[E + col + e], pb[e]);
+        if (tail.dbias != nullptr) atomicAdd(&red[2 * E + col + e], pt[e]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < E; i += blockDim.x) {
+        atomicAdd(&dgamma[i], red[i]);
+        atomicAdd(&dbeta[i], red[E + i]);
+        if (tail.dbias != nullptr) atomicAdd(&tail.dbias[i], red[2 * E + i]);
+    }
+}
+
 int layernorm_bwd(const __nv_bfloat16* dy_a, const __nv_bfloat16* dy_b, const __nv_bfloat16* x, const float* stats,
                   const float* gamma, const __nv_bfloat16* dres, __nv_bfloat16* dx, float* dgamma, float* dbeta,
                   int rows, int E, cudaStream_t s) {
@@ -306,6 +413,15 @@ int layernorm_bwd_tail(const __nv_bfloat16* dy_a, const __nv_bfloat16* dy_b, con
     const int cap = 2 * device_sm_count_ew();
     if (grid > cap) grid = cap;
     const size_t smem = 3 * E * sizeof(float);
+    if (E == 1024) {
+        int wide = (rows + 1) / 2;                  // 2 rows per block pass
+        const int wide_cap = 4 * device_sm_count_ew();
+        if (wide > wide_cap) wide = wide_cap;
+        layernorm_bwd_split_kernel<4><<<wide, 256, smem, s>>>(dy_a, dy_b, x, stats, gamma, dres, dx, dgamma, dbeta, rows, E, tail);
+        CB200_CUDA_OK(cudaGetLastError());
+        note_launch(1);
+        return 0;
+    }
     switch (E / 256) {
         case 1: layernorm_bwd_kernel<1><<<grid, 256, smem, s>>>(dy_a, dy_b, x, stats, gamma, dres, dx, dgamma, dbeta, rows, E, tail); break;
         case 2: layernorm_bwd_kernel<2><<<grid, 256, smem, s>>>(dy_a, dy_b, x, stats, gamma, dres, dx, dgamma, dbeta, rows, E, tail); break;

@@ -57,7 +57,13 @@ def run(name, layers, embedding, heads, T, B, train, steps=5):
 
 
 if __name__ == '__main__':
-    run('configs[0] forward+loss default', 8, 256, 16, 1024, 4, train=False)
-    run('configs[1] train step T2048 (bench.py headline)', 8, 256, 16, 2048, 32, train=True)
-    run('configs[3] long context T4096', 8, 256, 16, 4096, 16, train=True)
-    run('configs[4] scaled L12 E1024', 12, 1024, 16, 1024, 16, train=True)
+    # optional arguments: the configurations to run (0, 1, 3, 4; default all) -- e.g. `bench_configs.py 4` under ncu
+    only = {int(v) for v in sys.argv[1:]} or {0, 1, 3, 4}
+    if 0 in only:
+        run('configs[0] forward+loss default', 8, 256, 16, 1024, 4, train=False)
+    if 1 in only:
+        run('configs[1] train step T2048 (bench.py headline)', 8, 256, 16, 2048, 32, train=True)
+    if 3 in only:
+        run('configs[3] long context T4096', 8, 256, 16, 4096, 16, train=True)
+    if 4 in only:
+        run('configs[4] scaled L12 E1024', 12, 1024, 16, 1024, 16, train=True)
