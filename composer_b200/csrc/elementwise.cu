@@ -599,23 +599,51 @@ int cast_bf16(const float* src, __nv_bfloat16* dst, size_t n, cudaStream_t s) {
 __global__ void __launch_bounds__(256)
 transpose_cast_kernel(const float* __restrict__ params, __nv_bfloat16* __restrict__ dst_base,
                       const TransposeJob* __restrict__ jobs) {
-    __shared__ float tile[32][33];
+    // 64 x 64 tiles: 256-byte row segments in, 128-byte row segments out (16-byte stores of 8 bf16 each); the 32 x 32
+    // version wrote 64 bytes per warp instruction and ran at 2 TB/s on the 152 M parameters of the scaled config.
+    __shared__ float tile[64][65];
     const TransposeJob job = jobs[blockIdx.z];
-    const int tiles_c = (job.cols + 31) / 32;
-    const int tiles_r = (job.rows + 31) / 32;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    const int tiles_c = (job.cols + 63) / 64;
+    const int tiles_r = (job.rows + 63) / 64;
+    const bool vec_in = (job.cols % 4 == 0) && (job.src_offset % 4 == 0);
+    const bool vec_out = (job.dst_ld % 8 == 0) && (job.dst_offset % 8 == 0);
     for (int tile_id = blockIdx.x; tile_id < tiles_c * tiles_r; tile_id += gridDim.x) {
         const int tr = tile_id / tiles_c, tc = tile_id % tiles_c;
         __syncthreads();
-        for (int i = ty; i < 32; i += 8) {
-            const int r = tr * 32 + i, c = tc * 32 + tx;
-            tile[i][tx] = (r < job.rows && c < job.cols) ? params[job.src_offset + static_cast<size_t>(r) * job.cols + c] : 0.f;
+        {   // load: 16 threads x float4 per row, 16 rows per pass
+            const int lc = (threadIdx.x & 15) * 4, lr = threadIdx.x >> 4;
+            for (int i = lr; i < 64; i += 16) {
+                const int r = tr * 64 + i, c = tc * 64 + lc;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r < job.rows) {
+                    const float* src = params + job.src_offset + static_cast<size_t>(r) * job.cols + c;
+                    if (vec_in && c + 3 < job.cols) v = *reinterpret_cast<const float4*>(src);
+                    else {
+                        if (c < job.cols) v.x = src[0];
+                        if (c + 1 < job.cols) v.y = src[1];
+                        if (c + 2 < job.cols) v.z = src[2];
+                        if (c + 3 < job.cols) v.w = src[3];
+                    }
+                }
+                tile[i][lc] = v.x; tile[i][lc + 1] = v.y; tile[i][lc + 2] = v.z; tile[i][lc + 3] = v.w;
+            }
         }
         __syncthreads();
-        for (int i = ty; i < 32; i += 8) {
-            const int c = tc * 32 + i, r = tr * 32 + tx;
-            if (c < job.cols && r < job.rows)
-                dst_base[job.dst_offset + static_cast<size_t>(c) * job.dst_ld + r] = __float2bfloat16_rn(tile[tx][i]);
+        {   // store: 8 threads x 8 bf16 per output row (= source column), 32 output rows per pass
+            const int sr = (threadIdx.x & 7) * 8, sc = threadIdx.x >> 3;
+            for (int i = sc; i < 64; i += 32) {
+                const int c = tc * 64 + i, r = tr * 64 + sr;
+                if (c >= job.cols || r >= job.rows) continue;
+                __nv_bfloat16* dst = dst_base + job.dst_offset + static_cast<size_t>(c) * job.dst_ld + r;
+                if (vec_out && r + 7 < job.rows) {
+                    uint4 o;
+                    o.x = pack_bf16(tile[sr][i], tile[sr + 1][i]); o.y = pack_bf16(tile[sr + 2][i], tile[sr + 3][i]);
+                    o.z = pack_bf16(tile[sr + 4][i], tile[sr + 5][i]); o.w = pack_bf16(tile[sr + 6][i], tile[sr + 7][i]);
+                    *reinterpret_cast<uint4*>(dst) = o;
+                } else {
+                    for (int k = 0; k < 8 && r + k < job.rows; ++k) dst[k] = __float2bfloat16_rn(tile[sr + k][i]);
+                }
+            }
         }
     }
 }
