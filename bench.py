@@ -439,11 +439,20 @@ def generation_benchmark(model, world, rank, device, dist):
     kv_write = per_rank * 2 * L * E * 2 * length
     bytes_per_gpu = weights * length + kv_read + kv_write
     peaks, kind = load_peaks()
+    # DRAM bytes of one generation at this shape (one launch of the persistent kernel) from the committed ncu capture
+    traffic = None
+    summary_path = os.path.join(ROOT, 'profiles', 'ncu_summary.json')
+    if world == 1 and os.path.exists(summary_path):
+        with open(summary_path) as handle:
+            entry = json.load(handle).get('decode_mega_kernel<16, 4>')
+        if entry and 'prompt 1, 1,024 events' in entry.get('capture', ''):
+            traffic = entry.get('dram_bytes_per_launch')
     return {'metric': 'generated events/s (256 sequences x 1024 events, temperature 1.0, KV-cache decode)',
             'value': total * length / seconds, 'unit': 'events/s', 'seconds': seconds, 'sequences_per_gpu': per_rank,
             'us_per_step': seconds / length * 1e6,
             'roofline': {'bound': 'hbm', 'achieved': bytes_per_gpu / seconds / 1e9, 'peak': peaks['hbm_gbs'],
-                         'unit': 'GB/s', 'frac': bytes_per_gpu / seconds / 1e9 / peaks['hbm_gbs'], 'traffic': None,
+                         'unit': 'GB/s', 'frac': bytes_per_gpu / seconds / 1e9 / peaks['hbm_gbs'], 'traffic': traffic,
+                         'algorithmic_bytes': bytes_per_gpu,
                          'peak_source': kind},
             'sample_ids': out[0, :8].tolist(),
             'implementation': decode_implementation(gen_model, per_rank)}
