@@ -552,7 +552,7 @@ def check_generate_impls_agree(B=19, prompt_len=3, length=50, embedding=256, hea
         rows = (got[0] == ref[0]).all(axis=1)
         if rows.any():
             results.append(_stats('final logits vs per-step kernels (%d identical rows)' % int(rows.sum()),
-                                  got[2][torch.from_numpy(rows)], ref[2][torch.from_numpy(rows)], 2e-2))
+                                  got[2][torch.from_numpy(rows)], ref[2][torch.from_numpy(rows)], 5e-3))
     a, b = outs[(0, 0)], outs[(0, 2)]
     # the two runs differ in cluster size, hence in the K split of the mlp c_proj: a near-tie may flip a token
     same = float(min((a[1][:, :8] == b[1][:, :8]).mean(), (a[0] == b[0]).mean()))
@@ -618,9 +618,11 @@ def _check_generate(B, prompt_len, length, embedding, heads, window=64, sharp=Fa
             edge = np.abs(cdf - u[:, None]).min(axis=-1)
             near += int(((chosen != out_s[:, step]) & (edge < 5e-3)).sum())
             if step == length - 1:
-                # logits of the last step: every cached token of every layer has been read by then
+                # logits of the last step: every cached token of every layer has been read by then (measured 1-2e-3 of
+                # the largest logit in every variant, `tools/generate_margins.py`; a k|v row read from the wrong place
+                # in one of two 16-token tiles gave 2.5e-2 with the initialiser's near-uniform attention)
                 results.append(_stats('last-step logits vs oracle%s' % (' (sharp attention)' if sharp else ''),
-                                      last_logits.float().cpu(), torch.from_numpy(logits[:, -1].numpy()).float(), 3e-2))
+                                      last_logits.float().cpu(), torch.from_numpy(logits[:, -1].numpy()).float(), 8e-3))
             ids = np.concatenate([ids, out_s[:, step:step + 1]], axis=1)
     results.append({'name': 'sampled decode agreement %d/%d (+%d at CDF edges)' % (agree, total, near),
                     'rel': total - agree - near, 'tol': 0, 'nan': False, 'ok': agree + near == total})
