@@ -149,7 +149,7 @@ def check_gemm_wgrad(tokens=512, M=256, N=768, seed=11, ldm_pad=0):
               ptr(outf), N, 0.0, 0, 0, 0, 0, stream())
     torch.cuda.synchronize()
     ref = init + a[:, :M].float().t() @ b.float()
-    return _finish(_stats('gemm_wgrad tokens%d M%d N%d' % (tokens, M, N), outf, ref, 1e-2))
+    return _finish(_stats('gemm_wgrad tokens%d M%d N%d' % (tokens, M, N), outf, ref, 2e-5))      # fp32 accumulation of the same bf16 operands: measured <= 7e-7
 
 
 def check_logits_ce(M=300, V=390, E=256, seed=13):
@@ -170,10 +170,10 @@ def check_logits_ce(M=300, V=390, E=256, seed=13):
     ref_loss = torch.nn.functional.cross_entropy(z, labels.long(), reduction='sum')
     (ref_loss * scale).backward()
     ref_correct = int((z.argmax(dim=-1) == labels.long()).sum())
-    results = [_stats('ce logits', logits, z.detach(), 2e-3),
+    results = [_stats('ce logits', logits, z.detach(), 2e-5),      # fp32 out of TMEM: measured 6e-7
                _stats('ce dlogits', dlogits[:, :V], z.grad, 1e-2),
                _stats('ce dlogits pad', dlogits[:, V:], torch.zeros_like(dlogits[:, V:]), 0.0, scale=1.0),
-               _stats('ce loss', loss, ref_loss.detach().reshape(1), 1e-3)]
+               _stats('ce loss', loss, ref_loss.detach().reshape(1), 5e-6)]
     hits = int(correct.item())
     results.append({'name': 'ce correct', 'ok': abs(hits - ref_correct) <= 1, 'got': hits, 'ref': ref_correct,
                     'rel': 0.0, 'tol': 0.0, 'nan': False})
@@ -239,8 +239,8 @@ def check_layernorm(rows=301, E=256):
     torch.cuda.synchronize()
     ref.backward(dy_a.float() + dy_b.float())
     results.append(_stats('layernorm_bwd dx', dx, xf.grad + dres.float(), 1e-2))
-    results.append(_stats('layernorm_bwd dgamma', dgamma, gf.grad, 1e-2))
-    results.append(_stats('layernorm_bwd dbeta', dbeta, bf.grad, 1e-2))
+    results.append(_stats('layernorm_bwd dgamma', dgamma, gf.grad, 1e-5))     # fp32 column sums: measured 2e-7
+    results.append(_stats('layernorm_bwd dbeta', dbeta, bf.grad, 1e-5))
     return _finish(results)
 
 
@@ -254,7 +254,7 @@ def check_bias_grad(rows=1000, N=768, rate=0.1):
     if rate > 0:
         ref = ref * rowmajor_mask(rows, N, rate, 5, 1, 3, 2).float() / (1 - rate)
         torch.cuda.synchronize()
-    results = [_stats('bias_grad dbias', dbias, ref.sum(dim=0), 2e-3)]
+    results = [_stats('bias_grad dbias', dbias, ref.sum(dim=0), 1e-5)]       # measured <= 3e-7
     if rate > 0:
         results.append(_stats('bias_grad g_out', g_out, ref, 1e-2))
     return _finish(results)
@@ -454,8 +454,9 @@ def check_engine_forward_backward(B=2, T=100, layers=2, embedding=256, heads=16,
     got_logits = logits.cpu().double().numpy().reshape(B * T, -1)
     results.append(_stats('engine logits', torch.from_numpy(got_logits), torch.from_numpy(ref_logits.reshape(B * T, -1)), tol))
     got_loss = float(loss_sum) / (B * T)
+    # (the mean over all positions averages the bf16 noise of the logits away: measured <= 4e-5)
     results.append({'name': 'engine loss', 'got': got_loss, 'ref': ref_loss, 'rel': abs(got_loss - ref_loss) / abs(ref_loss),
-                    'tol': tol, 'nan': got_loss != got_loss, 'ok': abs(got_loss - ref_loss) <= tol * abs(ref_loss)})
+                    'tol': 5e-4, 'nan': got_loss != got_loss, 'ok': abs(got_loss - ref_loss) <= 5e-4 * abs(ref_loss)})
     got_acc = float(correct) / (B * T)
     results.append({'name': 'engine accuracy', 'got': got_acc, 'ref': ref_acc, 'rel': abs(got_acc - ref_acc), 'tol': 0.02,
                     'nan': False, 'ok': abs(got_acc - ref_acc) <= 0.02})
@@ -490,8 +491,8 @@ def check_engine_adam_step(B=2, T=64):
     torch.cuda.synchronize()
     results = []
     for i, (a, b) in enumerate(zip(losses_got, losses_ref)):
-        results.append({'name': 'adam trajectory loss[%d]' % i, 'got': a, 'ref': b, 'rel': abs(a - b) / abs(b), 'tol': 2e-2,
-                        'nan': a != a, 'ok': abs(a - b) <= 2e-2 * abs(b)})
+        results.append({'name': 'adam trajectory loss[%d]' % i, 'got': a, 'ref': b, 'rel': abs(a - b) / abs(b), 'tol': 5e-4,
+                        'nan': a != a, 'ok': abs(a - b) <= 5e-4 * abs(b)})      # measured <= 2.2e-5
     got = model.get_weights()
     worst = 0.0
     for name in params:
@@ -619,7 +620,7 @@ def _check_generate(B, prompt_len, length, embedding, heads, window=64, sharp=Fa
             near += int(((chosen != out_s[:, step]) & (edge < 5e-3)).sum())
             if step == length - 1:
                 # logits of the last step: every cached token of every layer has been read by then (measured 1-2e-3 of
-                # the largest logit in every variant, `tools/generate_margins.py`; a k|v row read from the wrong place
+                # the largest logit in every variant, `tools/parity_margins.py`; a k|v row read from the wrong place
                 # in one of two 16-token tiles gave 2.5e-2 with the initialiser's near-uniform attention)
                 results.append(_stats('last-step logits vs oracle%s' % (' (sharp attention)' if sharp else ''),
                                       last_logits.float().cpu(), torch.from_numpy(logits[:, -1].numpy()).float(), 8e-3))
