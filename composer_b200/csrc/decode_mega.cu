@@ -1011,7 +1011,11 @@ static MegaSmem mega_smem_layout(int E, int F, int V, int D, int CL, int nst, in
     s.nst = nst;
     s.nst_extra = nst_extra;
     s.zp = CL * s.vs;
-    s.zbuf = take(MG_ROWS * s.zp * 4);
+    // The logits matrix (CTA 0) shares the GELU buffer: c_fc writes that buffer and mlp c_proj reads it before the
+    // barrier in front of the logits phase, and the sampler has read the logits before the barrier that ends the
+    // step; every kilobyte not spent here is ring depth, which the attention phase is sensitive to.
+    if (MG_ROWS * s.zp * 4 <= MG_ROWS * s.pf) s.zbuf = s.bufg;
+    else s.zbuf = take(MG_ROWS * s.zp * 4);
     s.ring = take((MG_WARPS * nst + nst_extra) * MG_STAGE);
     s.bars = take((MG_WARPS * nst + nst_extra) * 8);
     s.toks = take(MG_ROWS * 4);
