@@ -149,3 +149,17 @@ def test_bucketed_allreduce_over_gloo_world_size_2():
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_gloo_worker, args=(2, port, results), nprocs=2, join=True)
     assert dict(results) == {0: True, 1: True}
+
+
+def test_tools_and_bench_compile():
+    '''The measurement scripts are not imported by any other test (most need a GPU, one needs TensorFlow): at
+    least their syntax is checked here, so that an edit cannot leave the driver's bench or a profiling recipe
+    unparsable.'''
+    import glob
+    import py_compile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    scripts = sorted(glob.glob(os.path.join(root, 'tools', '*.py'))) + [os.path.join(root, 'bench.py'),
+                                                                      os.path.join(root, '__graft_entry__.py')]
+    assert len(scripts) >= 10
+    for path in scripts:
+        py_compile.compile(path, doraise=True)
