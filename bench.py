@@ -426,13 +426,21 @@ def generation_benchmark(model, world, rank, device, dist):
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
-    start = time.perf_counter()
-    out = gen_model.generate(prompt, length, temperature=1.0, seed=7, sequence_index_base=rank * per_rank)
-    torch.cuda.synchronize()
-    seconds = torch.tensor([time.perf_counter() - start], device=device, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(seconds, op=dist.ReduceOp.MAX)
-    seconds = float(seconds)
+    # two timed generations (each: barrier, wall clock around the call, max over ranks); the faster one is reported
+    # and both are listed: a whole generation is one kernel launch, a single timing has nothing to average over
+    runs = []
+    for _ in range(2):
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        start = time.perf_counter()
+        out = gen_model.generate(prompt, length, temperature=1.0, seed=7, sequence_index_base=rank * per_rank)
+        torch.cuda.synchronize()
+        elapsed = torch.tensor([time.perf_counter() - start], device=device, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(elapsed, op=dist.ReduceOp.MAX)
+        runs.append(float(elapsed))
+    seconds = min(runs)
     E, L = MODEL['embedding_size'], MODEL['decoder_layers_count']
     weights = 2 * (gen_model.count_params() - 1024 * E + E)
     kv_read = sum(per_rank * 2 * L * E * 2 * t for t in range(length))
@@ -448,7 +456,8 @@ def generation_benchmark(model, world, rank, device, dist):
         if entry and 'prompt 1, 1,024 events' in entry.get('capture', ''):
             traffic = entry.get('dram_bytes_per_launch')
     return {'metric': 'generated events/s (256 sequences x 1024 events, temperature 1.0, KV-cache decode)',
-            'value': total * length / seconds, 'unit': 'events/s', 'seconds': seconds, 'sequences_per_gpu': per_rank,
+            'value': total * length / seconds, 'unit': 'events/s', 'seconds': seconds, 'seconds_of_each_run': runs,
+            'sequences_per_gpu': per_rank,
             'us_per_step': seconds / length * 1e6,
             'roofline': {'bound': 'hbm', 'achieved': bytes_per_gpu / seconds / 1e9, 'peak': peaks['hbm_gbs'],
                          'unit': 'GB/s', 'frac': bytes_per_gpu / seconds / 1e9 / peaks['hbm_gbs'], 'traffic': traffic,
