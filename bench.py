@@ -402,6 +402,8 @@ def decode_implementation(model, batch):
     size = 8 if cap8 > 0 and (batch <= cap8 * 8 or cap4 <= 0) else 4
     cap = cap8 if size == 8 else cap4
     clusters = min(batch, cap) if min(batch, cap) * 8 >= batch else -(-batch // 8)
+    share = -(-batch // clusters)          # the fewest clusters with the same largest share of sequences
+    clusters = -(-batch // share)
     return {'kernel': 'decode_mega_kernel (one persistent launch per generation)', 'cluster_size': size,
             'clusters': clusters, 'co_resident_clusters': cap, 'launches_per_generation': 3}
 

@@ -1081,7 +1081,11 @@ static int mega_cluster_count(int B, int resident, int max_clusters_hint) {
     if (max_clusters_hint > 0 && max_clusters_hint < resident) resident = max_clusters_hint;
     int ncl = B < resident ? B : resident;
     if (static_cast<long long>(ncl) * MG_ROWS < B) ncl = (B + MG_ROWS - 1) / MG_ROWS;
-    return ncl;
+    // the fewest clusters with the same largest share of sequences: a cluster's step time hardly depends on its
+    // share, the slowest cluster sets the time, and clusters that are not needed only add L2 traffic and the risk
+    // that the last one does not become resident with the others (it would then run after one of them has finished)
+    const int share = (B + ncl - 1) / ncl;
+    return (B + share - 1) / share;
 }
 
 template <int D, int CL>
