@@ -15,7 +15,7 @@ PACKAGE_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PACKAGE_DIR, 'csrc')
 BUILD_DIR = os.path.join(PACKAGE_DIR, 'build')
 LIBRARY = os.path.join(PACKAGE_DIR, 'libcomposer_b200.so')
-SOURCES = ['gemm.cu', 'elementwise.cu', 'attention.cu', 'attention_tc.cu', 'decode.cu', 'decode_mega.cu', 'engine.cu']
+SOURCES = ['gemm.cu', 'elementwise.cu', 'attention.cu', 'attention_fwd_tc.cu', 'attention_tc.cu', 'decode.cu', 'decode_mega.cu', 'engine.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']
 

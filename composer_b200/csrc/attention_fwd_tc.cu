@@ -1,0 +1,426 @@
+// Causal attention forward on the 5th-generation tensor cores (tcgen05 / TMEM), fed by TMA.
+//
+// Reference semantics (composer/models/transformer.py:331-371): S = q k^T, S *= rsqrt(d_h) (:345-348, before the
+// mask), causal mask S*b - 1e4*(1-b) (:351-354; the masked probabilities underflow to exactly 0 in fp32, so they
+// are skipped here), softmax (:360), dropout on the probabilities (:361), P v (:367); heads split / merged as
+// :373-395, i.e. head h owns columns [h*d_h, (h+1)*d_h) of the q | k | v thirds of c_attn's output.
+//
+// Persistent CTAs (two per SM) walk work items (one 128-row query tile of one (batch, head)), heaviest first:
+//   warp 5 (one lane)  TMA producer: Q tile, then the K / V tiles of the item through a ring (SWIZZLE = row bytes)
+//   warp 4 (one lane)  MMA issuer:   S = Q K^T  (tcgen05.mma, M 128 x N KT, fp32 in TMEM, double buffered), issued
+//                                    one tile ahead of the softmax;  O~ = P V  (M 128 x N d_h) once P is ready
+//   warps 0-3          softmax, thread = query row (TMEM lane): tcgen05.ld of the whole row, running max, exp2 with
+//                      the scale folded into one FFMA2, row sum, dropout, bf16 P written back INTO THE S BUFFER'S
+//                      COLUMNS with tcgen05.st and consumed from there as the A operand (TS form of tcgen05.mma),
+//                      so the probabilities never cross shared memory (PSMEM variant: swizzled smem tile, kept for
+//                      A/B).  O~ of a tile lands in spare columns of the same buffer and is folded into the thread's
+//                      fp32 output row one tile later (o = o*alpha + O~): with d_h <= 64 that is cheaper than
+//                      rescaling an accumulator in TMEM and needs no correction warps.
+// At d_h = 16 a 128 x 128 tile is ~130 tensor-pipe cycles against 1,024 MUFU cycles (16 ex2 / clk / SM), so the
+// budget is instructions per score element: packed fp32 pairs (FFMA2 / FADD2 / FMUL2), a 3-input max, and a dropout
+// stream of 1.5 instructions per element (common.cuh) keep the loop at ~5 per element, below the MUFU bound of 8.
+#include "attention.h"
+#include "gemm.h"
+
+#include <type_traits>
+
+namespace cb200 {
+
+constexpr int TCF_THREADS = 256;
+constexpr int TCF_SOFTMAX_REGS = 200, TCF_CONTROL_REGS = 56;   // 128 * (200 + 56) = half of the register file
+
+template <int D, bool PSMEM>
+struct TcfCfg {
+    static constexpr int KT = (D == 16) ? 128 : 64;        // keys per tile (the row of S a thread holds in registers)
+    static constexpr int RB = 2 * D;                        // bytes per row of a Q / K / V tile
+    static constexpr int QTILE = 128 * RB;
+    static constexpr int KTILE = KT * RB;
+    static constexpr int NKV = (D == 64) ? 3 : 4;           // K / V ring stages
+    static constexpr int PBYTES = (KT / 64) * 128 * 128;    // P in shared memory: 64-key halves of [128 rows][128 B]
+    static constexpr size_t SMEM = 2 * QTILE + NKV * 2 * KTILE + (PSMEM ? 2 * PBYTES : 0) + 256 + 1024;
+};
+
+__device__ __forceinline__ float fmax3f(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
+struct TcfCursor {
+    int item, it, qi, bh, j, n, g;   // it: ordinal of the item in this CTA; n: tiles of the item; g: tiles so far
+};
+
+template <int D, bool DROP, bool PSMEM>
+__global__ void __launch_bounds__(TCF_THREADS, 2)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
+                   __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int T, int H, int BH, int nq,
+                   float scale_log2, AttnDropKey drop) {
+    using C = TcfCfg<D, PSMEM>;
+    constexpr int KT = C::KT, RB = C::RB, QTILE = C::QTILE, KTILE = C::KTILE, NKV = C::NKV, NCH = KT / 32;
+    constexpr uint32_t LT = umma_layout_for_row_bytes(RB);
+    constexpr uint32_t COL_O = 64;                          // O~ inside a buffer (P occupies columns 0 .. KT/2 - 1)
+    static_assert(COL_O + D <= 128 && KT / 2 <= COL_O, "TMEM buffer layout");
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;                                     // [2][QTILE]
+    uint8_t* sK = sQ + 2 * QTILE;                           // [NKV][KTILE]
+    uint8_t* sV = sK + NKV * KTILE;                         // [NKV][KTILE]
+    uint8_t* sP = sV + NKV * KTILE;                         // [2][PBYTES] (PSMEM only)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + (PSMEM ? 2 * C::PBYTES : 0));
+    uint64_t* bar_q_full = bars;                            // [2] Q tile landed
+    uint64_t* bar_q_free = bars + 2;                        // [2] the item's last S MMA has read it
+    uint64_t* bar_kv_full = bars + 4;                       // [NKV]
+    uint64_t* bar_kv_free = bars + 4 + NKV;                 // [NKV] the tile's P V MMAs have read it
+    uint64_t* bar_s_full = bars + 4 + 2 * NKV;              // [2] S complete in TMEM
+    uint64_t* bar_p_full = bar_s_full + 2;                  // [2] P written by every softmax thread
+    uint64_t* bar_o_full = bar_s_full + 4;                  // [2] O~ complete in TMEM
+    uint64_t* bar_buf_free = bar_s_full + 6;                // [2] O~ read: the buffer may take S of tile g + 2
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_s_full + 8);
+
+    const int E = H * D;
+    const int items = nq * BH;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+
+    if (warp == 4 && lane == 0) {
+        tma_prefetch_desc(&tm_q);
+        tma_prefetch_desc(&tm_kv);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bar_q_full[i], 1);
+            mbar_init(&bar_q_free[i], 1);
+            mbar_init(&bar_s_full[i], 1);
+            mbar_init(&bar_p_full[i], 128);
+            mbar_init(&bar_o_full[i], 1);
+            mbar_init(&bar_buf_free[i], 128);
+        }
+        for (int i = 0; i < NKV; ++i) {
+            mbar_init(&bar_kv_full[i], 1);
+            mbar_init(&bar_kv_free[i], 1);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 6) tmem_alloc<256>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    auto setup = [&](TcfCursor& c) {
+        c.qi = nq - 1 - c.item / BH;                        // heaviest query tiles first
+        c.bh = c.item % BH;
+        c.n = (c.qi + 1) * (128 / KT);
+        c.j = 0;
+    };
+    auto advance = [&](TcfCursor& c) {
+        ++c.g;
+        if (++c.j == c.n) {
+            c.item += gridDim.x;
+            ++c.it;
+            if (c.item < items) setup(c);
+        }
+    };
+
+    if (warp >= 4) {
+        setmaxnreg_dec<TCF_CONTROL_REGS>();
+        if (warp == 5) {
+            // ===================== TMA producer =====================
+            if (elect_one()) {
+                TcfCursor c{static_cast<int>(blockIdx.x), 0, 0, 0, 0, 0, 0};
+                if (c.item < items) setup(c);
+                while (c.item < items) {
+                    const int b = c.bh / H, h = c.bh % H;
+                    const int row0 = b * T;
+                    if (c.j == 0) {
+                        const int qs = c.it & 1;
+                        mbar_wait(&bar_q_free[qs], ((c.it >> 1) & 1) ^ 1);
+                        mbar_expect_tx(&bar_q_full[qs], QTILE);
+                        tma_load_2d(sQ + qs * QTILE, &tm_q, &bar_q_full[qs], h * D, row0 + c.qi * 128);
+                    }
+                    const int st = c.g % NKV;
+                    mbar_wait(&bar_kv_free[st], ((c.g / NKV) & 1) ^ 1);
+                    mbar_expect_tx(&bar_kv_full[st], 2 * KTILE);
+                    tma_load_2d(sK + st * KTILE, &tm_kv, &bar_kv_full[st], E + h * D, row0 + c.j * KT);
+                    tma_load_2d(sV + st * KTILE, &tm_kv, &bar_kv_full[st], 2 * E + h * D, row0 + c.j * KT);
+                    advance(c);
+                }
+            }
+        } else if (warp == 4) {
+            // ===================== MMA issuer =====================
+            if (elect_one()) {
+                constexpr uint32_t IDESC_S = umma_idesc_bf16(128, KT, 0, 0);     // Q K^T
+                constexpr uint32_t IDESC_O = umma_idesc_bf16(128, D, 0, 1);      // P V (V is MN-major)
+                auto issue_s = [&](const TcfCursor& c) {
+                    const int qs = c.it & 1, st = c.g % NKV, buf = c.g & 1;
+                    if (c.j == 0) mbar_wait(&bar_q_full[qs], (c.it >> 1) & 1);
+                    mbar_wait(&bar_kv_full[st], (c.g / NKV) & 1);
+                    mbar_wait(&bar_buf_free[buf], ((c.g >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t aQ = smem_u32(sQ + qs * QTILE), aK = smem_u32(sK + st * KTILE);
+#pragma unroll
+                    for (int ks = 0; ks < D / 16; ++ks)
+                        umma_bf16(tmem + buf * 128, umma_smem_desc(aQ + ks * 32, 16, 8 * RB, LT),
+                                  umma_smem_desc(aK + ks * 32, 16, 8 * RB, LT), IDESC_S, ks > 0 ? 1u : 0u);
+                    umma_commit(&bar_s_full[buf]);
+                    if (c.j == c.n - 1) umma_commit(&bar_q_free[qs]);
+                };
+                auto issue_pv = [&](const TcfCursor& c) {
+                    const int st = c.g % NKV, buf = c.g & 1;
+                    mbar_wait(&bar_p_full[buf], (c.g >> 1) & 1);
+                    tc_fence_after();
+                    const uint32_t aV = smem_u32(sV + st * KTILE);
+#pragma unroll
+                    for (int ks = 0; ks < KT / 16; ++ks) {
+                        const uint64_t dv = umma_smem_desc(aV + ks * 16 * RB, KT * RB, 8 * RB, LT);
+                        if (PSMEM) {
+                            const uint32_t aP = smem_u32(sP + buf * C::PBYTES);
+                            umma_bf16(tmem + buf * 128 + COL_O,
+                                      umma_smem_desc(aP + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024, 2u), dv, IDESC_O,
+                                      ks > 0 ? 1u : 0u);
+                        } else {
+                            umma_bf16_ts(tmem + buf * 128 + COL_O, tmem + buf * 128 + ks * 8, dv, IDESC_O, ks > 0 ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(&bar_o_full[buf]);
+                    umma_commit(&bar_kv_free[st]);
+                };
+                TcfCursor cs{static_cast<int>(blockIdx.x), 0, 0, 0, 0, 0, 0};
+                if (cs.item < items) setup(cs);
+                TcfCursor cp = cs;
+                if (cs.item < items) {
+                    issue_s(cs);
+                    advance(cs);
+                }
+                while (cp.item < items) {
+                    if (cs.item < items) {
+                        issue_s(cs);                        // S runs one tile ahead of the softmax
+                        advance(cs);
+                    }
+                    issue_pv(cp);
+                    advance(cp);
+                }
+            }
+        }
+    } else {
+        // ===================== softmax warps: thread = query row =====================
+        setmaxnreg_inc<TCF_SOFTMAX_REGS>();
+        const int r = warp * 32 + lane;
+        const uint32_t t_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+        const float thr = __uint_as_float(drop.thr_bits);
+        const float ks_scale = DROP ? drop.keep_scale : 1.0f;
+        const uint64_t c2 = f2_pack(scale_log2, scale_log2);
+        int g = 0;
+        for (int item = blockIdx.x; item < items; item += gridDim.x) {
+            const int qi = nq - 1 - item / BH, bh = item % BH;
+            const int b = bh / H, h = bh % H;
+            const int n = (qi + 1) * (128 / KT);
+            const int row_g = qi * 128 + r;                 // query row inside the sequence
+            const int rmin = qi * 128 + warp * 32, rmax = rmin + 31;
+            const uint32_t dbase = DROP ? attn_drop_base(drop, bh) : 0u;
+            float o_acc[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) o_acc[d] = 0.f;
+            float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
+
+            auto fold_o = [&](int gp) {                     // o = o * alpha + O~ of tile gp, then release its buffer
+                const int pb = gp & 1;
+                mbar_wait(&bar_o_full[pb], (gp >> 1) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int d0 = 0; d0 < D; d0 += 16) {
+                    uint32_t op[16];
+                    tmem_ld16(t_lane + pb * 128 + COL_O + d0, op);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int d = 0; d < 16; ++d) o_acc[d0 + d] = fmaf(o_acc[d0 + d], alpha_prev, __uint_as_float(op[d]));
+                }
+                tc_fence_before();
+                mbar_arrive(&bar_buf_free[pb]);
+            };
+
+            for (int j = 0; j < n; ++j, ++g) {
+                const int buf = g & 1;
+                const uint32_t tbuf = t_lane + buf * 128;
+                mbar_wait(&bar_s_full[buf], (g >> 1) & 1);
+                tc_fence_after();
+                uint32_t s[KT];
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) tmem_ld32(tbuf + 32 * c, *reinterpret_cast<uint32_t(*)[32]>(&s[32 * c]));
+                if (j > 0) fold_o(g - 1);                   // (its tcgen05.wait::ld also covers the S loads above)
+                else tmem_ld_wait();
+
+                const int key0 = j * KT;
+                const bool diag = key0 + KT - 1 > qi * 128;  // some key of the tile lies above some row of the q tile
+                uint32_t x = 0;
+                if (DROP) {
+                    x = attn_row_seed(dbase, static_cast<uint32_t>(row_g), static_cast<uint32_t>(key0 >> 7));
+                    if (KT == 64 && (key0 & 64)) x *= mcg_mul_pow(32);
+                }
+                float alpha = 0.f;
+                uint64_t sum_a = f2_pack(0.f, 0.f), sum_b = sum_a;
+                // Two copies of the tile arithmetic: only tiles that touch the diagonal pay for the causal mask
+                // (32-key chunks wholly above the warp's rows are skipped, the straddling ones are masked per element).
+                auto tile_math = [&](auto masked) {
+                    constexpr bool MASKED = decltype(masked)::value;
+                    // ---- running max ----
+                    float mx0 = m_run, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) {
+                        const int kmin = key0 + 32 * c;
+                        if (MASKED && kmin > rmax) continue;
+                        if (MASKED && kmin + 31 > rmin) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                if (kmin + i > row_g) s[32 * c + i] = 0xff800000u;   // -inf
+                        }
+#pragma unroll
+                        for (int i = 0; i < 32; i += 8) {
+                            mx0 = fmax3f(mx0, __uint_as_float(s[32 * c + i]), __uint_as_float(s[32 * c + i + 1]));
+                            mx1 = fmax3f(mx1, __uint_as_float(s[32 * c + i + 2]), __uint_as_float(s[32 * c + i + 3]));
+                            mx2 = fmax3f(mx2, __uint_as_float(s[32 * c + i + 4]), __uint_as_float(s[32 * c + i + 5]));
+                            mx3 = fmax3f(mx3, __uint_as_float(s[32 * c + i + 6]), __uint_as_float(s[32 * c + i + 7]));
+                        }
+                    }
+                    const float m_new = fmaxf(fmax3f(mx0, mx1, mx2), mx3);
+                    alpha = fast_exp2((m_run - m_new) * scale_log2);   // first tile: exp2(-inf) = 0
+                    m_run = m_new;
+                    const float nmc = -m_new * scale_log2;
+                    const uint64_t n2 = f2_pack(nmc, nmc);
+                    // ---- P = exp2(S c - m c), row sum (before dropout), dropout, bf16 ----
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) {
+                        const int kmin = key0 + 32 * c;
+                        uint32_t pk[16];
+                        if (MASKED && kmin > rmax) {
+#pragma unroll
+                            for (int q = 0; q < 16; ++q) pk[q] = 0u;
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 16; ++q) {
+                                const uint64_t t2 = f2_fma(f2_pack(s[32 * c + 2 * q], s[32 * c + 2 * q + 1]), c2, n2);
+                                float t0, t1;
+                                f2_unpack(t2, t0, t1);
+                                float p0 = fast_exp2(t0), p1 = fast_exp2(t1);
+                                uint64_t p2 = f2_pack(p0, p1);
+                                if (q & 1) sum_b = f2_add(sum_b, p2);
+                                else       sum_a = f2_add(sum_a, p2);
+                                if (DROP) {
+                                    float m0, m1;
+                                    attn_drop_pair(x, thr, m0, m1);
+                                    p2 = f2_mul(p2, f2_pack(m0, m1));
+                                    f2_unpack(p2, p0, p1);
+                                }
+                                pk[q] = pack_bf16(p0, p1);
+                            }
+                        }
+                        if (PSMEM) {
+                            // row r of the 64-key half: 128 bytes, 16-byte pieces XOR-swizzled by (r & 7) (SWIZZLE_128B)
+                            const uint32_t base = smem_u32(sP) + buf * C::PBYTES + (c >> 1) * 16384 + r * 128;
+#pragma unroll
+                            for (int q4 = 0; q4 < 4; ++q4) {
+                                const uint32_t off = static_cast<uint32_t>((((c & 1) * 4 + q4) ^ (r & 7)) << 4);
+                                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + off), "r"(pk[4 * q4]),
+                                             "r"(pk[4 * q4 + 1]), "r"(pk[4 * q4 + 2]), "r"(pk[4 * q4 + 3]) : "memory");
+                            }
+                        } else {
+                            tmem_st16(tbuf + 16 * c, pk);
+                        }
+                    }
+                };
+                if (diag) tile_math(std::true_type{});
+                else      tile_math(std::false_type{});
+                float sa0, sa1, sb0, sb1;
+                f2_unpack(sum_a, sa0, sa1);
+                f2_unpack(sum_b, sb0, sb1);
+                l_run = fmaf(l_run, alpha, (sa0 + sa1) + (sb0 + sb1));
+                if (PSMEM) {
+                    fence_proxy_async_smem();
+                } else {
+                    tmem_st_wait();
+                    tc_fence_before();
+                }
+                mbar_arrive(&bar_p_full[buf]);
+                alpha_prev = alpha;
+            }
+            fold_o(g - 1);
+
+            // ---- finalize the row ----
+            if (row_g < T) {
+                const float inv = ks_scale / l_run;
+                __nv_bfloat16* dst = out + (static_cast<size_t>(b) * T + row_g) * E + h * D;
+#pragma unroll
+                for (int d0 = 0; d0 < D; d0 += 8) {
+                    uint4 v;
+                    v.x = pack_bf16(o_acc[d0] * inv, o_acc[d0 + 1] * inv);
+                    v.y = pack_bf16(o_acc[d0 + 2] * inv, o_acc[d0 + 3] * inv);
+                    v.z = pack_bf16(o_acc[d0 + 4] * inv, o_acc[d0 + 5] * inv);
+                    v.w = pack_bf16(o_acc[d0 + 6] * inv, o_acc[d0 + 7] * inv);
+                    *reinterpret_cast<uint4*>(dst + d0) = v;
+                }
+                if (lse != nullptr) lse[(static_cast<size_t>(b) * H + h) * T + row_g] = fmaf(m_run, scale_log2, log2f(l_run));
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 6) {
+        tc_fence_after();
+        tmem_dealloc<256>(tmem);
+    }
+}
+
+template <int D, bool DROP, bool PSMEM>
+static int launch_fwd_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse, int B, int T, int H, float scale,
+                         const AttnDropKey& key, cudaStream_t s) {
+    using C = TcfCfg<D, PSMEM>;
+    constexpr size_t smem = C::SMEM;
+    const int E = H * D;
+    CUtensorMap tm_q, tm_kv;
+    int rc = make_tmap_bf16_sw(&tm_q, qkv, 3 * E, static_cast<uint64_t>(B) * T, 3 * E, D, 128, C::RB);
+    if (rc) return rc;
+    rc = make_tmap_bf16_sw(&tm_kv, qkv, 3 * E, static_cast<uint64_t>(B) * T, 3 * E, D, C::KT, C::RB);
+    if (rc) return rc;
+    auto kernel = attn_fwd_tc_kernel<D, DROP, PSMEM>;
+    static bool configured = false;
+    if (!configured) {
+        CB200_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    const int nq = (T + 127) / 128;
+    const long long items = static_cast<long long>(nq) * B * H;
+    const int per_sm = (2 * smem + 4096 <= 232448) ? 2 : 1;
+    long long grid = static_cast<long long>(per_sm) * device_sm_count();
+    if (grid > items) grid = items;
+    kernel<<<static_cast<int>(grid), TCF_THREADS, smem, s>>>(tm_q, tm_kv, out, lse, T, H, B * H, nq,
+                                                              scale * 1.4426950408889634f, key);
+    CB200_CUDA_OK(cudaGetLastError());
+    note_launch(1);
+    return 0;
+}
+
+template <int D>
+static int launch_fwd_tc_d(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse, int B, int T, int H, float scale,
+                           const AttnDropKey& key, bool psmem, cudaStream_t s) {
+    const bool dropping = key.thr_bits != 0;
+    if (psmem)
+        return dropping ? launch_fwd_tc<D, true, true>(qkv, out, lse, B, T, H, scale, key, s)
+                        : launch_fwd_tc<D, false, true>(qkv, out, lse, B, T, H, scale, key, s);
+    return dropping ? launch_fwd_tc<D, true, false>(qkv, out, lse, B, T, H, scale, key, s)
+                    : launch_fwd_tc<D, false, false>(qkv, out, lse, B, T, H, scale, key, s);
+}
+
+// The tcgen05 forward.  psmem = false: P stays in TMEM (TS-form MMA); true: P goes through shared memory.
+int attention_fwd_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse, int B, int T, int H, int D, float scale,
+                     const AttnDropKey& key, bool psmem, cudaStream_t s) {
+    switch (D) {
+        case 16: return launch_fwd_tc_d<16>(qkv, out, lse, B, T, H, scale, key, psmem, s);
+        case 32: return launch_fwd_tc_d<32>(qkv, out, lse, B, T, H, scale, key, psmem, s);
+        case 64: return launch_fwd_tc_d<64>(qkv, out, lse, B, T, H, scale, key, psmem, s);
+        default: break;
+    }
+    set_error("attention head size %d is not supported (16, 32 or 64)", D);
+    return -1;
+}
+
+}  // namespace cb200

@@ -25,7 +25,7 @@ namespace cb200 {
 
 constexpr int TCB_SM_WARPS = 16;                       // softmax warps: 4 row bands x 4 column quarters
 constexpr int TCB_THREADS = (TCB_SM_WARPS + 2) * 32;   // + control warp + TMEM allocator warp
-constexpr int TCB_CPT = 128 / (TCB_SM_WARPS / 4);      // key columns per softmax thread (64)
+constexpr int TCB_CPT = 128 / (TCB_SM_WARPS / 4);      // key columns per softmax thread (32)
 constexpr int TCB_TILE = 128;                          // query rows per tile = keys per CTA
 
 template <int D>
@@ -187,14 +187,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         const float* glse = lse + (static_cast<size_t>(b) * H + h) * T;
         const float* gdelta = delta + (static_cast<size_t>(b) * H + h) * T;
         float* dqb = dq_acc + static_cast<size_t>(b) * T * E + h * D;
-        // dropout: this thread's row meets 4 lanes' streams (tig = 0..3) of the m16n8k16 ownership map
-        uint32_t stream_base = 0, mult4[4] = {1u, 1u, 1u, 1u};
-        const int g = r & 7, hi = (r >> 3) & 1;
-        if (DROP) {
-#pragma unroll
-            for (int tig = 0; tig < 4; ++tig) mult4[tig] = attn_lane_mult(drop, 4 * g + tig);
-            stream_base = attn_stream_base(drop, b * H + h, 0).base;
-        }
+        // dropout: the row's stream of this 128-key block (common.cuh); this thread starts at pair 16 * cq
+        const float thr = __uint_as_float(drop.thr_bits);
+        const uint32_t drop_base = DROP ? attn_drop_base(drop, b * H + h) : 0u;
+        const uint32_t drop_jump = (cq == 0) ? 1u : (cq == 1) ? mcg_mul_pow(16) : (cq == 2) ? mcg_mul_pow(32) : mcg_mul_pow(48);
+        const uint64_t sc2 = f2_pack(scale_log2, scale_log2);
         const float dq_scale = scale * ks_scale;
 
         auto drain_dq = [&](int t) {                  // tile t's dQ: every warp reduces a quarter of the head's columns
@@ -238,71 +235,67 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
             const bool diagonal = (it == 0);
             const uint32_t bp_a = smem_u32(sP) + (it % NBUF_P) * PBYTES;
             const uint32_t bs_a = smem_u32(sdS) + (it % NBUF_P) * PBYTES;
-            uint32_t xs[4] = {0, 0, 0, 0};
-            // 16 columns at a time keep the live register set small
+            uint32_t x = 0;
+            if (DROP) x = attn_row_seed(drop_base, static_cast<uint32_t>(row_g), static_cast<uint32_t>(kb)) * drop_jump;
+            const uint64_t nlse2 = f2_pack(-lse_r, -lse_r), ndl2 = f2_pack(-dl_r, -dl_r);
+            // The thread's 32 columns of S and dP are pulled out of TMEM at once and the columns are released
+            // immediately: the control thread issues S / dP of the next tile under this tile's arithmetic.
+            uint32_t sv_all[TCB_CPT], dv_all[TCB_CPT];
+            if (!(diagonal && cq > quad)) {                        // else: every key of the slice is above the band
+                tmem_ld32(t_lane + COL_S + cq * TCB_CPT, sv_all);
+                tmem_ld32(t_lane + COL_DP + cq * TCB_CPT, dv_all);
+                tmem_ld_wait();
+            }
+            tc_fence_before();
+            mbar_arrive(bar_sdp_free);
 #pragma unroll
             for (int ch = 0; ch < TCB_CPT / 16; ++ch) {
                 const int col0 = cq * TCB_CPT + ch * 16;           // first key column of this chunk (inside the tile)
-                const bool last = (ch == TCB_CPT / 16 - 1);
                 uint32_t pk[8], dk_[8];                            // packed bf16 pairs of P (dropped) and dS'
                 if (diagonal && col0 > quad * 32 + 31) {
-                    // every key of this chunk is above every row of this band
-                    if (last) {
-                        tc_fence_before();
-                        mbar_arrive(bar_sdp_free);
-                    }
+                    // every key of this chunk is above every row of this band (and so is every later chunk of the thread)
 #pragma unroll
                     for (int i = 0; i < 8; ++i) { pk[i] = 0u; dk_[i] = 0u; }
                 } else {
-                    uint32_t sv[16], dv_[16];
-                    tmem_ld16(t_lane + COL_S + col0, sv);
-                    tmem_ld16(t_lane + COL_DP + col0, dv_);
-                    tmem_ld_wait();
-                    if (last) {
-                        tc_fence_before();
-                        mbar_arrive(bar_sdp_free);                 // the next tile's S/dP may overwrite TMEM now
-                    }
+                    const uint32_t* sv = sv_all + 16 * ch;
+                    const uint32_t* dv_ = dv_all + 16 * ch;
                     const bool partial = diagonal && (col0 + 15 > quad * 32);
-                    if (DROP && (ch == 0 || (col0 & 63) == 0)) {
-                        // (re)seed at the thread's first chunk and at every new 64-key dropout block.  The stream is
-                        // parked two positions before element idx = 4*t + 2*hi (t = first 8-key group of the chunk),
-                        // so that every pair below advances by A^3 then A.
-                        // One hash per (16-row group, 64-key block), then this thread's four lane multipliers.
-                        const uint32_t park = ((col0 & 32) ? mcg_mul_pow(16) : 1u) * (hi ? 1u : mcg_inv_pow(2));
-                        const uint32_t hash = attn_block_hash(stream_base, static_cast<uint32_t>(row_g) >> 4,
-                                                              static_cast<uint32_t>((k0 + col0) >> 6)) * park;
+                    // two copies of the pair loop: only chunks that straddle the diagonal pay for the mask.
+                    // Per pair: FFMA2, 2 MUFU, [IMAD.WIDE, 2 FSET, FMUL2], FFMA2 / FADD2, FMUL2, 2 F2FP.
+                    auto pairs = [&](auto masked) {
 #pragma unroll
-                        for (int tig = 0; tig < 4; ++tig) xs[tig] = hash * mult4[tig];
-                    }
-                    // two copies of the element loop: only chunks that straddle the diagonal pay for the mask
-                    auto elements = [&](auto masked) {
-#pragma unroll
-                        for (int t2 = 0; t2 < 2; ++t2) {
-#pragma unroll
-                            for (int tig = 0; tig < 4; ++tig) {
-                                float pd[2], ds[2];
-#pragma unroll
-                                for (int e = 0; e < 2; ++e) {
-                                    const int c = 8 * t2 + 2 * tig + e;              // column inside this chunk
-                                    float pv = fast_exp2(fmaf(__uint_as_float(sv[c]), scale_log2, -lse_r));
-                                    if (decltype(masked)::value && (col0 + c > r)) pv = 0.f;
-                                    float dpv = __uint_as_float(dv_[c]);
-                                    pd[e] = pv;
-                                    if (DROP) {
-                                        xs[tig] *= (e == 0) ? mcg_mul_pow(3) : ATTN_MCG_A;
-                                        const bool dropped = xs[tig] < drop.threshold32;
-                                        dpv = dropped ? 0.f : dpv;
-                                        pd[e] = dropped ? 0.f : pd[e];
-                                    }
-                                    ds[e] = pv * (dpv - dl_r);
-                                }
-                                pk[4 * t2 + tig] = pack_bf16(pd[0], pd[1]);
-                                dk_[4 * t2 + tig] = pack_bf16(ds[0], ds[1]);
+                        for (int q = 0; q < 8; ++q) {
+                            const uint64_t t2 = f2_fma(f2_pack(sv[2 * q], sv[2 * q + 1]), sc2, nlse2);
+                            float t0, t1;
+                            f2_unpack(t2, t0, t1);
+                            float p0 = fast_exp2(t0), p1 = fast_exp2(t1);
+                            if (decltype(masked)::value) {
+                                if (col0 + 2 * q > r) p0 = 0.f;
+                                if (col0 + 2 * q + 1 > r) p1 = 0.f;
                             }
+                            const uint64_t p2 = f2_pack(p0, p1);
+                            const uint64_t dp2 = f2_pack(dv_[2 * q], dv_[2 * q + 1]);
+                            uint64_t u2, pm2;
+                            if (DROP) {
+                                float m0, m1;
+                                attn_drop_pair(x, thr, m0, m1);
+                                const uint64_t m2 = f2_pack(m0, m1);
+                                u2 = f2_fma(m2, dp2, ndl2);        // M.dP - delta/ks
+                                pm2 = f2_mul(p2, m2);
+                            } else {
+                                u2 = f2_add(dp2, ndl2);
+                                pm2 = p2;
+                            }
+                            const uint64_t ds2 = f2_mul(p2, u2);
+                            float a0, a1, b0, b1;
+                            f2_unpack(pm2, a0, a1);
+                            f2_unpack(ds2, b0, b1);
+                            pk[q] = pack_bf16(a0, a1);
+                            dk_[q] = pack_bf16(b0, b1);
                         }
                     };
-                    if (partial) elements(std::true_type{});
-                    else         elements(std::false_type{});
+                    if (partial) pairs(std::true_type{});
+                    else         pairs(std::false_type{});
                 }
                 if (ch == 0 && NBUF_P == 1 && it >= 1) mbar_wait(&bar_dq_full[(it - 1) & 1], ((it - 1) >> 1) & 1);   // single buffer: tile it-1's MMAs must be done
                 // two 16-byte chunks of this row per tensor; chunk index XOR (row & 7) = SWIZZLE_128B
@@ -391,7 +384,7 @@ static int launch_bwd_tc(const __nv_bfloat16* qkv, const __nv_bfloat16* dout, co
 int attention_bwd_tc_main(const __nv_bfloat16* qkv, const __nv_bfloat16* dout, const float* lse, const float* delta,
                           float* dq_acc, __nv_bfloat16* dqkv, int B, int T, int H, int D, float scale,
                           const AttnDropKey& key, cudaStream_t s) {
-    const bool dropping = key.threshold32 != 0;
+    const bool dropping = key.thr_bits != 0;
     switch (D) {
         case 16: return dropping ? launch_bwd_tc<16, true>(qkv, dout, lse, delta, dq_acc, dqkv, B, T, H, scale, key, s)
                                  : launch_bwd_tc<16, false>(qkv, dout, lse, delta, dq_acc, dqkv, B, T, H, scale, key, s);

@@ -158,19 +158,22 @@ __host__ __device__ __forceinline__ Philox4 drop_bits_rowmajor(const DropoutPara
     return philox4x32_10(row, col8, 0x0D0Du, site, p.seed_lo, drop_key1(p, site, layer));
 }
 
-// Attention-probability dropout.  The T x T keep mask is defined per 16 x 64 block (16 query rows
-// starting at 16*i16, 64 keys starting at 64*jb) of one (batch, head) pair `bh`.  In the m16n8k16
-// accumulator layout such a block is owned by 32 lanes; lane = 4*g + tig owns the 32 elements
-//     idx = 4*t + e,  t = 0..7, e = 0..3  ->  (row 16*i16 + g + 8*(e >> 1), key 64*jb + 8*t + 2*tig + (e & 1)).
-// Their keep decisions come from one multiplicative congruential stream modulo 2^32:
-//     x_0 = attn_stream_seed(...) (odd),  x_{n+1} = A x_n,  element idx is kept iff x_{idx+1} >= threshold32
-// (the comparison is dominated by the high bits, the good ones of a power-of-two MCG).  The seed is a
-// Philox-keyed bijective hash of the block coordinates: the key is drawn once per launch from
-// Philox4x32-10 of (seed, step, layer), so forward, backward and the mask export regenerate identical
-// masks at 3 instructions per element (IMAD, ISETP, FSEL) instead of a Philox call per 8 elements.
+// Attention-probability dropout.  The T x T keep mask of one (batch, head) pair `bh` is defined per
+// (query row i, block of 128 keys jb) by one multiplicative congruential stream modulo 2^32:
+//     x_0 = attn_row_seed(base(bh), i, jb) (odd),   x_{p+1} = lo32(A x_p),   p = 0 .. 63
+// and pair p decides keys 128 jb + 2p and 128 jb + 2p + 1 from the two halves of the 64-bit product A x_p:
+//     key 2p     is kept iff  float_bits(lo32(A x_p)) >= thr  or the comparison is unordered  (set.geu.f32)
+//     key 2p + 1 is kept iff  float_bits(hi32(A x_p)) >= thr  or unordered.
+// Reading the random words as fp32 makes the keep decision ONE instruction per element that already yields
+// the multiplier 1.0f / 0.0f (FSET.BF), and the 64-bit product is one IMAD.WIDE per pair: 1.5 instructions per
+// element, regenerated identically by forward, backward and the mask export.  Both words are dominated by the
+// high bits of the product, the good ones of a power-of-two MCG.  A thread that owns a contiguous, even-aligned
+// range of a row's keys starts at x_p = x_0 A^p (one multiply).  `thr` is a negative float chosen so that the
+// number of 32-bit patterns that compare >= thr (or are NaN) is (1 - rate) 2^32 (attn_drop_threshold_bits).
+// The base is drawn once per launch from Philox4x32-10 of (seed, step, layer).
 struct AttnDropKey {
     uint32_t k0, k1;
-    uint32_t threshold32;   // drop when x < threshold32 ; 0 = dropout off
+    uint32_t thr_bits;      // fp32 bit pattern of the threshold; 0 = dropout off
     float keep_scale;
 };
 
@@ -181,48 +184,39 @@ __host__ __device__ constexpr uint32_t mcg_mul_pow(int n) {
     for (int i = 0; i < n; ++i) a *= ATTN_MCG_A;
     return a;
 }
-// A^-n modulo 2^32 (A is odd, so it is invertible): Newton iteration x <- x (2 - a x).
-__host__ __device__ constexpr uint32_t mcg_inv_pow(int n) {
-    const uint32_t a = mcg_mul_pow(n);
-    uint32_t x = a;
-    for (int i = 0; i < 6; ++i) x *= 2u - a * x;
-    return x;
-}
 
 __host__ __device__ __forceinline__ uint32_t fmix32(uint32_t h) {
     h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
     return h;
 }
 
-// The stream of lane `lane` for block (i16, jb) of (batch * head) starts at
-//     seed = (fmix32(base ^ block coordinates) | 1) * mult(lane)          (odd times odd: odd, a valid MCG state)
-// with base hashed from (batch * head) and mult(lane) an odd multiplier hashed from the lane, both computed once
-// per thread.  One hash per block serves every lane's stream: the tcgen05 backward kernel, whose threads own a
-// query row and therefore meet four lanes' streams per block, pays one hash and four multiplies instead of four
-// hashes (which were 2.5 of its ~15 instructions per score element).
-struct AttnStream {
-    uint32_t base;   // per (batch * head)
-    uint32_t mult;   // per lane, odd
-};
-
-__host__ __device__ __forceinline__ uint32_t attn_lane_mult(const AttnDropKey& key, uint32_t lane) {
-    return fmix32(lane * 0x9E3779B9u + key.k1) | 1u;
+__host__ __device__ __forceinline__ uint32_t attn_drop_base(const AttnDropKey& key, uint32_t bh) {
+    return fmix32(bh ^ key.k0) + key.k1;
 }
 
-__host__ __device__ __forceinline__ AttnStream attn_stream_base(const AttnDropKey& key, uint32_t bh, uint32_t lane) {
-    AttnStream s;
-    s.base = fmix32(bh ^ key.k0) + key.k1;
-    s.mult = attn_lane_mult(key, lane);
-    return s;
+// (row < 2^17, jb < 2^10: injective for T <= 2^17); fmix32 is a bijection, so distinct (row, block) pairs get
+// distinct hashes; | 1 makes the state odd (a valid MCG state).
+__host__ __device__ __forceinline__ uint32_t attn_row_seed(uint32_t base, uint32_t row, uint32_t jb) {
+    return fmix32(base ^ ((row << 10) | jb)) | 1u;
 }
 
-// (i16 < 2^13, jb < 2^11: injective for T <= 2^17); fmix32 is a bijection, so distinct blocks get distinct hashes.
-__host__ __device__ __forceinline__ uint32_t attn_block_hash(uint32_t base, uint32_t i16, uint32_t jb) {
-    return fmix32(base ^ ((i16 << 11) | jb)) | 1u;
-}
-
-__host__ __device__ __forceinline__ uint32_t attn_stream_seed(const AttnStream& s, uint32_t i16, uint32_t jb) {
-    return attn_block_hash(s.base, i16, jb) * s.mult;
+// Threshold pattern for a drop rate: with K = round((1 - rate) 2^32) patterns to keep.  Negative threshold
+// -f(T): every non-negative pattern (2^31, NaNs included: unordered keeps), the 2^23 - 1 negative NaNs and the
+// negative patterns of magnitude <= T are kept, K = 2^31 + 2^23 + T.  Rates above ~0.498 need a positive one.
+__host__ __device__ __forceinline__ uint32_t attn_drop_threshold_bits(double rate) {
+    if (rate <= 0.0) return 0u;
+    const double keep = (1.0 - rate) * 4294967296.0;
+    const double edge = 2147483648.0 + 8388608.0;
+    if (keep >= edge) {
+        double t = keep - edge;
+        if (t < 8388608.0) t = 8388608.0;              // stay a normal number
+        if (t > 2139095039.0) t = 2139095039.0;        // below infinity
+        return 0x80000000u | static_cast<uint32_t>(t);
+    }
+    double t = edge - 1.0 - keep;                        // keep iff pattern >= +f(T):  K = 2^31 - T + 2^23 - 1
+    if (t < 8388608.0) t = 8388608.0;
+    if (t > 2139095040.0) t = 2139095040.0;
+    return static_cast<uint32_t>(t);
 }
 
 __host__ __device__ __forceinline__ AttnDropKey make_attn_drop_key(const DropoutParams& p, uint32_t layer) {
@@ -230,15 +224,54 @@ __host__ __device__ __forceinline__ AttnDropKey make_attn_drop_key(const Dropout
     const Philox4 r = philox4x32_10(layer, p.step, SITE_ATTN_W, 0x17u, p.seed_lo, p.seed_hi);
     k.k0 = r.x; k.k1 = r.y;
     if (p.threshold16 == 0) {
-        k.threshold32 = 0; k.keep_scale = 1.f;
+        k.thr_bits = 0; k.keep_scale = 1.f;
     } else {
-        double t = static_cast<double>(p.rate) * 4294967296.0;
-        if (t > 4294967295.0) t = 4294967295.0;
-        k.threshold32 = static_cast<uint32_t>(t);
+        k.thr_bits = attn_drop_threshold_bits(static_cast<double>(p.rate));
         k.keep_scale = p.keep_scale;
     }
     return k;
 }
+
+#ifdef __CUDACC__
+// One pair of keep multipliers (1.0f / 0.0f) and the stream advance.
+__device__ __forceinline__ void attn_drop_pair(uint32_t& x, float thr, float& m0, float& m1) {
+    uint32_t lo, hi;
+    asm("{\n\t.reg .b64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}" : "=r"(lo), "=r"(hi) : "r"(x), "r"(ATTN_MCG_A));
+    asm("set.geu.f32.f32 %0, %1, %2;" : "=f"(m0) : "f"(__uint_as_float(lo)), "f"(thr));
+    asm("set.geu.f32.f32 %0, %1, %2;" : "=f"(m1) : "f"(__uint_as_float(hi)), "f"(thr));
+    x = lo;
+}
+
+// ---- packed fp32 pairs (Blackwell: FFMA2 / FADD2 / FMUL2 do two lanes per issue slot) -------------------
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ uint64_t f2_pack(uint32_t lo, uint32_t hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+#endif
 
 __host__ __device__ __forceinline__ uint32_t drop_u16(const Philox4& r, int e) {
     uint32_t w = (e < 2) ? r.x : (e < 4) ? r.y : (e < 6) ? r.z : r.w;
@@ -397,6 +430,36 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4]) {
 }
 
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Registers -> TMEM: thread t of the warp writes TMEM lane (warp_quadrant*32 + t), columns [col, col+16).
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+          "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// D[tmem] (+)= A[tmem] * B[smem desc]: the A operand (M x 16 bf16, K-major) is read from TMEM, where row m
+// is lane m and two consecutive k share a 32-bit column (what a 32x32b tcgen05.st of packed pairs writes).
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// Register re-distribution between the warpgroups of a CTA (all four warps of the group execute it).
+template <int REGS>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS)); }
+template <int REGS>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS)); }
 
 // ---- UMMA descriptors (cf. PTX ISA "tcgen05 shared memory descriptor") -----
 // 64-bit shared-memory matrix descriptor for a SWIZZLE_128B operand tile.

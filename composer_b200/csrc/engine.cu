@@ -924,9 +924,10 @@ int cb200_set_decode_profile(void* counters) {
     return 0;
 }
 
-int cb200_set_attention_bwd_impl(int impl) {
-    CB200_REQUIRE(impl == 0 || impl == 1, "attention backward implementation must be 0 (tcgen05) or 1 (mma.sync)");
-    attention_set_bwd_impl(impl);
+int cb200_set_attention_fwd_impl(int impl) {
+    CB200_REQUIRE(impl >= 0 && impl <= 2,
+                  "attention forward implementation must be 0 (tcgen05, P in TMEM), 1 (mma.sync) or 2 (tcgen05, P in smem)");
+    attention_set_fwd_impl(impl);
     return 0;
 }
 

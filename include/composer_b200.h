@@ -151,9 +151,10 @@ int cb200_attention_fwd(const void* qkv, void* out, float* lse, int B, int T, in
 int cb200_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta,
                         float* dq_acc, void* dqkv, int B, int T, int H, int D, float scale, float dropout_rate,
                         uint64_t seed, uint32_t step, uint32_t layer, void* stream);
-/* Attention backward has two implementations of the same arithmetic: 0 = tcgen05 / TMEM (default),
- * 1 = warp-level mma.sync (kept for A/B measurements and as a cross-check in the tests). */
-int cb200_set_attention_bwd_impl(int impl);
+/* Attention forward has three implementations of the same arithmetic: 0 = tcgen05 / TMEM, probabilities kept in
+ * TMEM and consumed by a TS-form MMA (default); 1 = warp-level mma.sync (round 1; kept for A/B measurements and as
+ * a cross-check in the tests); 2 = tcgen05 / TMEM with the probabilities staged through shared memory. */
+int cb200_set_attention_fwd_impl(int impl);
 /* Selects how cb200_generate runs: 0 (default) = one persistent thread-block-cluster kernel for the whole
  * generation when the shape allows it (embedding_size 256 or 512, heads a multiple of 4), 1 = one CUDA graph
  * of per-layer kernels per step.  max_clusters > 0 caps the clusters of the persistent kernel (tests);

@@ -301,8 +301,16 @@ def _attention_reference(qkv, B, T, H, D, scale, keep=None, rate=0.0):
     return out
 
 
-def check_attention(B=2, T=200, H=16, D=16, rate=0.0, backward=True, bwd_impl=0):
-    _lib.call('cb200_set_attention_bwd_impl', bwd_impl)
+def check_attention(B=2, T=200, H=16, D=16, rate=0.0, backward=True, fwd_impl=0):
+    '''fwd_impl: 0 = tcgen05 with P in TMEM (default), 1 = round-1 mma.sync kernel, 2 = tcgen05 with P through smem.'''
+    _lib.call('cb200_set_attention_fwd_impl', fwd_impl)
+    try:
+        return _check_attention(B, T, H, D, rate, backward)
+    finally:
+        _lib.call('cb200_set_attention_fwd_impl', 0)
+
+
+def _check_attention(B, T, H, D, rate, backward):
     E = H * D
     scale = 1.0 / math.sqrt(D)
     qkv = _randn(B, T, 3 * E, scale=1.0, seed=61)
@@ -335,7 +343,6 @@ def check_attention(B=2, T=200, H=16, D=16, rate=0.0, backward=True, bwd_impl=0)
             results.append(_stats('attention_bwd %s' % nm, d[:, i * E:(i + 1) * E], g[:, i * E:(i + 1) * E], 3e-2))
         results.append(_stats('attention_bwd dq_acc rezeroed', dq_acc.reshape(B * T, E),
                               torch.zeros(B * T, E, device=DEV), 0.0, scale=1.0))
-        _lib.call('cb200_set_attention_bwd_impl', 0)
     return _finish(results)
 
 
@@ -398,14 +405,25 @@ GROUPS = {
     'attention_fwd': [lambda: check_attention(1, 64, 2, 16, backward=False),
                       lambda: check_attention(2, 200, 16, 16, backward=False),
                       lambda: check_attention(2, 256, 4, 64, backward=False),
-                      lambda: check_attention(2, 200, 16, 16, rate=0.1, backward=False)],
+                      lambda: check_attention(2, 200, 16, 16, rate=0.1, backward=False),
+                      lambda: check_attention(1, 130, 4, 32, rate=0.1, backward=False),
+                      # more work items than resident CTAs (persistent loop, Q / K / V rings wrap, both S buffers)
+                      lambda: check_attention(6, 1024, 16, 16, rate=0.1, backward=False),
+                      lambda: check_attention(2, 640, 16, 64, rate=0.1, backward=False),
+                      # the other two forward implementations: P staged through shared memory, round-1 mma.sync kernel
+                      lambda: check_attention(2, 200, 16, 16, rate=0.1, backward=False, fwd_impl=2),
+                      lambda: check_attention(6, 1024, 16, 16, backward=False, fwd_impl=2),
+                      lambda: check_attention(2, 384, 4, 64, rate=0.1, backward=False, fwd_impl=2),
+                      lambda: check_attention(1, 192, 4, 32, rate=0.1, backward=False, fwd_impl=2),
+                      lambda: check_attention(2, 200, 16, 16, rate=0.1, backward=False, fwd_impl=1),
+                      lambda: check_attention(2, 256, 4, 64, rate=0.1, backward=False, fwd_impl=1),
+                      lambda: check_attention(1, 192, 4, 32, rate=0.1, backward=False, fwd_impl=1)],
     'attention_bwd': [lambda: check_attention(1, 64, 2, 16), lambda: check_attention(2, 200, 16, 16),
                       lambda: check_attention(1, 256, 4, 64), lambda: check_attention(1, 192, 4, 32),
                       lambda: check_attention(2, 200, 16, 16, rate=0.1),
                       lambda: check_attention(1, 4096, 2, 16, rate=0.1), lambda: check_attention(1, 1000, 2, 64, rate=0.1),
                       lambda: check_attention(3, 130, 4, 32, rate=0.1), lambda: check_attention(2, 16, 4, 16),
-                      lambda: check_attention(2, 200, 16, 16, rate=0.1, bwd_impl=1),
-                      lambda: check_attention(1, 256, 4, 64, bwd_impl=1), lambda: check_attention(1, 192, 4, 32, rate=0.1, bwd_impl=1)],
+                      lambda: check_attention(1, 2048, 4, 16, rate=0.1)],
     'decode_linear': [check_decode_linear, lambda: check_decode_linear(256, 1024, 256, 1),
                       lambda: check_decode_linear(130, 256, 1024, 2), lambda: check_decode_linear(1, 256, 256, 2),
                       lambda: check_decode_linear(32, 3072, 1024, 0)],
