@@ -184,6 +184,17 @@ def _distributed_context():
     return rank, world_size, local_rank
 
 
+def _agreed_seed(ctx):
+    '''The run's seed, identical on every rank (rank 0's: without --seed each process draws its own from the clock).'''
+
+    from composer_b200 import parallel
+    seed = parallel.agree_on_seed((ctx.obj or {}).get('seed', 0))
+    if ctx.obj is not None:
+        ctx.obj['seed'] = seed
+    np.random.seed(seed % (2 ** 32))
+    return seed
+
+
 def get_dataset(model_type, dataset_path, config, mode='', use_generator=True, max_files=None,
                 show_progress_bar=True, shuffle_files=True, shuffle_dataset=True, seed=0, rank=0, world_size=1):
     '''
@@ -278,8 +289,8 @@ def train(ctx, model_type, dataset_path, logdir, restoredir, config_filepath, ep
 
     '''
 
-    seed = (ctx.obj or {}).get('seed', 0)
     rank, world_size, local_rank = _distributed_context()
+    seed = _agreed_seed(ctx)
     if restoredir is not None:
         config = get_config_from_restoredir(restoredir)
         model_logdir = None
@@ -376,8 +387,8 @@ def generate(ctx, model_type, restoredir, output_filepath, prompt, prompt_length
 
     '''
 
-    seed = (ctx.obj or {}).get('seed', 0)
     rank, world_size, _ = _distributed_context()
+    seed = _agreed_seed(ctx)
     config = get_config_from_restoredir(restoredir)
     model, _ = create_model(model_type, config, seed=seed)
     model.load_from_checkpoint(restoredir)

@@ -374,8 +374,9 @@ static int backward_layer(Engine& e, int l, cudaStream_t s) {
 
     // ---- MLP ----
     // g = dropout_bwd(d x3); d b_proj2 += colsum(g): done by the kernel that produced d x3 (ln_f backward for the last
-    // block, ln_1 backward of the block above otherwise) unless the model runs without LayerNorm
-    if (!ln && (rc = bias_grad(e.bufP, e.bufG, G + o.proj2_b, M, E, e.drop_res, SITE_MLP, layer, s))) return rc;
+    // block, ln_1 backward of the block above otherwise).  Without LayerNorm in the blocks only the last block is
+    // served that way (ln_f is unconditional, transformer.py:811); the others get their own pass here.
+    if (!ln && l != e.L - 1 && (rc = bias_grad(e.bufP, e.bufG, G + o.proj2_b, M, E, e.drop_res, SITE_MLP, layer, s))) return rc;
     const bf16* g_mlp = dropping ? e.bufG : e.bufP;
     {   // du = (g W2^T) * gelu'(u)
         GemmDesc d = gemm_desc(GEMM_MUL_DGELU, M, F, E, g_mlp, E, S + o.proj2_w, E);

@@ -121,6 +121,17 @@ def prefetch_pinned(dataset, depth=2):
         def __iter__(self):
             slots = queue.Queue(maxsize=depth)
             end = object()
+            stop = threading.Event()
+
+            def put(item):
+                # never blocks for good: the consumer may have stopped (max_steps, an exception) and left
+                while not stop.is_set():
+                    try:
+                        slots.put(item, timeout=0.1)
+                        return True
+                    except queue.Full:
+                        continue
+                return False
 
             def produce():
                 try:
@@ -128,16 +139,24 @@ def prefetch_pinned(dataset, depth=2):
                         pair = (torch.from_numpy(np.ascontiguousarray(x)), torch.from_numpy(np.ascontiguousarray(y)))
                         if torch.cuda.is_available():
                             pair = (pair[0].pin_memory(), pair[1].pin_memory())
-                        slots.put(pair)
-                finally:
-                    slots.put(end)
+                        if not put(pair):
+                            return
+                    put(end)
+                except BaseException as error:   # a bad file, pinned-memory exhaustion: surfaces in the consumer
+                    put(error)
 
-            threading.Thread(target=produce, daemon=True).start()
-            while True:
-                item = slots.get()
-                if item is end:
-                    return
-                yield item
+            thread = threading.Thread(target=produce, daemon=True)
+            thread.start()
+            try:
+                while True:
+                    item = slots.get()
+                    if item is end:
+                        return
+                    if isinstance(item, BaseException):
+                        raise item
+                    yield item
+            finally:
+                stop.set()
 
     return _Prefetcher()
 

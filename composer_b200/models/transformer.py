@@ -293,13 +293,38 @@ class Transformer(BaseModel):
         self._loss_dev.zero_()
         self._correct_dev.zero_()
         with torch.cuda.device(self.device):
+            # dropout masks differ between data-parallel ranks (everything else keyed by the seed does not)
             _lib.call('cb200_forward', self._engine, _ptr(ids), _ptr(labels), batch, sequence, int(training),
-                      self.seed, step, 1.0 / (batch * sequence), _ptr(self._loss_dev), _ptr(self._correct_dev),
-                      _ptr(logits), _stream())
+                      parallel.rank_dropout_seed(self.seed, self._rank()), step, 1.0 / (batch * sequence),
+                      _ptr(self._loss_dev), _ptr(self._correct_dev), _ptr(logits), _stream())
         self._last_ids = (ids, labels)   # keep the device buffers alive until backward has run
         if return_logits:
             return self._loss_dev, self._correct_dev, logits
         return self._loss_dev, self._correct_dev
+
+    def _rank(self):
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            return torch.distributed.get_rank(self.process_group)
+        return 0
+
+    def sync_replicas(self):
+        '''
+        Data-parallel replicas start from rank 0's variables and optimizer state (a restore or a seed that
+        differs between ranks would otherwise leave them apart for good: only gradients are exchanged).
+        '''
+
+        if not (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            return
+        if torch.distributed.get_world_size(self.process_group) == 1:
+            return
+        torch.distributed.broadcast(self._params, src=0, group=self.process_group)
+        if self._adam_m is not None:
+            torch.distributed.broadcast(self._adam_m, src=0, group=self.process_group)
+            torch.distributed.broadcast(self._adam_v, src=0, group=self.process_group)
+        counters = torch.tensor([self._adam_t, self._global_step, self._epoch], dtype=torch.int64, device=self.device)
+        torch.distributed.broadcast(counters, src=0, group=self.process_group)
+        self._adam_t, self._global_step, self._epoch = (int(v) for v in counters.tolist())
+        self._refresh_shadows()
 
     def _gradient_buckets(self):
         return parallel.gradient_buckets(self._layout, self.decoder_layers_count)
@@ -389,25 +414,55 @@ class Transformer(BaseModel):
         '''
         Autoregressively samples ``length`` new event ids after ``prompt_ids``
         ([batch, prompt_length], every row the same length) with a KV cache.
-        ``temperature <= 0`` selects argmax.  Raises when
-        ``prompt_length + length - 1 > window_size`` (the positional table has
-        ``window_size`` rows, transformer.py:675-679; TF-CPU raises as well).
-        Returns an int32 CUDA tensor [batch, length].
+        ``temperature <= 0`` selects argmax.  Returns an int32 CUDA tensor [batch, length].
+
+        The positional table has ``window_size`` rows (transformer.py:675-679), so one cached pass covers
+        ``prompt_length + length - 1 <= window_size`` positions.  The reference's loop never runs out of
+        positions because it feeds every token back at position 0 without any context (cli.py:663-676), and its
+        default invocation (prompt 10, length 1024, window 1024) must keep working: a longer request is served
+        in windows, each one re-primed with the last ``window_size // 2`` tokens at positions 0.. (the usual
+        sliding-window continuation).  The diagnostics outputs are only defined for a single window.
         '''
 
         prompt = self._as_ids(prompt_ids)
         batch, prompt_length = prompt.shape
+        seed = self.seed if seed is None else int(seed)
+        if prompt_length > self.window_size:
+            raise ValueError('the prompt has %d tokens but position embeddings exist only for window_size = %d'
+                             % (prompt_length, self.window_size))
+        if prompt_length - 1 + length <= self.window_size:
+            return self._generate_window(prompt, length, temperature, seed, sequence_index_base, return_uniforms,
+                                         return_last_logits)
+        if return_uniforms or return_last_logits:
+            raise ValueError('prompt_length + length - 1 = %d exceeds window_size = %d: uniforms / logits are only '
+                             'returned for a generation that fits one window'
+                             % (prompt_length - 1 + length, self.window_size))
+        logging.warning('Generating %d events after a %d-event prompt needs more than window_size = %d positions: '
+                        'continuing in windows re-primed with the last %d events.'
+                        % (length, prompt_length, self.window_size, max(1, self.window_size // 2)))
+        pieces, context, remaining, window = [], prompt, length, 0
+        while remaining > 0:
+            count = min(remaining, self.window_size - context.shape[1] + 1)
+            ids = self._generate_window(context, count, temperature, seed + window, sequence_index_base, False, False)
+            pieces.append(ids)
+            remaining -= count
+            context = torch.cat([context, ids], dim=1)[:, -max(1, self.window_size // 2):].contiguous()
+            window += 1
+        return torch.cat(pieces, dim=1)
+
+    def _generate_window(self, prompt, length, temperature, seed, sequence_index_base, return_uniforms,
+                         return_last_logits):
+        '''One cached pass of ``cb200_generate``: prompt_length + length - 1 <= window_size positions.'''
+
+        batch, prompt_length = prompt.shape
         steps = prompt_length - 1 + length
-        if steps > self.window_size:
-            raise ValueError('prompt_length + length - 1 = %d exceeds window_size = %d: position embeddings exist '
-                             'only for window_size positions' % (steps, self.window_size))
         if self._bound is None:
             self._bind(1, min(self.window_size, 64), training=False)
-        seed = self.seed if seed is None else int(seed)
         with torch.cuda.device(self.device):
             t_max = (steps + 63) // 64 * 64
             key = (batch, t_max)
             if self._decode_state is None or self._decode_state[0] != key:
+                self._decode_state = None
                 cache = torch.empty(_lib.call('cb200_kv_cache_elems', self._engine, batch, t_max),
                                     dtype=torch.bfloat16, device=self.device)
                 need = _lib.call('cb200_decode_workspace_bytes', self._engine, batch)
@@ -419,8 +474,8 @@ class Transformer(BaseModel):
             last = torch.empty((batch, self.vocab_size), dtype=torch.float32, device=self.device) \
                 if return_last_logits else None
             _lib.call('cb200_generate', self._engine, _ptr(cache), t_max, _ptr(workspace), workspace.numel(),
-                      _ptr(prompt), batch, prompt_length, length, float(temperature), seed, int(sequence_index_base),
-                      _ptr(out), _ptr(uniforms), _ptr(last), _stream())
+                      _ptr(prompt), batch, prompt_length, length, float(temperature), seed % (1 << 64),
+                      int(sequence_index_base), _ptr(out), _ptr(uniforms), _ptr(last), _stream())
         extras = [t for t in (uniforms, last) if t is not None]
         return (out, *extras) if extras else out
 
@@ -506,9 +561,10 @@ class Transformer(BaseModel):
         ``save_frequency`` steps or epochs.  Like the reference, ``epochs=N``
         stops when the 1-based epoch counter reaches N (transformer.py:890, 907).
 
-        Differences, all host-side: metrics are read back every ``log_every``
-        steps (the reference formats them every step, a device sync), and
-        ``max_steps`` (extension) bounds the run for benchmarks and tests.
+        Differences, all host-side: the per-step scalars are read back every
+        ``log_every`` steps in one copy (the reference formats them every step,
+        a device sync per step; every step is still written), and ``max_steps``
+        (extension) bounds the run for benchmarks and tests.
         '''
 
         from tqdm import tqdm
@@ -518,13 +574,18 @@ class Transformer(BaseModel):
         if restoredir is not None:
             try:
                 path = self.latest_checkpoint(logdir)
-                self._restore(path, with_optimizer=True)
-                logging.info('Model restored from \'{}\'.'.format(path))
+                if path is None:
+                    # tf.train.Checkpoint.restore(None) is a no-op (transformer.py:896-897): start from scratch
+                    logging.info('No checkpoint in \'{}\'; initializing from scratch.'.format(logdir))
+                else:
+                    self._restore(path, with_optimizer=True)
+                    logging.info('Model restored from \'{}\'.'.format(path))
             except Exception:
                 logging.error('Failed to restore model from \'{}\'.'.format(restoredir))
                 raise SystemExit(1)
 
         rank = torch.distributed.get_rank() if torch.distributed.is_initialized() else 0
+        self.sync_replicas()
         writer = None
         if rank == 0:
             try:
@@ -537,6 +598,26 @@ class Transformer(BaseModel):
         steps_per_epoch = None
         steps_done = 0
         history = []
+        # Per-step scalars are written for EVERY step like the reference (transformer.py:933-936), but read back
+        # in one device->host copy every ``log_every`` steps from a small ring on the device.
+        ring = torch.zeros((max(1, log_every), 2), dtype=torch.float32, device=self.device)
+        ring_steps = []
+
+        def flush_ring(progress_bar=None):
+            if not ring_steps:
+                return
+            values = ring[:len(ring_steps)].cpu().numpy()          # host sync, every log_every steps
+            for (step_number, tokens), (loss_sum_value, correct_value) in zip(ring_steps, values):
+                loss_value, accuracy = float(loss_sum_value) / tokens, float(correct_value) / tokens
+                history.append((step_number, loss_value, accuracy))
+                if writer is not None:
+                    writer.add_scalar('loss', loss_value, step_number)
+                    writer.add_scalar('accuracy', accuracy, step_number)
+            if progress_bar is not None:
+                progress_bar.set_description('- loss: {:.4f} - accuracy: {:.4f}'.format(history[-1][1], history[-1][2]))
+            ring_steps.clear()
+
+        stopped_early = False
         while epochs is None or self._epoch < epochs:
             current_epoch = self._epoch
             logging.info('Epoch {}'.format(current_epoch if epochs is None else '{}/{}'.format(current_epoch, epochs)))
@@ -553,14 +634,12 @@ class Transformer(BaseModel):
                     epoch_tokens += tokens
                     epoch_batches += 1
                     global_step = self._global_step
-                    if global_step % log_every == 0 or log_every == 1:
-                        loss_value = float(loss_sum) / tokens          # host sync, every log_every steps
-                        accuracy = float(correct) / tokens
-                        history.append((global_step, loss_value, accuracy))
-                        if writer is not None:
-                            writer.add_scalar('loss', loss_value, global_step)
-                            writer.add_scalar('accuracy', accuracy, global_step)
-                        progress_bar.set_description('- loss: {:.4f} - accuracy: {:.4f}'.format(loss_value, accuracy))
+                    slot = len(ring_steps)
+                    ring[slot, 0] = loss_sum[0]
+                    ring[slot, 1] = correct[0].float()
+                    ring_steps.append((global_step, tokens))
+                    if len(ring_steps) == ring.shape[0]:
+                        flush_ring(progress_bar)
                     if save_frequency_mode == ModelSaveFrequencyMode.GLOBAL_STEP and \
                             global_step % save_frequency == 0 and rank == 0:
                         save_path = self.save_checkpoint(logdir, max_checkpoints)
@@ -569,8 +648,14 @@ class Transformer(BaseModel):
                     steps_done += 1
                     progress_bar.update(1)
                     if max_steps is not None and steps_done >= max_steps:
+                        stopped_early = True
                         break
 
+                flush_ring(progress_bar)
+                if stopped_early:
+                    # a bounded run (max_steps) ends inside an epoch: no epoch summaries, no epoch checkpoint, and
+                    # the epoch counter stays, so that a resumed run does not skip the rest of this epoch
+                    break
                 if epoch_batches and writer is not None:
                     writer.add_scalar('epoch_loss', float(epoch_loss) / epoch_batches, current_epoch)
                     writer.add_scalar('epoch_accuracy', float(epoch_correct) / max(epoch_tokens, 1), current_epoch)
@@ -581,7 +666,7 @@ class Transformer(BaseModel):
                 if steps_per_epoch is None:
                     steps_per_epoch = progress_bar.n
                 self._epoch += 1
-            if max_steps is not None and steps_done >= max_steps:
+            if stopped_early:
                 break
             if epoch_batches == 0:
                 logging.warning('The dataset yielded no batches; stopping.')

@@ -58,3 +58,25 @@ def shard_range(total, world_size, rank):
     base, extra = divmod(total, world_size)
     start = rank * base + min(rank, extra)
     return start, start + base + (1 if rank < extra else 0)
+
+
+def agree_on_seed(seed, group=None):
+    '''
+    Every rank adopts rank 0's seed.  Without ``--seed`` each process derives its own seed from the clock
+    (composer/cli.py:51-57), and that seed drives the initial weights, the file shuffle and the window order:
+    replicas that disagree on it never train one model.  No-op for a single process.
+    '''
+
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return int(seed)
+    holder = [int(seed)]
+    dist.broadcast_object_list(holder, src=0, group=group)
+    return int(holder[0])
+
+
+def rank_dropout_seed(seed, rank):
+    '''The dropout key of a data-parallel rank: masks must differ between ranks, everything else must not.'''
+
+    return (int(seed) + 0x9E3779B97F4A7C15 * int(rank)) % (1 << 64)

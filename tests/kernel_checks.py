@@ -436,13 +436,14 @@ GROUPS = {
 # Whole model against the CPU oracle (oracle/transformer_oracle.py)
 # ---------------------------------------------------------------------------
 
-def _small_model(layers=2, embedding=256, heads=16, window=128, vocab=390, dropout=0.0, seed=3):
+def _small_model(layers=2, embedding=256, heads=16, window=128, vocab=390, dropout=0.0, seed=3, layer_norm=True):
     from composer_b200.models.transformer import Transformer
     from oracle import transformer_oracle as oracle
 
     cfg = oracle.OracleConfig(vocab_size=vocab, embedding_size=embedding, window_size=window,
                               decoder_layers_count=layers, attention_head_count=heads,
-                              attention_dropout_rate=dropout, residual_dropout_rate=dropout)
+                              attention_dropout_rate=dropout, residual_dropout_rate=dropout,
+                              use_layer_normalization=layer_norm)
     weights = oracle.init_parameters(cfg, seed=seed)
     # make biases / LayerNorm parameters non-trivial so that their gradients and uses are exercised
     rng = __import__('numpy').random.default_rng(seed + 1)
@@ -451,23 +452,25 @@ def _small_model(layers=2, embedding=256, heads=16, window=128, vocab=390, dropo
             weights[name] = (0.02 * rng.standard_normal(weights[name].shape)).astype('float32')
         elif name.endswith('/gamma'):
             weights[name] = (1.0 + 0.05 * rng.standard_normal(weights[name].shape)).astype('float32')
-    model = Transformer(vocab, embedding, window, layers, heads, False, 0.0, 0.02, dropout, dropout, 1e-5, True, True)
+    model = Transformer(vocab, embedding, window, layers, heads, False, 0.0, 0.02, dropout, dropout, 1e-5, True, layer_norm)
     model.set_weights(weights)
     return model, cfg, weights
 
 
-def check_engine_forward_backward(B=2, T=100, layers=2, embedding=256, heads=16, tol=2e-2):
+def check_engine_forward_backward(B=2, T=100, layers=2, embedding=256, heads=16, tol=2e-2, layer_norm=True,
+                                  oracle_dtype=None):
     import numpy as np
     from oracle import transformer_oracle as oracle
 
-    model, cfg, weights = _small_model(layers, embedding, heads, window=max(T, 128))
+    model, cfg, weights = _small_model(layers, embedding, heads, window=max(T, 128), layer_norm=layer_norm)
     rng = np.random.default_rng(11)
     draw = rng.integers(0, cfg.vocab_size, size=(B, T + 1))
     x, y = draw[:, :-1], draw[:, 1:]
     loss_sum, correct, logits = model.forward_loss(x, y, training=True, return_logits=True)
     model.backward()
     torch.cuda.synchronize()
-    ref_loss, ref_acc, ref_logits, ref_grads = oracle.loss_and_gradients(weights, x, y, cfg, dtype=torch.float64)
+    ref_loss, ref_acc, ref_logits, ref_grads = oracle.loss_and_gradients(weights, x, y, cfg,
+                                                                          dtype=oracle_dtype or torch.float64)
     results = []
     got_logits = logits.cpu().double().numpy().reshape(B * T, -1)
     results.append(_stats('engine logits', torch.from_numpy(got_logits), torch.from_numpy(ref_logits.reshape(B * T, -1)), tol))
@@ -682,3 +685,99 @@ GROUPS['generate'] = [check_generate, lambda: check_generate(impl=1),
                       lambda: check_generate(B=3, prompt_len=20, length=40, embedding=1024, heads=16, sharp=True),
                       check_generate_impls_agree,
                       lambda: check_generate_impls_agree(B=33, embedding=512, heads=16)]
+
+
+# ---------------------------------------------------------------------------
+# BASELINE.json configurations at their stated shapes
+# ---------------------------------------------------------------------------
+
+def check_config0_forward_loss(B=4, T=1024, layers=8, embedding=256, heads=16):
+    '''configs[0] exactly: default_config.yml hyperparameters (8 blocks, d_model 256, 16 heads, window 1024),
+    forward + loss on a batch of 4 sequences; logits <= 2e-2 of the largest logit, loss <= 5e-4 relative.'''
+    import numpy as np
+    from oracle import transformer_oracle as oracle
+
+    model, cfg, weights = _small_model(layers, embedding, heads, window=T)
+    rng = np.random.default_rng(101)
+    draw = rng.integers(0, cfg.vocab_size, size=(B, T + 1))
+    x, y = draw[:, :-1], draw[:, 1:]
+    loss_sum, correct, logits = model.forward_loss(x, y, training=False, return_logits=True)
+    torch.cuda.synchronize()
+    params = oracle.to_torch(weights, torch.float64)
+    with torch.no_grad():
+        ref_logits, _ = oracle.transformer_call(params, x, cfg)
+        ref_loss = float(oracle.sparse_categorical_crossentropy(y, ref_logits))
+        ref_acc = float(oracle.batch_accuracy(y, ref_logits))
+    got_loss = float(loss_sum) / (B * T)
+    results = [_stats('configs[0] logits (L%d E%d H%d T%d B%d)' % (layers, embedding, heads, T, B),
+                      logits.double().cpu().reshape(B * T, -1), ref_logits.reshape(B * T, -1), 2e-2),
+               {'name': 'configs[0] loss', 'got': got_loss, 'ref': ref_loss, 'rel': abs(got_loss - ref_loss) / abs(ref_loss),
+                'tol': 5e-4, 'nan': got_loss != got_loss, 'ok': abs(got_loss - ref_loss) <= 5e-4 * abs(ref_loss)},
+               {'name': 'configs[0] accuracy', 'got': float(correct) / (B * T), 'ref': ref_acc,
+                'rel': abs(float(correct) / (B * T) - ref_acc), 'tol': 0.01, 'nan': False,
+                'ok': abs(float(correct) / (B * T) - ref_acc) <= 0.01}]
+    # the model call (Transformer.__call__) returns the same logits
+    again, _ = model(x)
+    results.append(_stats('configs[0] __call__ logits', again.double().cpu().reshape(B * T, -1),
+                          ref_logits.reshape(B * T, -1), 2e-2))
+    return _finish(results)
+
+
+def check_greedy_sweep(layers=12, embedding=1024, heads=16, prompts=16, prompt_len=8, length=256, window=512, seed=33):
+    '''configs[4]: the scaled model (12 blocks, d_model 1024, d_h 64): forward logits on a batch, then a greedy
+    decode of `prompts` x `length` steps that must be token-identical with the oracle's cached (`past=`) decode at
+    every step where the oracle's top-2 logit margin exceeds the tolerance (2e-2 of the largest logit).  The oracle
+    is fed the device's tokens, so that a non-decisive divergence does not cascade.'''
+    import numpy as np
+    from oracle import transformer_oracle as oracle
+
+    model, cfg, weights = _small_model(layers, embedding, heads, window=window, seed=seed)
+    rng = np.random.default_rng(seed + 1)
+    params = oracle.to_torch(weights, torch.float64)
+    results = []
+    # forward logits at the scaled width
+    draw = rng.integers(0, cfg.vocab_size, size=(2, 129))
+    x = draw[:, :-1]
+    logits, _ = model(x)
+    with torch.no_grad():
+        ref_logits, _ = oracle.transformer_call(params, x, cfg)
+    results.append(_stats('scaled model logits (L%d E%d)' % (layers, embedding), logits.double().cpu().reshape(256, -1),
+                          ref_logits.reshape(256, -1), 2e-2))
+    prompt = rng.integers(0, cfg.vocab_size, size=(prompts, prompt_len))
+    out = model.generate(prompt, length, temperature=0.0).cpu().numpy()
+    checked = mismatches = 0
+    worst_margin_of_mismatch = 0.0
+    with torch.no_grad():
+        past = None
+        context = torch.as_tensor(prompt).long()
+        for step in range(length):
+            step_logits, past = oracle.transformer_call(params, context, cfg, past=past)
+            last = step_logits[:, -1].numpy()
+            top2 = np.sort(last, axis=-1)[:, -2:]
+            margin = top2[:, 1] - top2[:, 0]
+            scale = np.abs(last).max(axis=-1)
+            decisive = margin > 2e-2 * scale
+            wrong = (out[:, step] != last.argmax(axis=-1)) & decisive
+            checked += int(decisive.sum())
+            mismatches += int(wrong.sum())
+            if wrong.any():
+                worst_margin_of_mismatch = max(worst_margin_of_mismatch, float((margin / scale)[wrong].max()))
+            context = torch.as_tensor(out[:, step:step + 1]).long()
+    results.append({'name': 'greedy sweep %d prompts x %d steps (decisive %d of %d)' % (prompts, length, checked,
+                                                                                    prompts * length),
+                    'rel': mismatches, 'tol': 0, 'nan': False, 'worst_margin_of_mismatch': worst_margin_of_mismatch,
+                    'ok': mismatches == 0 and checked >= prompts * length // 4})
+    return _finish(results)
+
+
+GROUPS['configs'] = [
+    check_config0_forward_loss,
+    # configs[1]'s sequence length: forward, loss and every gradient at T 2048 (2 blocks keep the CPU oracle's
+    # attention matrices, [B, H, T, T] per block, within a few GB; fp32 oracle for the same reason)
+    lambda: check_engine_forward_backward(B=2, T=2048, layers=2, oracle_dtype=torch.float32),
+    # the block stack without LayerNorm (use_layer_normalization: false; only ln_f remains, transformer.py:583-594, 811)
+    lambda: check_engine_forward_backward(B=2, T=100, layers=3, layer_norm=False),
+    check_greedy_sweep,
+    # the default model through the persistent decode kernel: 16 prompts x 256 steps as well
+    lambda: check_greedy_sweep(layers=8, embedding=256, heads=16, prompts=16, prompt_len=4, length=256, window=320),
+]

@@ -137,6 +137,11 @@ def _gloo_worker(rank, world, port, results):
     total = shard.mean().clone()
     dist.all_reduce(total)
     ok = ok and abs(float(total) / world - (world - 1) / 2) < 1e-6
+    # without --seed every process draws its own seed from the clock: all ranks must adopt rank 0's
+    ok = ok and parallel.agree_on_seed(1000 + 17 * rank) == 1000
+    # ... while the dropout key differs between ranks (and is the plain seed on rank 0)
+    keys = {parallel.rank_dropout_seed(1000, r) for r in range(world)}
+    ok = ok and len(keys) == world and parallel.rank_dropout_seed(1000, 0) == 1000
     results[rank] = ok
     dist.destroy_process_group()
 
@@ -163,3 +168,51 @@ def test_tools_and_bench_compile():
     assert len(scripts) >= 10
     for path in scripts:
         py_compile.compile(path, doraise=True)
+
+
+def test_agree_on_seed_is_identity_without_a_process_group():
+    assert parallel.agree_on_seed(12345) == 12345
+    assert 0 <= parallel.rank_dropout_seed(-5, 3) < 2 ** 64
+
+
+def test_prefetcher_propagates_errors_and_stops_its_thread():
+    import threading
+    import time
+
+    import numpy as np
+
+    from composer_b200 import data
+
+    class Broken:
+        def __len__(self):
+            return 3
+
+        def __iter__(self):
+            yield np.zeros((2, 4), dtype=np.int64), np.zeros((2, 4), dtype=np.int64)
+            raise OSError('bad file')
+
+    iterator = iter(data.prefetch_pinned(Broken()))
+    next(iterator)
+    try:
+        next(iterator)
+        raised = False
+    except OSError:
+        raised = True
+    assert raised, 'an exception in the loader thread must not look like the end of the epoch'
+
+    class Endless:
+        def __len__(self):
+            return 10 ** 9
+
+        def __iter__(self):
+            while True:
+                yield np.zeros((2, 4), dtype=np.int64), np.zeros((2, 4), dtype=np.int64)
+
+    before = threading.active_count()
+    iterator = iter(data.prefetch_pinned(Endless(), depth=2))
+    next(iterator)
+    iterator.close()                  # the consumer leaves early (max_steps): the producer must exit
+    deadline = time.time() + 5
+    while threading.active_count() > before and time.time() < deadline:
+        time.sleep(0.05)
+    assert threading.active_count() <= before

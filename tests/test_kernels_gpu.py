@@ -41,11 +41,29 @@ def test_native_library_is_loaded():
     assert library.cb200_launch_count() > before
 
 
-def test_generate_rejects_positions_beyond_the_window():
+def test_generate_beyond_the_window_continues_in_windows():
+    '''The reference's default invocation (prompt 10, length 1024, window 1024) asks for more positions than wpe has
+    rows; the model serves it in re-primed windows, while the C ABI itself refuses positions beyond the window.'''
+    import ctypes
     import kernel_checks
+    from composer_b200 import _lib
     model, cfg, _ = kernel_checks._small_model(1, 256, 16, window=32)
+    out = model.generate([[1, 2, 3]], 75, temperature=0.0)
+    assert tuple(out.shape) == (1, 75) and int(out.min()) >= 0 and int(out.max()) < cfg.vocab_size
+    # the first window is exactly what a single-window call returns
+    first = model.generate([[1, 2, 3]], 30, temperature=0.0)
+    assert torch.equal(out[:, :30], first)
     with pytest.raises(ValueError):
-        model.generate([[1, 2, 3]], 40)
+        model.generate([[1, 2, 3]], 75, return_uniforms=True)
+    with pytest.raises(ValueError):
+        model.generate([list(range(40))], 4)
+    _, cache, workspace = model._decode_state
+    prompt = torch.tensor([[1, 2, 3]], dtype=torch.int32, device='cuda')
+    ids = torch.empty((1, 40), dtype=torch.int32, device='cuda')
+    with pytest.raises(_lib.NativeError):
+        _lib.call('cb200_generate', model._engine, ctypes.c_void_p(cache.data_ptr()), 64,
+                  ctypes.c_void_p(workspace.data_ptr()), workspace.numel(), ctypes.c_void_p(prompt.data_ptr()), 1, 3, 40,
+                  0.0, 0, 0, ctypes.c_void_p(ids.data_ptr()), None, None, None)
 
 
 def test_relative_attention_is_refused():

@@ -153,3 +153,72 @@ def test_get_dataset_errors(tmp_path):
         cli_module.get_dataset(cli_module.ModelType.TRANSFORMER, tmp_path, cfg, 'validation')
     with pytest.raises(cli_module.DatasetError):
         cli_module.get_dataset(cli_module.ModelType.TRANSFORMER, tmp_path, cfg, 'train')
+
+
+# ---------------------------------------------------------------------------
+# `.data` codec against files written by the reference (sequence.py:1500-1587)
+# ---------------------------------------------------------------------------
+
+def _data_golden():
+    import json
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'data_golden.json')
+    with open(path) as handle:
+        fixture = json.load(handle)
+    import sys
+    assert fixture['byteorder'] == sys.byteorder      # the reference packs with native byte order
+    return fixture['cases']
+
+
+def test_data_files_match_the_reference_writer_byte_for_byte(tmp_path):
+    '''Our writer reproduces the reference's `.data` bytes; our readers return what the reference's readers do.'''
+
+    cases = _data_golden()
+    assert len(cases) >= 10 and any(not case['ids'] for case in cases)        # includes an empty sequence
+    for index, case in enumerate(cases):
+        reference_bytes = bytes.fromhex(case['file_hex'])
+        notes = [sequence.Note(*n) for n in case['notes']]
+        sustains = [sequence.SustainPeriod(*s) for s in case['sustain_periods']]
+        events = sequence.NoteSequence(notes, sustains).to_event_sequence(
+            case['time_step_increment'], case['max_time_steps'], case['velocity_bins'])
+        ours = tmp_path / ('ours_%d.data' % index)
+        events.to_integer_encoding().to_file(str(ours))
+        assert ours.read_bytes() == reference_bytes, 'case %d: written bytes differ from the reference writer' % index
+        theirs = tmp_path / ('reference_%d.data' % index)
+        theirs.write_bytes(reference_bytes)
+        ids, _, ranges, settings = sequence.IntegerEncodedEventSequence.event_ids_from_file(str(theirs))
+        assert list(ids) == case['ids']
+        assert tuple(settings) == (case['time_step_increment'], case['max_time_steps'], case['velocity_bins'])
+        as_array = sequence.IntegerEncodedEventSequence.event_ids_from_file(str(theirs), as_numpy_array=True)[0]
+        assert as_array.tolist() == case['ids']
+        assert list(sequence.IntegerEncodedEventSequence.event_ids_from_file_as_generator(str(theirs))) == case['ids']
+        back = sequence.IntegerEncodedEventSequence.from_file(str(theirs), decode=False)
+        assert [list(pair) for pair in back.events] == case['pairs']
+        # decode=True gives the event sequence the file was written from
+        decoded = sequence.IntegerEncodedEventSequence.from_file(str(theirs), decode=True)
+        assert [(e.type, e.value) for e in decoded.events] == [(e.type, e.value) for e in events.events]
+
+
+def test_data_files_against_the_live_reference_codec(tmp_path):
+    '''Both directions against the reference module itself when /root/reference is present (skipped elsewhere).'''
+
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden'))
+    from reference_shims import load_reference_sequence
+    ref = load_reference_sequence()
+    if ref is None:
+        pytest.skip('the reference tree is not available on this machine')
+    rng = np.random.default_rng(5)
+    vocabulary = sequence.EventVocabulary(10, 100, 32)
+    for index in range(6):
+        ids = rng.integers(0, 390, size=int(rng.integers(0, 300)))
+        decoded = [sequence.IntegerEncodedEventSequence.id_to_event(int(i), vocabulary.ranges, vocabulary.value_ranges)
+                   for i in ids]
+        ours = tmp_path / ('ours_%d.data' % index)
+        sequence.EventSequence(decoded, 10, 100, 32).to_integer_encoding().to_file(str(ours))
+        # the reference reads our file ...
+        ref_ids = [int(v) for v in ref.IntegerEncodedEventSequence.event_ids_from_file(str(ours))[0]]
+        assert ref_ids == ids.tolist()
+        # ... and re-writes it identically
+        theirs = tmp_path / ('theirs_%d.data' % index)
+        ref.IntegerEncodedEventSequence.from_file(str(ours), decode=False).to_file(str(theirs))
+        assert theirs.read_bytes() == ours.read_bytes()
