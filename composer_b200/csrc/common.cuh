@@ -312,7 +312,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "=r"(done)
             : "r"(addr), "r"(parity), "r"(100000u)
             : "memory");
-        if (spins > (1u << 20)) __trap();
+        if (spins > (1u << 16)) __trap();   // ~6 s at the 0.1 ms suspend hint
     }
 }
 

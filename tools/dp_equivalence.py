@@ -100,9 +100,10 @@ def main():
         single.apply_gradients(1e-3, 1)
     torch.cuda.synchronize()
     a, b = dp_model._params, single._params
-    diff = float((a - b).abs().max())
-    checks.append({'name': '3 Adam steps: max |w_dp - w_1rank| (lr 1e-3; Adam moves every weight ~lr per step)',
-                   'got': diff, 'tol': 2e-3, 'ok': diff <= 2e-3})
+    # Adam's first steps move every coordinate by ~lr whatever the gradient's size, so a coordinate whose gradient is
+    # numerically zero may move the other way: compare the mean update error in units of lr
+    diff = float((a - b).abs().mean()) / 1e-3
+    checks.append({'name': '3 Adam steps: mean |w_dp - w_1rank| / lr', 'got': diff, 'tol': 0.05, 'ok': diff <= 0.05})
     gathered = [torch.empty_like(a) for _ in range(world)]
     dist.all_gather(gathered, a)
     same = all(bool(torch.equal(gathered[0], g)) for g in gathered[1:])

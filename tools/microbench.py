@@ -102,11 +102,19 @@ def main():
     out = torch.empty(B, T, E, device=dev, dtype=bf)
     lse = torch.empty(B, H, T, device=dev)
     att_flops = 4.0 * B * H * T * (T + 1) / 2 * D
-    for rate in (0.0, 0.1):
-        t = timeit(lambda: _lib.call('cb200_attention_fwd', ptr(qkv), ptr(out), ptr(lse), B, T, H, D, scale, rate, 1,
-                                     1, 1, stream()), iters=5)
-        rows.append(('attention fwd (dropout %.1f)' % rate, t * 1e6, att_flops / t / 1e12,
-                     B * H * T * (T + 1) / 2 / t / 1e12))
+    impl_names = {0: 'tcgen05, P in TMEM', 2: 'tcgen05, P via smem', 1: 'mma.sync (round 1)'}
+    for impl in (0, 2, 1):
+        _lib.call('cb200_set_attention_fwd_impl', impl)
+        for rate in (0.0, 0.1):
+            try:
+                t = timeit(lambda: _lib.call('cb200_attention_fwd', ptr(qkv), ptr(out), ptr(lse), B, T, H, D, scale, rate,
+                                             1, 1, 1, stream()), iters=5)
+                rows.append(('attention fwd [%s] (dropout %.1f)' % (impl_names[impl], rate), t * 1e6, att_flops / t / 1e12,
+                             B * H * T * (T + 1) / 2 / t / 1e12))
+            except Exception as error:      # keep the rest of the table
+                rows.append(('attention fwd [%s] FAILED: %s' % (impl_names[impl], str(error)[:60]), 0.0, 0.0, 0.0))
+    _lib.call('cb200_set_attention_fwd_impl', 0)
+    _lib.call('cb200_attention_fwd', ptr(qkv), ptr(out), ptr(lse), B, T, H, D, scale, 0.1, 1, 1, 1, stream())
     dout = torch.randn(B, T, E, device=dev).to(bf)
     delta = torch.empty(B, H, T, device=dev)
     dq_acc = torch.zeros(B, T, E, device=dev)
@@ -141,9 +149,9 @@ def main():
     rows.append(('bias grad + dropout bwd [M, E]', t * 1e6, 0.0, 2 * M * E * 2 / t / 1e9))
 
     print('shapes: B %d T %d E %d H %d (M = %d tokens)' % (B, T, E, H, M))
-    print('%-36s %10s %10s %12s' % ('kernel', 'us', 'TFLOP/s', 'GB/s | Texp/s'))
+    print('%-58s %10s %10s %12s' % ('kernel', 'us', 'TFLOP/s', 'GB/s | Texp/s'))
     for name, us, tf, gb in rows:
-        print('%-36s %10.1f %10.1f %12.2f' % (name, us, tf, gb))
+        print('%-58s %10.1f %10.1f %12.2f' % (name, us, tf, gb))
 
 
 if __name__ == '__main__':
