@@ -160,24 +160,26 @@ __host__ __device__ __forceinline__ Philox4 drop_bits_rowmajor(const DropoutPara
 
 // Attention-probability dropout.  The T x T keep mask of one (batch, head) pair `bh` is defined per
 // (query row i, block of 128 keys jb) by one multiplicative congruential stream modulo 2^32:
-//     x_0 = attn_row_seed(base(bh), i, jb) (odd),   x_{p+1} = lo32(A x_p),   p = 0 .. 63
-// and pair p decides keys 128 jb + 2p and 128 jb + 2p + 1 from the two halves of the 64-bit product A x_p:
-//     key 2p     is kept iff  float_bits(lo32(A x_p)) >= thr  or the comparison is unordered  (set.geu.f32)
-//     key 2p + 1 is kept iff  float_bits(hi32(A x_p)) >= thr  or unordered.
-// Reading the random words as fp32 makes the keep decision ONE instruction per element that already yields
-// the multiplier 1.0f / 0.0f (FSET.BF), and the 64-bit product is one IMAD.WIDE per pair: 1.5 instructions per
-// element, regenerated identically by forward, backward and the mask export.  Both words are dominated by the
-// high bits of the product, the good ones of a power-of-two MCG.  A thread that owns a contiguous, even-aligned
-// range of a row's keys starts at x_p = x_0 A^p (one multiply).  `thr` is a negative float chosen so that the
-// number of 32-bit patterns that compare >= thr (or are NaN) is (1 - rate) 2^32 (attn_drop_threshold_bits).
-// The base is drawn once per launch from Philox4x32-10 of (seed, step, layer).
+//     x_0 = attn_row_seed(base(bh), i, jb) (odd),   x_{p+1} = A x_p,   p = 0 .. 63
+// and pair p decides keys 128 jb + 2p and 128 jb + 2p + 1 from two odd multiples of the state:
+//     key 2p     is kept iff  float_bits(A x_p) >= thr  or the comparison is unordered  (set.geu.f32)
+//     key 2p + 1 is kept iff  float_bits(C x_p) >= thr  or unordered.
+// Both words are bijections of the state, hence uniform over the odd 32-bit patterns (the HIGH half of the
+// 64-bit product A x is not: it never exceeds A), and the comparison is dominated by their high bits, the good
+// ones of a power-of-two MCG.  Reading the random words as fp32 makes the keep decision ONE instruction per
+// element that already yields the multiplier 1.0f / 0.0f (FSET.BF): 2 instructions per element in all (IMAD +
+// FSET), regenerated identically by forward, backward and the mask export.  A thread that owns a contiguous,
+// even-aligned range of a row's keys starts at x_p = x_0 A^p (one multiply).  `thr` is a negative float chosen so
+// that the number of 32-bit patterns that compare >= thr (or are NaN) is (1 - rate) 2^32
+// (attn_drop_threshold_bits).  The base is drawn once per launch from Philox4x32-10 of (seed, step, layer).
 struct AttnDropKey {
     uint32_t k0, k1;
     uint32_t thr_bits;      // fp32 bit pattern of the threshold; 0 = dropout off
     float keep_scale;
 };
 
-constexpr uint32_t ATTN_MCG_A = 0x93D765DDu;   // Steele & Vigna (2021), good 32-bit MCG multiplier
+constexpr uint32_t ATTN_MCG_A = 0x93D765DDu;   // Steele & Vigna (2021), good 32-bit MCG multipliers
+constexpr uint32_t ATTN_MCG_C = 0xADB4A92Du;
 
 __host__ __device__ constexpr uint32_t mcg_mul_pow(int n) {
     uint32_t a = 1;
@@ -235,11 +237,10 @@ __host__ __device__ __forceinline__ AttnDropKey make_attn_drop_key(const Dropout
 #ifdef __CUDACC__
 // One pair of keep multipliers (1.0f / 0.0f) and the stream advance.
 __device__ __forceinline__ void attn_drop_pair(uint32_t& x, float thr, float& m0, float& m1) {
-    uint32_t lo, hi;
-    asm("{\n\t.reg .b64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}" : "=r"(lo), "=r"(hi) : "r"(x), "r"(ATTN_MCG_A));
-    asm("set.geu.f32.f32 %0, %1, %2;" : "=f"(m0) : "f"(__uint_as_float(lo)), "f"(thr));
-    asm("set.geu.f32.f32 %0, %1, %2;" : "=f"(m1) : "f"(__uint_as_float(hi)), "f"(thr));
-    x = lo;
+    const uint32_t w0 = x * ATTN_MCG_A, w1 = x * ATTN_MCG_C;
+    asm("set.geu.f32.f32 %0, %1, %2;" : "=f"(m0) : "f"(__uint_as_float(w0)), "f"(thr));
+    asm("set.geu.f32.f32 %0, %1, %2;" : "=f"(m1) : "f"(__uint_as_float(w1)), "f"(thr));
+    x = w0;
 }
 
 // ---- packed fp32 pairs (Blackwell: FFMA2 / FADD2 / FMUL2 do two lanes per issue slot) -------------------

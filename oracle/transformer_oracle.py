@@ -367,7 +367,9 @@ def loss_and_gradients(params_np, ids, labels, cfg, dtype=torch.float64, dropout
     logits, _ = transformer_call(params, ids, cfg, dropout_masks=dropout_masks)
     loss = sparse_categorical_crossentropy(labels, logits)
     loss.backward()
-    grads = OrderedDict((name, p.grad.detach().numpy()) for name, p in params.items())
+    # (a variable the configuration does not use, e.g. ln_1 / ln_2 without LayerNorm, has no gradient: zeros)
+    grads = OrderedDict((name, (p.grad if p.grad is not None else torch.zeros_like(p)).detach().numpy())
+                        for name, p in params.items())
     return float(loss.detach()), float(batch_accuracy(labels, logits.detach())), logits.detach().numpy(), grads
 
 
