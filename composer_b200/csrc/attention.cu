@@ -357,7 +357,7 @@ attn_dq_store_kernel(float* __restrict__ dq_acc, __nv_bfloat16* __restrict__ dqk
 // ---------------------------------------------------------------------------
 // Host launchers
 // ---------------------------------------------------------------------------
-static int g_attention_fwd_impl = 0;   // 0: tcgen05, P in TMEM (TS MMA); 1: round-1 mma.sync kernel; 2: tcgen05, P through smem
+static int g_attention_fwd_impl = 0;   // 0: tcgen05, P in TMEM (TS MMA); 1: round-1 mma.sync kernel; 2: tcgen05, P through smem; 3, 4: tile-shape variants of 0
 void attention_set_fwd_impl(int impl) { g_attention_fwd_impl = impl; }
 
 static const float kLog2e = 1.4426950408889634f;
@@ -376,7 +376,7 @@ int attention_fwd(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse, int 
     CB200_REQUIRE(T <= (1 << 17), "sequences above 2^17 tokens are not supported by the attention dropout stream");
     const AttnDropKey key = make_attn_drop_key(drop, layer);
     if (g_attention_fwd_impl != 1)
-        return attention_fwd_tc(qkv, out, lse, B, T, H, D, scale, key, g_attention_fwd_impl == 2, s);
+        return attention_fwd_tc(qkv, out, lse, B, T, H, D, scale, key, g_attention_fwd_impl, s);
     const float c = scale * kLog2e;
     const bool dropping = key.thr_bits != 0;
     switch (D) {

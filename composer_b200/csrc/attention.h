@@ -17,12 +17,13 @@ int attention_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* out, const __nv
                   const DropoutParams& drop, uint32_t layer, cudaStream_t s);
 
 // Selects the forward kernel: 0 = tcgen05 / TMEM with P kept in TMEM (default), 1 = round-1 warp-level mma.sync
-// kernel (A/B reference), 2 = tcgen05 / TMEM with P staged through shared memory.
+// kernel (A/B reference), 2 = tcgen05 / TMEM with P staged through shared memory, 3 / 4 = tile-shape variants of 0
+// for d_h 16 (64-key tiles, 3 / 4 CTAs per SM).
 void attention_set_fwd_impl(int impl);
 
 // tcgen05 / TMEM forward (attention_fwd_tc.cu).
 int attention_fwd_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse, int B, int T, int H, int D, float scale,
-                     const AttnDropKey& key, bool psmem, cudaStream_t s);
+                     const AttnDropKey& key, int variant, cudaStream_t s);
 
 // tcgen05 / TMEM implementation of the main backward kernel (attention_tc.cu).
 int attention_bwd_tc_main(const __nv_bfloat16* qkv, const __nv_bfloat16* dout, const float* lse, const float* delta,

@@ -27,17 +27,29 @@
 namespace cb200 {
 
 constexpr int TCF_THREADS = 256;
-constexpr int TCF_SOFTMAX_REGS = 200, TCF_CONTROL_REGS = 56;   // 128 * (200 + 56) = half of the register file
 
-template <int D, bool PSMEM>
+// KT: keys per tile = the part of a score row a thread holds in registers.  CPS: CTAs per SM.  Four softmax warps
+// per CTA means CPS softmax warps per scheduler: KT 128 needs ~180 registers per softmax thread (2 CTAs per SM), KT 64
+// about 110 (3 or 4 per SM: more warps to hide the MUFU / TMEM / barrier latencies, twice the per-tile hand-offs).
+template <int D, bool PSMEM, int KT_, int CPS_>
 struct TcfCfg {
-    static constexpr int KT = (D == 16) ? 128 : 64;        // keys per tile (the row of S a thread holds in registers)
+    static constexpr int KT = KT_, CPS = CPS_;
     static constexpr int RB = 2 * D;                        // bytes per row of a Q / K / V tile
     static constexpr int QTILE = 128 * RB;
     static constexpr int KTILE = KT * RB;
     static constexpr int NKV = (D == 64) ? 3 : 4;           // K / V ring stages
     static constexpr int PBYTES = (KT / 64) * 128 * 128;    // P in shared memory: 64-key halves of [128 rows][128 B]
     static constexpr size_t SMEM = 2 * QTILE + NKV * 2 * KTILE + (PSMEM ? 2 * PBYTES : 0) + 256 + 1024;
+    // TMEM: two buffers; a buffer holds S (KT fp32 columns), later P (KT/2 columns of bf16 pairs) and O~ (D columns)
+    static constexpr int COL_O = KT / 2;
+    static constexpr int BUF_COLS = (KT / 2 + D <= 64 && KT <= 64) ? 64 : 128;
+    static constexpr int TMEM_COLS = 2 * BUF_COLS;
+    // registers after setmaxnreg: 128 * (SOFTMAX + CONTROL) = the CTA's share of the register file
+    static constexpr int LAUNCH_REGS = (65536 / (CPS * TCF_THREADS)) / 8 * 8;
+    static constexpr int CONTROL_REGS = (CPS == 2) ? 56 : 24;
+    static constexpr int SOFTMAX_REGS = 2 * LAUNCH_REGS - CONTROL_REGS;
+    static_assert(COL_O + D <= BUF_COLS && KT <= BUF_COLS, "TMEM buffer layout");
+    static_assert(CPS * TMEM_COLS <= 512, "TMEM budget");
 };
 
 __device__ __forceinline__ float fmax3f(float a, float b, float c) {
@@ -50,33 +62,33 @@ struct TcfCursor {
     int item, it, qi, bh, j, n, g;   // it: ordinal of the item in this CTA; n: tiles of the item; g: tiles so far
 };
 
-template <int D, bool DROP, bool PSMEM>
-__global__ void __launch_bounds__(TCF_THREADS, 2)
+template <int D, bool DROP, bool PSMEM, int KT_, int CPS_>
+__global__ void __launch_bounds__(TCF_THREADS, CPS_)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                    __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int T, int H, int BH, int nq,
                    float scale_log2, AttnDropKey drop) {
-    using C = TcfCfg<D, PSMEM>;
+    using C = TcfCfg<D, PSMEM, KT_, CPS_>;
     constexpr int KT = C::KT, RB = C::RB, QTILE = C::QTILE, KTILE = C::KTILE, NKV = C::NKV, NCH = KT / 32;
     constexpr uint32_t LT = umma_layout_for_row_bytes(RB);
-    constexpr uint32_t COL_O = 64;                          // O~ inside a buffer (P occupies columns 0 .. KT/2 - 1)
-    static_assert(COL_O + D <= 128 && KT / 2 <= COL_O, "TMEM buffer layout");
+    constexpr uint32_t COL_O = C::COL_O, BUFC = C::BUF_COLS;
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sQ = smem;                                     // [2][QTILE]
-    uint8_t* sK = sQ + 2 * QTILE;                           // [NKV][KTILE]
-    uint8_t* sV = sK + NKV * KTILE;                         // [NKV][KTILE]
-    uint8_t* sP = sV + NKV * KTILE;                         // [2][PBYTES] (PSMEM only)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + (PSMEM ? 2 * C::PBYTES : 0));
-    uint64_t* bar_q_full = bars;                            // [2] Q tile landed
-    uint64_t* bar_q_free = bars + 2;                        // [2] the item's last S MMA has read it
-    uint64_t* bar_kv_full = bars + 4;                       // [NKV]
-    uint64_t* bar_kv_free = bars + 4 + NKV;                 // [NKV] the tile's P V MMAs have read it
-    uint64_t* bar_s_full = bars + 4 + 2 * NKV;              // [2] S complete in TMEM
-    uint64_t* bar_p_full = bar_s_full + 2;                  // [2] P written by every softmax thread
-    uint64_t* bar_o_full = bar_s_full + 4;                  // [2] O~ complete in TMEM
-    uint64_t* bar_buf_free = bar_s_full + 6;                // [2] O~ read: the buffer may take S of tile g + 2
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_s_full + 8);
+    // everything below is a 32-bit shared-space address (no generic -> shared conversions in the loops)
+    const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sQ = smem;                               // [2][QTILE]
+    const uint32_t sK = sQ + 2 * QTILE;                     // [NKV][KTILE]
+    const uint32_t sV = sK + NKV * KTILE;                   // [NKV][KTILE]
+    const uint32_t sP = sV + NKV * KTILE;                   // [2][PBYTES] (PSMEM only)
+    const uint32_t bars = sP + (PSMEM ? 2 * C::PBYTES : 0);
+    const uint32_t bar_q_full = bars;                       // [2] Q tile landed
+    const uint32_t bar_q_free = bars + 16;                  // [2] the item's last S MMA has read it
+    const uint32_t bar_kv_full = bars + 32;                 // [NKV]
+    const uint32_t bar_kv_free = bar_kv_full + 8 * NKV;     // [NKV] the tile's P V MMAs have read it
+    const uint32_t bar_s_full = bar_kv_free + 8 * NKV;      // [2] S complete in TMEM
+    const uint32_t bar_p_full = bar_s_full + 16;            // [2] P written by every softmax thread
+    const uint32_t bar_o_full = bar_s_full + 32;            // [2] O~ complete in TMEM
+    const uint32_t bar_buf_free = bar_s_full + 48;          // [2] O~ read: the buffer may take S of tile g + 2
+    const uint32_t tmem_slot = bar_s_full + 64;
 
     const int E = H * D;
     const int items = nq * BH;
@@ -87,24 +99,28 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         tma_prefetch_desc(&tm_q);
         tma_prefetch_desc(&tm_kv);
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&bar_q_full[i], 1);
-            mbar_init(&bar_q_free[i], 1);
-            mbar_init(&bar_s_full[i], 1);
-            mbar_init(&bar_p_full[i], 128);
-            mbar_init(&bar_o_full[i], 1);
-            mbar_init(&bar_buf_free[i], 128);
+            mbar_init_a(bar_q_full + 8 * i, 1);
+            mbar_init_a(bar_q_free + 8 * i, 1);
+            mbar_init_a(bar_s_full + 8 * i, 1);
+            mbar_init_a(bar_p_full + 8 * i, 128);
+            mbar_init_a(bar_o_full + 8 * i, 1);
+            mbar_init_a(bar_buf_free + 8 * i, 128);
         }
         for (int i = 0; i < NKV; ++i) {
-            mbar_init(&bar_kv_full[i], 1);
-            mbar_init(&bar_kv_free[i], 1);
+            mbar_init_a(bar_kv_full + 8 * i, 1);
+            mbar_init_a(bar_kv_free + 8 * i, 1);
         }
         mbar_fence_init();
     }
-    if (warp == 6) tmem_alloc<256>(tmem_slot);
+    if (warp == 6) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(C::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
+    uint32_t tmem;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot) : "memory");
 
     auto setup = [&](TcfCursor& c) {
         c.qi = nq - 1 - c.item / BH;                        // heaviest query tiles first
@@ -122,7 +138,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     };
 
     if (warp >= 4) {
-        setmaxnreg_dec<TCF_CONTROL_REGS>();
+        setmaxnreg_dec<C::CONTROL_REGS>();
         if (warp == 5) {
             // ===================== TMA producer =====================
             if (elect_one()) {
@@ -133,15 +149,15 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                     const int row0 = b * T;
                     if (c.j == 0) {
                         const int qs = c.it & 1;
-                        mbar_wait(&bar_q_free[qs], ((c.it >> 1) & 1) ^ 1);
-                        mbar_expect_tx(&bar_q_full[qs], QTILE);
-                        tma_load_2d(sQ + qs * QTILE, &tm_q, &bar_q_full[qs], h * D, row0 + c.qi * 128);
+                        mbar_wait_a(bar_q_free + 8 * qs, ((c.it >> 1) & 1) ^ 1);
+                        mbar_expect_tx_a(bar_q_full + 8 * qs, QTILE);
+                        tma_load_2d_a(sQ + qs * QTILE, &tm_q, bar_q_full + 8 * qs, h * D, row0 + c.qi * 128);
                     }
                     const int st = c.g % NKV;
-                    mbar_wait(&bar_kv_free[st], ((c.g / NKV) & 1) ^ 1);
-                    mbar_expect_tx(&bar_kv_full[st], 2 * KTILE);
-                    tma_load_2d(sK + st * KTILE, &tm_kv, &bar_kv_full[st], E + h * D, row0 + c.j * KT);
-                    tma_load_2d(sV + st * KTILE, &tm_kv, &bar_kv_full[st], 2 * E + h * D, row0 + c.j * KT);
+                    mbar_wait_a(bar_kv_free + 8 * st, ((c.g / NKV) & 1) ^ 1);
+                    mbar_expect_tx_a(bar_kv_full + 8 * st, 2 * KTILE);
+                    tma_load_2d_a(sK + st * KTILE, &tm_kv, bar_kv_full + 8 * st, E + h * D, row0 + c.j * KT);
+                    tma_load_2d_a(sV + st * KTILE, &tm_kv, bar_kv_full + 8 * st, 2 * E + h * D, row0 + c.j * KT);
                     advance(c);
                 }
             }
@@ -152,37 +168,37 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                 constexpr uint32_t IDESC_O = umma_idesc_bf16(128, D, 0, 1);      // P V (V is MN-major)
                 auto issue_s = [&](const TcfCursor& c) {
                     const int qs = c.it & 1, st = c.g % NKV, buf = c.g & 1;
-                    if (c.j == 0) mbar_wait(&bar_q_full[qs], (c.it >> 1) & 1);
-                    mbar_wait(&bar_kv_full[st], (c.g / NKV) & 1);
-                    mbar_wait(&bar_buf_free[buf], ((c.g >> 1) & 1) ^ 1);
+                    if (c.j == 0) mbar_wait_a(bar_q_full + 8 * qs, (c.it >> 1) & 1);
+                    mbar_wait_a(bar_kv_full + 8 * st, (c.g / NKV) & 1);
+                    mbar_wait_a(bar_buf_free + 8 * buf, ((c.g >> 1) & 1) ^ 1);
                     tc_fence_after();
-                    const uint32_t aQ = smem_u32(sQ + qs * QTILE), aK = smem_u32(sK + st * KTILE);
+                    const uint32_t aQ = sQ + qs * QTILE, aK = sK + st * KTILE;
 #pragma unroll
                     for (int ks = 0; ks < D / 16; ++ks)
-                        umma_bf16(tmem + buf * 128, umma_smem_desc(aQ + ks * 32, 16, 8 * RB, LT),
+                        umma_bf16(tmem + buf * BUFC, umma_smem_desc(aQ + ks * 32, 16, 8 * RB, LT),
                                   umma_smem_desc(aK + ks * 32, 16, 8 * RB, LT), IDESC_S, ks > 0 ? 1u : 0u);
-                    umma_commit(&bar_s_full[buf]);
-                    if (c.j == c.n - 1) umma_commit(&bar_q_free[qs]);
+                    umma_commit_a(bar_s_full + 8 * buf);
+                    if (c.j == c.n - 1) umma_commit_a(bar_q_free + 8 * qs);
                 };
                 auto issue_pv = [&](const TcfCursor& c) {
                     const int st = c.g % NKV, buf = c.g & 1;
-                    mbar_wait(&bar_p_full[buf], (c.g >> 1) & 1);
+                    mbar_wait_a(bar_p_full + 8 * buf, (c.g >> 1) & 1);
                     tc_fence_after();
-                    const uint32_t aV = smem_u32(sV + st * KTILE);
+                    const uint32_t aV = sV + st * KTILE;
 #pragma unroll
                     for (int ks = 0; ks < KT / 16; ++ks) {
                         const uint64_t dv = umma_smem_desc(aV + ks * 16 * RB, KT * RB, 8 * RB, LT);
                         if (PSMEM) {
-                            const uint32_t aP = smem_u32(sP + buf * C::PBYTES);
-                            umma_bf16(tmem + buf * 128 + COL_O,
+                            const uint32_t aP = sP + buf * C::PBYTES;
+                            umma_bf16(tmem + buf * BUFC + COL_O,
                                       umma_smem_desc(aP + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024, 2u), dv, IDESC_O,
                                       ks > 0 ? 1u : 0u);
                         } else {
-                            umma_bf16_ts(tmem + buf * 128 + COL_O, tmem + buf * 128 + ks * 8, dv, IDESC_O, ks > 0 ? 1u : 0u);
+                            umma_bf16_ts(tmem + buf * BUFC + COL_O, tmem + buf * BUFC + ks * 8, dv, IDESC_O, ks > 0 ? 1u : 0u);
                         }
                     }
-                    umma_commit(&bar_o_full[buf]);
-                    umma_commit(&bar_kv_free[st]);
+                    umma_commit_a(bar_o_full + 8 * buf);
+                    umma_commit_a(bar_kv_free + 8 * st);
                 };
                 TcfCursor cs{static_cast<int>(blockIdx.x), 0, 0, 0, 0, 0, 0};
                 if (cs.item < items) setup(cs);
@@ -203,7 +219,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         }
     } else {
         // ===================== softmax warps: thread = query row =====================
-        setmaxnreg_inc<TCF_SOFTMAX_REGS>();
+        setmaxnreg_inc<C::SOFTMAX_REGS>();
         const int r = warp * 32 + lane;
         const uint32_t t_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
         const float thr = __uint_as_float(drop.thr_bits);
@@ -224,24 +240,24 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 
             auto fold_o = [&](int gp) {                     // o = o * alpha + O~ of tile gp, then release its buffer
                 const int pb = gp & 1;
-                mbar_wait(&bar_o_full[pb], (gp >> 1) & 1);
+                mbar_wait_a(bar_o_full + 8 * pb, (gp >> 1) & 1);
                 tc_fence_after();
 #pragma unroll
                 for (int d0 = 0; d0 < D; d0 += 16) {
                     uint32_t op[16];
-                    tmem_ld16(t_lane + pb * 128 + COL_O + d0, op);
+                    tmem_ld16(t_lane + pb * BUFC + COL_O + d0, op);
                     tmem_ld_wait();
 #pragma unroll
                     for (int d = 0; d < 16; ++d) o_acc[d0 + d] = fmaf(o_acc[d0 + d], alpha_prev, __uint_as_float(op[d]));
                 }
                 tc_fence_before();
-                mbar_arrive(&bar_buf_free[pb]);
+                mbar_arrive_a(bar_buf_free + 8 * pb);
             };
 
             for (int j = 0; j < n; ++j, ++g) {
                 const int buf = g & 1;
-                const uint32_t tbuf = t_lane + buf * 128;
-                mbar_wait(&bar_s_full[buf], (g >> 1) & 1);
+                const uint32_t tbuf = t_lane + buf * BUFC;
+                mbar_wait_a(bar_s_full + 8 * buf, (g >> 1) & 1);
                 tc_fence_after();
                 uint32_t s[KT];
 #pragma unroll
@@ -315,7 +331,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                         }
                         if (PSMEM) {
                             // row r of the 64-key half: 128 bytes, 16-byte pieces XOR-swizzled by (r & 7) (SWIZZLE_128B)
-                            const uint32_t base = smem_u32(sP) + buf * C::PBYTES + (c >> 1) * 16384 + r * 128;
+                            const uint32_t base = sP + buf * C::PBYTES + (c >> 1) * 16384 + r * 128;
 #pragma unroll
                             for (int q4 = 0; q4 < 4; ++q4) {
                                 const uint32_t off = static_cast<uint32_t>((((c & 1) * 4 + q4) ^ (r & 7)) << 4);
@@ -339,7 +355,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                     tmem_st_wait();
                     tc_fence_before();
                 }
-                mbar_arrive(&bar_p_full[buf]);
+                mbar_arrive_a(bar_p_full + 8 * buf);
                 alpha_prev = alpha;
             }
             fold_o(g - 1);
@@ -366,14 +382,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     __syncthreads();
     if (warp == 6) {
         tc_fence_after();
-        tmem_dealloc<256>(tmem);
+        tmem_dealloc<C::TMEM_COLS>(tmem);
     }
 }
 
-template <int D, bool DROP, bool PSMEM>
+template <int D, bool DROP, bool PSMEM, int KT, int CPS>
 static int launch_fwd_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse, int B, int T, int H, float scale,
                          const AttnDropKey& key, cudaStream_t s) {
-    using C = TcfCfg<D, PSMEM>;
+    using C = TcfCfg<D, PSMEM, KT, CPS>;
     constexpr size_t smem = C::SMEM;
     const int E = H * D;
     CUtensorMap tm_q, tm_kv;
@@ -381,15 +397,17 @@ static int launch_fwd_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* ls
     if (rc) return rc;
     rc = make_tmap_bf16_sw(&tm_kv, qkv, 3 * E, static_cast<uint64_t>(B) * T, 3 * E, D, C::KT, C::RB);
     if (rc) return rc;
-    auto kernel = attn_fwd_tc_kernel<D, DROP, PSMEM>;
+    auto kernel = attn_fwd_tc_kernel<D, DROP, PSMEM, KT, CPS>;
     static bool configured = false;
     if (!configured) {
         CB200_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
+    // CTAs per SM: CPS by registers and TMEM (by construction), fewer when shared memory does not allow it
+    int per_sm = CPS;
+    while (per_sm > 1 && per_sm * (smem + 1024) > 233472) --per_sm;
     const int nq = (T + 127) / 128;
     const long long items = static_cast<long long>(nq) * B * H;
-    const int per_sm = (2 * smem + 4096 <= 232448) ? 2 : 1;
     long long grid = static_cast<long long>(per_sm) * device_sm_count();
     if (grid > items) grid = items;
     kernel<<<static_cast<int>(grid), TCF_THREADS, smem, s>>>(tm_q, tm_kv, out, lse, T, H, B * H, nq,
@@ -399,24 +417,29 @@ static int launch_fwd_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* ls
     return 0;
 }
 
-template <int D>
+template <int D, int KT, int CPS>
 static int launch_fwd_tc_d(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse, int B, int T, int H, float scale,
                            const AttnDropKey& key, bool psmem, cudaStream_t s) {
     const bool dropping = key.thr_bits != 0;
     if (psmem)
-        return dropping ? launch_fwd_tc<D, true, true>(qkv, out, lse, B, T, H, scale, key, s)
-                        : launch_fwd_tc<D, false, true>(qkv, out, lse, B, T, H, scale, key, s);
-    return dropping ? launch_fwd_tc<D, true, false>(qkv, out, lse, B, T, H, scale, key, s)
-                    : launch_fwd_tc<D, false, false>(qkv, out, lse, B, T, H, scale, key, s);
+        return dropping ? launch_fwd_tc<D, true, true, KT, 2>(qkv, out, lse, B, T, H, scale, key, s)
+                        : launch_fwd_tc<D, false, true, KT, 2>(qkv, out, lse, B, T, H, scale, key, s);
+    return dropping ? launch_fwd_tc<D, true, false, KT, CPS>(qkv, out, lse, B, T, H, scale, key, s)
+                    : launch_fwd_tc<D, false, false, KT, CPS>(qkv, out, lse, B, T, H, scale, key, s);
 }
 
-// The tcgen05 forward.  psmem = false: P stays in TMEM (TS-form MMA); true: P goes through shared memory.
+// The tcgen05 forward.  variant 0: P stays in TMEM (TS-form MMA), the default tile shape; 2: P goes through shared
+// memory; 3 / 4 / 5 (d_h 16 only, A/B): P in TMEM with 64-key tiles and 3 / 4 CTAs per SM, 128-key tiles and 2 per SM.
 int attention_fwd_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse, int B, int T, int H, int D, float scale,
-                     const AttnDropKey& key, bool psmem, cudaStream_t s) {
+                     const AttnDropKey& key, int variant, cudaStream_t s) {
+    const bool psmem = variant == 2;
     switch (D) {
-        case 16: return launch_fwd_tc_d<16>(qkv, out, lse, B, T, H, scale, key, psmem, s);
-        case 32: return launch_fwd_tc_d<32>(qkv, out, lse, B, T, H, scale, key, psmem, s);
-        case 64: return launch_fwd_tc_d<64>(qkv, out, lse, B, T, H, scale, key, psmem, s);
+        case 16:
+            if (variant == 3) return launch_fwd_tc_d<16, 64, 3>(qkv, out, lse, B, T, H, scale, key, false, s);
+            if (variant == 4) return launch_fwd_tc_d<16, 64, 4>(qkv, out, lse, B, T, H, scale, key, false, s);
+            return launch_fwd_tc_d<16, 128, 2>(qkv, out, lse, B, T, H, scale, key, psmem, s);
+        case 32: return launch_fwd_tc_d<32, 64, 2>(qkv, out, lse, B, T, H, scale, key, psmem, s);
+        case 64: return launch_fwd_tc_d<64, 64, 2>(qkv, out, lse, B, T, H, scale, key, psmem, s);
         default: break;
     }
     set_error("attention head size %d is not supported (16, 32 or 64)", D);

@@ -24,7 +24,13 @@
 namespace cb200 {
 
 constexpr int TCB_SM_WARPS = 16;                       // softmax warps: 4 row bands x 4 column quarters
-constexpr int TCB_THREADS = (TCB_SM_WARPS + 2) * 32;   // + control warp + TMEM allocator warp
+constexpr int TCB_THREADS = (TCB_SM_WARPS + 4) * 32;   // + one warpgroup: control warp, TMEM allocator warp, 2 idle
+// registers after setmaxnreg: the CTA is launched with 96 registers per thread (640 threads); the control warpgroup
+// keeps 32 and what it releases, 128 * 64, lets the 16 softmax warps grow by 16 each: they hold their 32 columns of S
+// and of dP (64 registers) while the next tile's MMAs already run.  (setmaxnreg.inc can only take what the CTA's own
+// warps released: 512 * (112 - 96) == 128 * (96 - 32).)
+constexpr int TCB_LAUNCH_REGS = 96, TCB_SOFTMAX_REGS = 112, TCB_CONTROL_REGS = 32;
+static_assert(TCB_SM_WARPS * 32 * (TCB_SOFTMAX_REGS - TCB_LAUNCH_REGS) <= 128 * (TCB_LAUNCH_REGS - TCB_CONTROL_REGS), "register pool");
 constexpr int TCB_CPT = 128 / (TCB_SM_WARPS / 4);      // key columns per softmax thread (32)
 constexpr int TCB_TILE = 128;                          // query rows per tile = keys per CTA
 
@@ -57,23 +63,24 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     static_assert(COL_DV + D <= 512, "TMEM budget");
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sK = smem;
-    uint8_t* sV = sK + TILE;
-    uint8_t* sQ = sV + TILE;                  // [NBUF_Q][TILE]
-    uint8_t* sdO = sQ + NBUF_Q * TILE;        // [NBUF_Q][TILE]
-    uint8_t* sP = sdO + NBUF_Q * TILE;        // [NBUF_P][PBYTES]
-    uint8_t* sdS = sP + NBUF_P * PBYTES;      // [NBUF_P][PBYTES]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + NBUF_P * PBYTES);
-    uint64_t* bar_kv = bars;                  // K, V landed
-    uint64_t* bar_load = bars + 1;            // [3] Q, dO tile landed
-    uint64_t* bar_s_full = bars + 4;          // S, dP complete in TMEM
-    uint64_t* bar_sdp_free = bars + 5;        // S, dP pulled into registers by every softmax thread
-    uint64_t* bar_p_full = bars + 6;          // P, dS' written to smem
+    // 32-bit shared-space addresses throughout (no generic -> shared conversions in the loops)
+    const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sK = smem;
+    const uint32_t sV = sK + TILE;
+    const uint32_t sQ = sV + TILE;                  // [NBUF_Q][TILE]
+    const uint32_t sdO = sQ + NBUF_Q * TILE;        // [NBUF_Q][TILE]
+    const uint32_t sP = sdO + NBUF_Q * TILE;        // [NBUF_P][PBYTES]
+    const uint32_t sdS = sP + NBUF_P * PBYTES;      // [NBUF_P][PBYTES]
+    const uint32_t bars = sdS + NBUF_P * PBYTES;
+    const uint32_t bar_kv = bars;                   // K, V landed
+    const uint32_t bar_load = bars + 8;             // [3] Q, dO tile landed
+    const uint32_t bar_s_full = bars + 32;          // S, dP complete in TMEM
+    const uint32_t bar_sdp_free = bars + 40;        // S, dP pulled into registers by every softmax thread
+    const uint32_t bar_p_full = bars + 48;          // P, dS' written to smem
     // one barrier per dQ buffer: a waiter may then lag a whole tile behind without meeting the phase parity again
-    uint64_t* bar_dq_full = bars + 7;         // [2] dV, dK, dQ MMAs of the tile complete
-    uint64_t* bar_dq_free = bars + 9;         // [2] dQ buffer drained from TMEM
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+    const uint32_t bar_dq_full = bars + 56;         // [2] dV, dK, dQ MMAs of the tile complete
+    const uint32_t bar_dq_free = bars + 72;         // [2] dQ buffer drained from TMEM
+    const uint32_t tmem_slot = bars + 88;
 
     const int E = H * D;
     const int kb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -86,43 +93,49 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     if (warp == TCB_SM_WARPS && lane == 0) {
         tma_prefetch_desc(&tm_qkv);
         tma_prefetch_desc(&tm_do);
-        mbar_init(bar_kv, 1);
-        for (int i = 0; i < 3; ++i) mbar_init(&bar_load[i], 1);
-        mbar_init(bar_s_full, 1);
-        mbar_init(bar_sdp_free, TCB_SM_WARPS * 32);
-        mbar_init(bar_p_full, TCB_SM_WARPS * 32);
+        mbar_init_a(bar_kv, 1);
+        for (int i = 0; i < 3; ++i) mbar_init_a(bar_load + 8 * i, 1);
+        mbar_init_a(bar_s_full, 1);
+        mbar_init_a(bar_sdp_free, TCB_SM_WARPS * 32);
+        mbar_init_a(bar_p_full, TCB_SM_WARPS * 32);
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&bar_dq_full[i], 1);
-            mbar_init(&bar_dq_free[i], TCB_SM_WARPS * 32);
+            mbar_init_a(bar_dq_full + 8 * i, 1);
+            mbar_init_a(bar_dq_free + 8 * i, TCB_SM_WARPS * 32);
         }
         mbar_fence_init();
     }
-    if (warp == TCB_SM_WARPS + 1) tmem_alloc<512>(tmem_slot);
+    if (warp == TCB_SM_WARPS + 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
+    uint32_t tmem;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot) : "memory");
     const int row_base = b * T;                            // first row of this sequence in the [B*T, ...] tensors
 
-    if (warp == TCB_SM_WARPS) {
+    if (warp >= TCB_SM_WARPS) {
+      setmaxnreg_dec<TCB_CONTROL_REGS>();
+      if (warp == TCB_SM_WARPS) {
         // ===================== control warp: TMA producer + MMA issuer =====================
         if (elect_one()) {
             constexpr uint32_t IDESC_S = umma_idesc_bf16(128, 128, 0, 0);     // Q K^T, dO V^T
             constexpr uint32_t IDESC_T = umma_idesc_bf16(128, D, 1, 1);       // P^T dO, dS^T Q
             constexpr uint32_t IDESC_Q = umma_idesc_bf16(128, D, 0, 1);       // dS K
-            const uint32_t aK = smem_u32(sK), aV = smem_u32(sV);
+            const uint32_t aK = sK, aV = sV;
             auto load_tile = [&](int t) {
                 const int buf = t % NBUF_Q;
                 const int y = row_base + (kb + t) * TCB_TILE;
-                mbar_expect_tx(&bar_load[buf], 2 * TILE);
-                tma_load_2d(sQ + buf * TILE, &tm_qkv, &bar_load[buf], h * D, y);
-                tma_load_2d(sdO + buf * TILE, &tm_do, &bar_load[buf], h * D, y);
+                mbar_expect_tx_a(bar_load + 8 * buf, 2 * TILE);
+                tma_load_2d_a(sQ + buf * TILE, &tm_qkv, bar_load + 8 * buf, h * D, y);
+                tma_load_2d_a(sdO + buf * TILE, &tm_do, bar_load + 8 * buf, h * D, y);
             };
             auto issue_s_dp = [&](int t) {
                 const int buf = t % NBUF_Q;
-                mbar_wait(&bar_load[buf], (t / NBUF_Q) & 1);
+                mbar_wait_a(bar_load + 8 * buf, (t / NBUF_Q) & 1);
                 tc_fence_after();
-                const uint32_t aQ = smem_u32(sQ + buf * TILE), aO = smem_u32(sdO + buf * TILE);
+                const uint32_t aQ = sQ + buf * TILE, aO = sdO + buf * TILE;
                 // K-major operands, d_h/16 k-steps of 32 bytes inside the swizzle row
 #pragma unroll
                 for (int ks = 0; ks < D / 16; ++ks)
@@ -132,33 +145,33 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
                 for (int ks = 0; ks < D / 16; ++ks)
                     umma_bf16(tmem + COL_DP, umma_smem_desc(aO + ks * 32, 16, 8 * RB, LT),
                               umma_smem_desc(aV + ks * 32, 16, 8 * RB, LT), IDESC_S, ks > 0 ? 1u : 0u);
-                umma_commit(bar_s_full);
+                umma_commit_a(bar_s_full);
             };
-            mbar_expect_tx(bar_kv, 2 * TILE);
-            tma_load_2d(sK, &tm_qkv, bar_kv, E + h * D, row_base + k0);
-            tma_load_2d(sV, &tm_qkv, bar_kv, 2 * E + h * D, row_base + k0);
+            mbar_expect_tx_a(bar_kv, 2 * TILE);
+            tma_load_2d_a(sK, &tm_qkv, bar_kv, E + h * D, row_base + k0);
+            tma_load_2d_a(sV, &tm_qkv, bar_kv, 2 * E + h * D, row_base + k0);
             load_tile(0);
             if (NBUF_Q == 3 && ntiles > 1) load_tile(1);
-            mbar_wait(bar_kv, 0);
+            mbar_wait_a(bar_kv, 0);
             issue_s_dp(0);
             for (int it = 0; it < ntiles; ++it) {
                 // the ring slot of tile it + NBUF_Q - 1 was last read by the MMAs of tile it - 1
-                if (it >= 1) mbar_wait(&bar_dq_full[(it - 1) & 1], ((it - 1) >> 1) & 1);
+                if (it >= 1) mbar_wait_a(bar_dq_full + 8 * ((it - 1) & 1), ((it - 1) >> 1) & 1);
                 if (it + NBUF_Q - 1 < ntiles) load_tile(it + NBUF_Q - 1);
                 if (it + 1 < ntiles) {
-                    mbar_wait(bar_sdp_free, it & 1);       // S/dP(it) are in registers: TMEM columns reusable
+                    mbar_wait_a(bar_sdp_free, it & 1);     // S/dP(it) are in registers: TMEM columns reusable
                     tc_fence_after();
                     issue_s_dp(it + 1);
                 }
-                mbar_wait(bar_p_full, it & 1);
+                mbar_wait_a(bar_p_full, it & 1);
                 tc_fence_after();
                 if (it >= 2) {
-                    mbar_wait(&bar_dq_free[it & 1], ((it - 2) >> 1) & 1);  // tile it - 2 drained from this dQ buffer
+                    mbar_wait_a(bar_dq_free + 8 * (it & 1), ((it - 2) >> 1) & 1);  // tile it - 2 drained from this dQ buffer
                     tc_fence_after();
                 }
                 const int buf = it % NBUF_Q;
-                const uint32_t aQ = smem_u32(sQ + buf * TILE), aO = smem_u32(sdO + buf * TILE);
-                const uint32_t aP = smem_u32(sP + (it % NBUF_P) * PBYTES), aS = smem_u32(sdS + (it % NBUF_P) * PBYTES);
+                const uint32_t aQ = sQ + buf * TILE, aO = sdO + buf * TILE;
+                const uint32_t aP = sP + (it % NBUF_P) * PBYTES, aS = sdS + (it % NBUF_P) * PBYTES;
                 // dV += P^T dO, dK += dS'^T Q : A = smem tile read MN-major (M = keys), K = 128 query rows
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks)
@@ -173,11 +186,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
                 for (int ks = 0; ks < 8; ++ks)
                     umma_bf16(tmem + COL_DQ + (it & 1) * D, umma_smem_desc(aS + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024, 2u),
                               umma_smem_desc(aK + ks * 16 * RB, 128 * RB, 8 * RB, LT), IDESC_Q, ks > 0 ? 1u : 0u);
-                umma_commit(&bar_dq_full[it & 1]);
+                umma_commit_a(bar_dq_full + 8 * (it & 1));
             }
         }
-    } else if (warp < TCB_SM_WARPS) {
+      }
+    } else {
         // ===================== softmax warps =====================
+        setmaxnreg_inc<TCB_SOFTMAX_REGS>();
         const int quad = warp & 3;                    // TMEM lane quadrant = 32-row band of the tile
         const int cq = warp >> 2;                     // which TCB_CPT-column slice of the 128 keys
         const int r = quad * 32 + lane;               // row inside the tile
@@ -198,7 +213,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
             constexpr int DC = D / 4;
             const int row_g = (kb + t) * TCB_TILE + r;
             const int buf = t & 1;
-            mbar_wait(&bar_dq_full[buf], (t >> 1) & 1);
+            mbar_wait_a(bar_dq_full + 8 * buf, (t >> 1) & 1);
             tc_fence_after();
             uint32_t v[DC];
             if (DC == 4) tmem_ld4(t_lane + COL_DQ + buf * D + cq * DC, reinterpret_cast<uint32_t(&)[4]>(v));
@@ -215,7 +230,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
                                  : "memory");
             }
             tc_fence_before();
-            mbar_arrive(&bar_dq_free[buf]);
+            mbar_arrive_a(bar_dq_free + 8 * buf);
         };
 
         // per-row softmax statistics are fetched one tile ahead (a global-memory latency per tile otherwise)
@@ -230,11 +245,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
                 lse_next = ok ? glse[row_n] : INFINITY;
                 dl_next = ok ? gdelta[row_n] : 0.f;
             }
-            mbar_wait(bar_s_full, it & 1);
+            mbar_wait_a(bar_s_full, it & 1);
             tc_fence_after();
             const bool diagonal = (it == 0);
-            const uint32_t bp_a = smem_u32(sP) + (it % NBUF_P) * PBYTES;
-            const uint32_t bs_a = smem_u32(sdS) + (it % NBUF_P) * PBYTES;
+            const uint32_t bp_a = sP + (it % NBUF_P) * PBYTES;
+            const uint32_t bs_a = sdS + (it % NBUF_P) * PBYTES;
             uint32_t x = 0;
             if (DROP) x = attn_row_seed(drop_base, static_cast<uint32_t>(row_g), static_cast<uint32_t>(kb)) * drop_jump;
             const uint64_t nlse2 = f2_pack(-lse_r, -lse_r), ndl2 = f2_pack(-dl_r, -dl_r);
@@ -247,7 +262,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
                 tmem_ld_wait();
             }
             tc_fence_before();
-            mbar_arrive(bar_sdp_free);
+            mbar_arrive_a(bar_sdp_free);
 #pragma unroll
             for (int ch = 0; ch < TCB_CPT / 16; ++ch) {
                 const int col0 = cq * TCB_CPT + ch * 16;           // first key column of this chunk (inside the tile)
@@ -297,7 +312,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
                     if (partial) pairs(std::true_type{});
                     else         pairs(std::false_type{});
                 }
-                if (ch == 0 && NBUF_P == 1 && it >= 1) mbar_wait(&bar_dq_full[(it - 1) & 1], ((it - 1) >> 1) & 1);   // single buffer: tile it-1's MMAs must be done
+                if (ch == 0 && NBUF_P == 1 && it >= 1) mbar_wait_a(bar_dq_full + 8 * ((it - 1) & 1), ((it - 1) >> 1) & 1);   // single buffer: tile it-1's MMAs must be done
                 // two 16-byte chunks of this row per tensor; chunk index XOR (row & 7) = SWIZZLE_128B
                 const uint32_t half_off = static_cast<uint32_t>((col0 >> 6) * 16384 + r * 128);
 #pragma unroll
@@ -312,7 +327,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
                 }
             }
             fence_proxy_async_smem();
-            mbar_arrive(bar_p_full);
+            mbar_arrive_a(bar_p_full);
             // dQ of the previous tile: its MMAs were issued a whole tile of softmax work ago
             if (it >= 1) drain_dq(it - 1);
         }

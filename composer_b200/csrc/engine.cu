@@ -926,8 +926,9 @@ int cb200_set_decode_profile(void* counters) {
 }
 
 int cb200_set_attention_fwd_impl(int impl) {
-    CB200_REQUIRE(impl >= 0 && impl <= 2,
-                  "attention forward implementation must be 0 (tcgen05, P in TMEM), 1 (mma.sync) or 2 (tcgen05, P in smem)");
+    CB200_REQUIRE(impl >= 0 && impl <= 4,
+                  "attention forward implementation must be 0 (tcgen05, P in TMEM), 1 (mma.sync), 2 (tcgen05, P in smem) "
+                  "or 3 / 4 (tile-shape variants of 0)");
     attention_set_fwd_impl(impl);
     return 0;
 }

@@ -302,7 +302,8 @@ def _attention_reference(qkv, B, T, H, D, scale, keep=None, rate=0.0):
 
 
 def check_attention(B=2, T=200, H=16, D=16, rate=0.0, backward=True, fwd_impl=0):
-    '''fwd_impl: 0 = tcgen05 with P in TMEM (default), 1 = round-1 mma.sync kernel, 2 = tcgen05 with P through smem.'''
+    '''fwd_impl: 0 = tcgen05 with P in TMEM (default), 1 = round-1 mma.sync kernel, 2 = tcgen05 with P through smem,
+    3 / 4 = tile-shape variants of 0 (d_h 16).'''
     _lib.call('cb200_set_attention_fwd_impl', fwd_impl)
     try:
         return _check_attention(B, T, H, D, rate, backward)
@@ -415,6 +416,11 @@ GROUPS = {
                       lambda: check_attention(6, 1024, 16, 16, backward=False, fwd_impl=2),
                       lambda: check_attention(2, 384, 4, 64, rate=0.1, backward=False, fwd_impl=2),
                       lambda: check_attention(1, 192, 4, 32, rate=0.1, backward=False, fwd_impl=2),
+                      # tile-shape variants of the default (64-key tiles, 3 / 4 CTAs per SM)
+                      lambda: check_attention(2, 200, 16, 16, rate=0.1, backward=False, fwd_impl=3),
+                      lambda: check_attention(6, 1024, 16, 16, rate=0.1, backward=False, fwd_impl=3),
+                      lambda: check_attention(2, 200, 16, 16, rate=0.1, backward=False, fwd_impl=4),
+                      lambda: check_attention(6, 1024, 16, 16, backward=False, fwd_impl=4),
                       lambda: check_attention(2, 200, 16, 16, rate=0.1, backward=False, fwd_impl=1),
                       lambda: check_attention(2, 256, 4, 64, rate=0.1, backward=False, fwd_impl=1),
                       lambda: check_attention(1, 192, 4, 32, rate=0.1, backward=False, fwd_impl=1)],
