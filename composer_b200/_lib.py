@@ -75,6 +75,7 @@ _SIGNATURES = {
     'cb200_attention_bwd': (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_int,
                                     c_f32, c_f32, c_u64, c_u32, c_u32, c_ptr]),
     'cb200_set_attention_fwd_impl': (c_int, [c_int]),
+    'cb200_set_attention_trace': (c_int, [c_ptr]),
     'cb200_set_decode_impl': (c_int, [c_int, c_int, c_int]),
     'cb200_set_decode_profile': (c_int, [c_ptr]),
     'cb200_decode_cluster_capacity': (c_int, [c_ptr, c_int]),

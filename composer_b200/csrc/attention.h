@@ -30,6 +30,9 @@ int attention_bwd_tc_main(const __nv_bfloat16* qkv, const __nv_bfloat16* dout, c
                           float* dq_acc, __nv_bfloat16* dqkv, int B, int T, int H, int D, float scale,
                           const AttnDropKey& key, cudaStream_t s);
 
+// Diagnostic: device buffer (12 x 512 int64) that receives the event timeline of the warps of one backward CTA.
+void attention_set_trace(long long* buffer);
+
 int attention_mask_export(uint8_t* mask, int B, int T, int H, const DropoutParams& drop, uint32_t layer, cudaStream_t s);
 
 }  // namespace cb200

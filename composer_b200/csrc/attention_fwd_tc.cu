@@ -7,8 +7,9 @@
 //
 // Persistent CTAs (two per SM) walk work items (one 128-row query tile of one (batch, head)), heaviest first:
 //   warp 5 (one lane)  TMA producer: Q tile, then the K / V tiles of the item through a ring (SWIZZLE = row bytes)
-//   warp 4 (one lane)  MMA issuer:   S = Q K^T  (tcgen05.mma, M 128 x N KT, fp32 in TMEM, double buffered), issued
-//                                    one tile ahead of the softmax;  O~ = P V  (M 128 x N d_h) once P is ready
+//   warp 4 (one lane)  S issuer:     S = Q K^T  (tcgen05.mma, M 128 x N KT, fp32 in TMEM, double buffered), issued
+//                                    one tile ahead of the softmax
+//   warp 7 (one lane)  P V issuer:   O~ = P V  (M 128 x N d_h) once P is ready
 //   warps 0-3          softmax, thread = query row (TMEM lane): tcgen05.ld of the whole row, running max, exp2 with
 //                      the scale folded into one FFMA2, row sum, dropout, bf16 P written back INTO THE S BUFFER'S
 //                      COLUMNS with tcgen05.st and consumed from there as the A operand (TS form of tcgen05.mma),
@@ -162,58 +163,58 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                 }
             }
         } else if (warp == 4) {
-            // ===================== MMA issuer =====================
+            // ===================== S issuer (runs one tile ahead of the softmax) =====================
+            // Two issuing threads (S here, P V in warp 7): an issuing thread runs alone at one instruction every few
+            // cycles, and with 9 small MMAs per tile that instruction stream is a large part of a tile's critical path.
+            // Descriptors are (lo, hi) words: hi is constant, lo = start address field + constant offsets.
             if (elect_one()) {
                 constexpr uint32_t IDESC_S = umma_idesc_bf16(128, KT, 0, 0);     // Q K^T
-                constexpr uint32_t IDESC_O = umma_idesc_bf16(128, D, 0, 1);      // P V (V is MN-major)
-                auto issue_s = [&](const TcfCursor& c) {
+                constexpr uint32_t HI_T = umma_desc_hi(8 * RB, LT);
+                const uint32_t q_lo = umma_desc_lo(sQ, 16), k_lo = umma_desc_lo(sK, 16);
+                TcfCursor c{static_cast<int>(blockIdx.x), 0, 0, 0, 0, 0, 0};
+                if (c.item < items) setup(c);
+                while (c.item < items) {
                     const int qs = c.it & 1, st = c.g % NKV, buf = c.g & 1;
                     if (c.j == 0) mbar_wait_a(bar_q_full + 8 * qs, (c.it >> 1) & 1);
                     mbar_wait_a(bar_kv_full + 8 * st, (c.g / NKV) & 1);
                     mbar_wait_a(bar_buf_free + 8 * buf, ((c.g >> 1) & 1) ^ 1);
                     tc_fence_after();
-                    const uint32_t aQ = sQ + qs * QTILE, aK = sK + st * KTILE;
+                    const uint32_t aq = q_lo + qs * (QTILE >> 4), ak = k_lo + st * (KTILE >> 4);
 #pragma unroll
                     for (int ks = 0; ks < D / 16; ++ks)
-                        umma_bf16(tmem + buf * BUFC, umma_smem_desc(aQ + ks * 32, 16, 8 * RB, LT),
-                                  umma_smem_desc(aK + ks * 32, 16, 8 * RB, LT), IDESC_S, ks > 0 ? 1u : 0u);
+                        umma_bf16_w(tmem + buf * BUFC, aq + ks * 2, HI_T, ak + ks * 2, HI_T, IDESC_S, ks > 0 ? 1u : 0u);
                     umma_commit_a(bar_s_full + 8 * buf);
                     if (c.j == c.n - 1) umma_commit_a(bar_q_free + 8 * qs);
-                };
-                auto issue_pv = [&](const TcfCursor& c) {
+                    advance(c);
+                }
+            }
+        } else if (warp == 7) {
+            // ===================== P V issuer =====================
+            if (elect_one()) {
+                constexpr uint32_t IDESC_O = umma_idesc_bf16(128, D, 0, 1);      // P V (V is MN-major)
+                constexpr uint32_t HI_T = umma_desc_hi(8 * RB, LT);
+                constexpr uint32_t HI_P = umma_desc_hi(1024, 2u);
+                const uint32_t v_lo = umma_desc_lo(sV, KT * RB), p_lo = umma_desc_lo(sP, 16);
+                TcfCursor c{static_cast<int>(blockIdx.x), 0, 0, 0, 0, 0, 0};
+                if (c.item < items) setup(c);
+                while (c.item < items) {
                     const int st = c.g % NKV, buf = c.g & 1;
+                    mbar_wait_a(bar_kv_full + 8 * st, (c.g / NKV) & 1);          // (long complete: S of the tile used it)
                     mbar_wait_a(bar_p_full + 8 * buf, (c.g >> 1) & 1);
                     tc_fence_after();
-                    const uint32_t aV = sV + st * KTILE;
+                    const uint32_t av = v_lo + st * (KTILE >> 4);
 #pragma unroll
                     for (int ks = 0; ks < KT / 16; ++ks) {
-                        const uint64_t dv = umma_smem_desc(aV + ks * 16 * RB, KT * RB, 8 * RB, LT);
-                        if (PSMEM) {
-                            const uint32_t aP = sP + buf * C::PBYTES;
-                            umma_bf16(tmem + buf * BUFC + COL_O,
-                                      umma_smem_desc(aP + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024, 2u), dv, IDESC_O,
-                                      ks > 0 ? 1u : 0u);
-                        } else {
-                            umma_bf16_ts(tmem + buf * BUFC + COL_O, tmem + buf * BUFC + ks * 8, dv, IDESC_O, ks > 0 ? 1u : 0u);
-                        }
+                        if (PSMEM)
+                            umma_bf16_w(tmem + buf * BUFC + COL_O, p_lo + buf * (C::PBYTES >> 4) + (ks >> 2) * (16384 >> 4) + (ks & 3) * 2,
+                                        HI_P, av + ks * (16 * RB >> 4), HI_T, IDESC_O, ks > 0 ? 1u : 0u);
+                        else
+                            umma_bf16_ts_w(tmem + buf * BUFC + COL_O, tmem + buf * BUFC + ks * 8, av + ks * (16 * RB >> 4), HI_T,
+                                           IDESC_O, ks > 0 ? 1u : 0u);
                     }
                     umma_commit_a(bar_o_full + 8 * buf);
                     umma_commit_a(bar_kv_free + 8 * st);
-                };
-                TcfCursor cs{static_cast<int>(blockIdx.x), 0, 0, 0, 0, 0, 0};
-                if (cs.item < items) setup(cs);
-                TcfCursor cp = cs;
-                if (cs.item < items) {
-                    issue_s(cs);
-                    advance(cs);
-                }
-                while (cp.item < items) {
-                    if (cs.item < items) {
-                        issue_s(cs);                        // S runs one tile ahead of the softmax
-                        advance(cs);
-                    }
-                    issue_pv(cp);
-                    advance(cp);
+                    advance(c);
                 }
             }
         }

@@ -518,6 +518,40 @@ __device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t smem_addr, uin
     return umma_smem_desc(smem_addr, lbo_bytes, sbo_bytes, 2u);
 }
 
+// The same descriptor as two 32-bit words.  Only the start-address field (bits 0-13 of the low word) changes
+// between the MMAs of a loop, so an issuing thread keeps `lo` words of its buffers in registers and adds
+// (byte offset >> 4) per k-step: one integer add per operand instead of re-encoding the descriptor (the issuing
+// thread executes alone at one instruction every few cycles, and a kernel with many small MMAs per tile is bound by
+// that instruction stream, see DESIGN.md "Attention").  No carry leaves the field: shared addresses are < 2^18.
+__host__ __device__ constexpr uint32_t umma_desc_hi(uint32_t sbo_bytes, uint32_t layout_type) {
+    return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (layout_type << 29);
+}
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+    return ((smem_addr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ void umma_bf16_w(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                            uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// A operand in TMEM (TS form), B descriptor as two words.
+__device__ __forceinline__ void umma_bf16_ts_w(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t b_hi,
+                                               uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
 // Swizzle mode whose span equals a row of `row_bytes` (32, 64 or 128) bytes.
 __host__ __device__ constexpr uint32_t umma_layout_for_row_bytes(int row_bytes) {
     return row_bytes == 128 ? 2u : row_bytes == 64 ? 4u : 6u;

@@ -933,6 +933,11 @@ int cb200_set_attention_fwd_impl(int impl) {
     return 0;
 }
 
+int cb200_set_attention_trace(void* buffer) {
+    attention_set_trace(static_cast<long long*>(buffer));
+    return 0;
+}
+
 int cb200_attention_dropout_mask(uint8_t* mask, int B, int T, int H, float dropout_rate, uint64_t seed, uint32_t step,
                                  uint32_t layer, void* stream) {
     return attention_mask_export(mask, B, T, H, make_dropout(dropout_rate, seed, step, dropout_rate > 0.f), layer,

@@ -155,6 +155,9 @@ int cb200_attention_bwd(const void* qkv, const void* out, const void* dout, cons
  * TMEM and consumed by a TS-form MMA (default); 1 = warp-level mma.sync (round 1; kept for A/B measurements and as
  * a cross-check in the tests); 2 = tcgen05 / TMEM with the probabilities staged through shared memory. */
 int cb200_set_attention_fwd_impl(int impl);
+/* Diagnostic: device buffer of 12 x 512 int64 that receives the event timeline ((event << 40) | SM clock; word 0 of
+ * each 512-word region = number of events) of every warp of one CTA of the attention backward kernel.  NULL disables. */
+int cb200_set_attention_trace(void* buffer);
 /* Selects how cb200_generate runs: 0 (default) = one persistent thread-block-cluster kernel for the whole
  * generation when the shape allows it (embedding_size 256 or 512, heads a multiple of 4), 1 = one CUDA graph
  * of per-layer kernels per step.  max_clusters > 0 caps the clusters of the persistent kernel (tests);
