@@ -6,6 +6,7 @@ library only needs the CUDA runtime.
     python -m composer_b200.build [--force]
 '''
 
+import hashlib
 import os
 import subprocess
 import sys
@@ -15,6 +16,7 @@ PACKAGE_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PACKAGE_DIR, 'csrc')
 BUILD_DIR = os.path.join(PACKAGE_DIR, 'build')
 LIBRARY = os.path.join(PACKAGE_DIR, 'libcomposer_b200.so')
+STAMP = LIBRARY + '.sha256'          # hash of the sources the library was built from (travels with it)
 SOURCES = ['gemm.cu', 'elementwise.cu', 'attention.cu', 'attention_fwd_tc.cu', 'attention_tc.cu', 'decode.cu', 'decode_mega.cu', 'engine.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']
@@ -27,18 +29,33 @@ def _nvcc():
     return 'nvcc'
 
 
-def _newest_dependency():
-    newest = 0.0
+def source_hash():
+    '''SHA-256 over every file the library is built from (csrc/, include/) and the compiler flags.'''
+
+    digest = hashlib.sha256(' '.join(NVCC_FLAGS + SOURCES).encode())
     for root in (CSRC, os.path.join(os.path.dirname(PACKAGE_DIR), 'include')):
-        for name in os.listdir(root):
-            newest = max(newest, os.path.getmtime(os.path.join(root, name)))
-    return newest
+        for name in sorted(os.listdir(root)):
+            path = os.path.join(root, name)
+            if os.path.isfile(path):
+                digest.update(name.encode())
+                with open(path, 'rb') as handle:
+                    digest.update(handle.read())
+    return digest.hexdigest()
+
+
+def is_current():
+    '''True when the library exists and was built from exactly the sources in the tree (hash, not mtime).'''
+
+    if not (os.path.exists(LIBRARY) and os.path.exists(STAMP)):
+        return False
+    with open(STAMP) as handle:
+        return handle.read().strip() == source_hash()
 
 
 def build(force=False, verbose=False):
     '''Compiles every .cu for sm_100a and links the shared library. Returns its path.'''
 
-    if not force and os.path.exists(LIBRARY) and os.path.getmtime(LIBRARY) >= _newest_dependency():
+    if not force and is_current():
         return LIBRARY
 
     os.makedirs(BUILD_DIR, exist_ok=True)
@@ -61,6 +78,8 @@ def build(force=False, verbose=False):
     result = subprocess.run(cmd, capture_output=True, text=True)
     if result.returncode != 0:
         raise RuntimeError('link failed:\n%s\n%s' % (result.stdout, result.stderr))
+    with open(STAMP, 'w') as handle:
+        handle.write(source_hash() + '\n')
     return LIBRARY
 
 
