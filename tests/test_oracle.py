@@ -149,3 +149,96 @@ def test_oracle_matches_tf_reference():
     first_undecided = np.where(~decided.all(axis=0))[0]
     upto = int(first_undecided[0]) if first_undecided.size else steps
     assert (ids[:, :upto] == data['decode_ids'][:, :upto]).all()
+
+
+# ---------------------------------------------------------------------------
+# Pin: the oracle against the reference's own transformer.py (executed under tests/golden/tf_shim.py)
+# ---------------------------------------------------------------------------
+
+def _golden_case(name):
+    import os
+    import sys
+    golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+    if golden not in sys.path:
+        sys.path.insert(0, golden)
+    import model_cases
+    data = np.load(os.path.join(golden, 'model_golden.npz'))
+    index = list(model_cases.CASES).index(name)
+    case = model_cases.CASES[name]
+    cfg = model_cases.case_config(oracle, case)
+    weights = model_cases.case_weights(oracle, cfg, 10 + index)
+    batches = model_cases.case_batches(case, 10 + index)
+    return case, cfg, weights, batches, {k[len(name) + 1:]: data[k] for k in data.files if k.startswith(name + '/')}
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize('name', ['small', 'no_layernorm_no_scale', 'default_heads'])
+def test_oracle_matches_reference_transformer(name):
+    '''
+    ``tests/golden/model_golden.npz`` holds what the reference's own ``Transformer`` (composer/models/transformer.py,
+    unmodified) computed for these weights and ids: ``call`` logits and presents, greedy ``past=`` decoding, and
+    the losses / accuracies / gradients / final variables of its own ``train`` loop.  The oracle must reproduce all
+    of it in fp64 (the fixture keeps gradients and variables in fp32, hence 1e-6 there).
+    '''
+
+    case, cfg, weights, batches, golden = _golden_case(name)
+    x0, y0 = batches[0]
+    params = oracle.to_torch(weights, torch.float64)
+    logits, presents = oracle.transformer_call(params, x0, cfg)
+    np.testing.assert_allclose(logits.numpy(), golden['logits'], rtol=0, atol=1e-11)
+    ours = np.stack([np.stack([p[0].numpy(), p[1].numpy()]) if isinstance(p, (tuple, list)) else p.numpy()
+                     for p in presents])
+    np.testing.assert_allclose(ours, golden['presents'], rtol=0, atol=1e-6)
+
+    steps = golden['decode_ids'].shape[1]
+    ids, step_logits = oracle.generate(weights, x0[:, :case['prompt']], steps, cfg, greedy=True)
+    np.testing.assert_allclose(step_logits, golden['decode_logits'], rtol=0, atol=1e-10)
+    assert (ids == golden['decode_ids']).all()
+
+    # the reference's train loop: per-step loss and accuracy, first-step gradients, variables after the last step
+    current = type(weights)((k, np.asarray(v, dtype=np.float64)) for k, v in weights.items())
+    adam = oracle.AdamState(current)
+    for step, (x, y) in enumerate(batches):
+        loss, accuracy, _, grads = oracle.loss_and_gradients(current, x, y, cfg)
+        assert abs(loss - golden['step_loss'][step]) < 1e-11
+        assert abs(accuracy - golden['step_accuracy'][step]) < 1e-12
+        if step == 0:
+            for variable in weights:
+                key = 'grad/' + variable
+                if key in golden:
+                    np.testing.assert_allclose(grads[variable], golden[key], rtol=2e-6, atol=1e-9, err_msg=variable)
+                else:   # never built by the reference (ln_1 / ln_2 without LayerNorm): no gradient here either
+                    assert '/ln_' in variable and not np.any(grads[variable])
+        current = adam.apply(current, grads)
+    for variable in weights:
+        if 'trained/' + variable in golden:
+            np.testing.assert_allclose(current[variable], golden['trained/' + variable], rtol=0, atol=2e-7,
+                                       err_msg=variable)
+            # the update itself (3e-3 per step) must agree, not just the weights it is added to
+            np.testing.assert_allclose(current[variable] - weights[variable],
+                                       golden['trained/' + variable] - weights[variable], rtol=0, atol=3e-7)
+
+
+def test_model_golden_is_what_the_reference_computes():
+    '''Where /root/reference exists: re-run the reference's transformer.py under the shim, compare with the fixture.'''
+
+    import os
+    import sys
+    golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+    if golden not in sys.path:
+        sys.path.insert(0, golden)
+    from reference_shims import load_reference_transformer
+    loaded = load_reference_transformer()
+    if loaded is None:
+        pytest.skip('the reference tree is not available here')
+    reference, _ = loaded
+    import make_model_golden
+    case, cfg, weights, batches, golden_case = _golden_case('small')
+    model, _ = make_model_golden.build_reference_model(reference, case, weights)
+    logits, presents = model(batches[0][0])
+    np.testing.assert_allclose(logits.numpy(), golden_case['logits'], rtol=0, atol=1e-12)
+    assert type(model).__module__ == 'composer.models.transformer'
+    assert os.path.realpath(sys.modules['composer.models.transformer'].__file__).startswith(
+        os.path.realpath(os.environ.get('COMPOSER_REFERENCE_ROOT', '/root/reference')))
