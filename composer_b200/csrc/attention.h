@@ -32,6 +32,7 @@ int attention_bwd_tc_main(const __nv_bfloat16* qkv, const __nv_bfloat16* dout, c
 
 // Diagnostic: device buffer (12 x 512 int64) that receives the event timeline of the warps of one backward CTA.
 void attention_set_trace(long long* buffer);
+long long* attention_get_trace();
 
 int attention_mask_export(uint8_t* mask, int B, int T, int H, const DropoutParams& drop, uint32_t layer, cudaStream_t s);
 

@@ -63,11 +63,12 @@ struct TcfCursor {
     int item, it, qi, bh, j, n, g;   // it: ordinal of the item in this CTA; n: tiles of the item; g: tiles so far
 };
 
-template <int D, bool DROP, bool PSMEM, int KT_, int CPS_>
+// ABL: timing-only ablations (results wrong): 1 no max pass, 2 no MUFU (multiply instead), 4 no P store, 8 no O~ load
+template <int D, bool DROP, bool PSMEM, int KT_, int CPS_, int ABL = 0>
 __global__ void __launch_bounds__(TCF_THREADS, CPS_)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                    __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int T, int H, int BH, int nq,
-                   float scale_log2, AttnDropKey drop) {
+                   float scale_log2, AttnDropKey drop, long long* __restrict__ trace) {
     using C = TcfCfg<D, PSMEM, KT_, CPS_>;
     constexpr int KT = C::KT, RB = C::RB, QTILE = C::QTILE, KTILE = C::KTILE, NKV = C::NKV, NCH = KT / 32;
     constexpr uint32_t LT = umma_layout_for_row_bytes(RB);
@@ -95,6 +96,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     const int items = nq * BH;
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+
+    // Diagnostic timeline (cb200_set_attention_trace): lane 0 of every warp of CTA 0 appends (event << 40 | clock) words
+    long long* tr = (trace != nullptr && blockIdx.x == 0 && lane == 0) ? trace + warp * 512 : nullptr;
+    int tr_n = 0;
+    auto TR = [&](int ev) {
+        if (tr != nullptr && tr_n < 511) tr[++tr_n] = (static_cast<long long>(ev) << 40) | (clock64() & 0xFFFFFFFFFFll);
+    };
+    TR(1);
 
     if (warp == 4 && lane == 0) {
         tma_prefetch_desc(&tm_q);
@@ -179,12 +188,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                     mbar_wait_a(bar_kv_full + 8 * st, (c.g / NKV) & 1);
                     mbar_wait_a(bar_buf_free + 8 * buf, ((c.g >> 1) & 1) ^ 1);
                     tc_fence_after();
+                    TR(10);
                     const uint32_t aq = q_lo + qs * (QTILE >> 4), ak = k_lo + st * (KTILE >> 4);
 #pragma unroll
                     for (int ks = 0; ks < D / 16; ++ks)
                         umma_bf16_w(tmem + buf * BUFC, aq + ks * 2, HI_T, ak + ks * 2, HI_T, IDESC_S, ks > 0 ? 1u : 0u);
                     umma_commit_a(bar_s_full + 8 * buf);
                     if (c.j == c.n - 1) umma_commit_a(bar_q_free + 8 * qs);
+                    TR(11);
                     advance(c);
                 }
             }
@@ -202,6 +213,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                     mbar_wait_a(bar_kv_full + 8 * st, (c.g / NKV) & 1);          // (long complete: S of the tile used it)
                     mbar_wait_a(bar_p_full + 8 * buf, (c.g >> 1) & 1);
                     tc_fence_after();
+                    TR(20);
                     const uint32_t av = v_lo + st * (KTILE >> 4);
 #pragma unroll
                     for (int ks = 0; ks < KT / 16; ++ks) {
@@ -214,6 +226,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                     }
                     umma_commit_a(bar_o_full + 8 * buf);
                     umma_commit_a(bar_kv_free + 8 * st);
+                    TR(21);
                     advance(c);
                 }
             }
@@ -243,10 +256,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                 const int pb = gp & 1;
                 mbar_wait_a(bar_o_full + 8 * pb, (gp >> 1) & 1);
                 tc_fence_after();
+                TR(35);
 #pragma unroll
                 for (int d0 = 0; d0 < D; d0 += 16) {
                     uint32_t op[16];
-                    tmem_ld16(t_lane + pb * BUFC + COL_O + d0, op);
+                    if (!(ABL & 8)) tmem_ld16(t_lane + pb * BUFC + COL_O + d0, op);
                     tmem_ld_wait();
 #pragma unroll
                     for (int d = 0; d < 16; ++d) o_acc[d0 + d] = fmaf(o_acc[d0 + d], alpha_prev, __uint_as_float(op[d]));
@@ -260,11 +274,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                 const uint32_t tbuf = t_lane + buf * BUFC;
                 mbar_wait_a(bar_s_full + 8 * buf, (g >> 1) & 1);
                 tc_fence_after();
+                TR(30);
                 uint32_t s[KT];
 #pragma unroll
                 for (int c = 0; c < NCH; ++c) tmem_ld32(tbuf + 32 * c, *reinterpret_cast<uint32_t(*)[32]>(&s[32 * c]));
                 if (j > 0) fold_o(g - 1);                   // (its tcgen05.wait::ld also covers the S loads above)
                 else tmem_ld_wait();
+                TR(31);
 
                 const int key0 = j * KT;
                 const bool diag = key0 + KT - 1 > qi * 128;  // some key of the tile lies above some row of the q tile
@@ -282,7 +298,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                     // ---- running max ----
                     float mx0 = m_run, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-                    for (int c = 0; c < NCH; ++c) {
+                    for (int c = 0; c < ((ABL & 1) ? 0 : NCH); ++c) {
                         const int kmin = key0 + 32 * c;
                         if (MASKED && kmin > rmax) continue;
                         if (MASKED && kmin + 31 > rmin) {
@@ -298,9 +314,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                             mx3 = fmax3f(mx3, __uint_as_float(s[32 * c + i + 6]), __uint_as_float(s[32 * c + i + 7]));
                         }
                     }
-                    const float m_new = fmaxf(fmax3f(mx0, mx1, mx2), mx3);
+                    float m_new = fmaxf(fmax3f(mx0, mx1, mx2), mx3);
+                    if (ABL & 1) m_new = 8.f;
                     alpha = fast_exp2((m_run - m_new) * scale_log2);   // first tile: exp2(-inf) = 0
                     m_run = m_new;
+                    TR(32);
                     const float nmc = -m_new * scale_log2;
                     const uint64_t n2 = f2_pack(nmc, nmc);
                     // ---- P = exp2(S c - m c), row sum (before dropout), dropout, bf16 ----
@@ -317,7 +335,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                                 const uint64_t t2 = f2_fma(f2_pack(s[32 * c + 2 * q], s[32 * c + 2 * q + 1]), c2, n2);
                                 float t0, t1;
                                 f2_unpack(t2, t0, t1);
-                                float p0 = fast_exp2(t0), p1 = fast_exp2(t1);
+                                float p0 = (ABL & 2) ? t0 * 0.001f : fast_exp2(t0), p1 = (ABL & 2) ? t1 * 0.001f : fast_exp2(t1);
                                 uint64_t p2 = f2_pack(p0, p1);
                                 if (q & 1) sum_b = f2_add(sum_b, p2);
                                 else       sum_a = f2_add(sum_a, p2);
@@ -340,7 +358,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                                              "r"(pk[4 * q4 + 1]), "r"(pk[4 * q4 + 2]), "r"(pk[4 * q4 + 3]) : "memory");
                             }
                         } else {
-                            tmem_st16(tbuf + 16 * c, pk);
+                            if (!(ABL & 4)) tmem_st16(tbuf + 16 * c, pk);
+                            else asm volatile("" ::"r"(pk[0] ^ pk[5] ^ pk[10] ^ pk[15]));
                         }
                     }
                 };
@@ -353,10 +372,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                 if (PSMEM) {
                     fence_proxy_async_smem();
                 } else {
+                    TR(33);
                     tmem_st_wait();
                     tc_fence_before();
                 }
                 mbar_arrive_a(bar_p_full + 8 * buf);
+                TR(34);
                 alpha_prev = alpha;
             }
             fold_o(g - 1);
@@ -379,6 +400,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         }
     }
 
+    if (tr != nullptr) tr[0] = tr_n;
     tc_fence_before();
     __syncthreads();
     if (warp == 6) {
@@ -387,7 +409,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     }
 }
 
-template <int D, bool DROP, bool PSMEM, int KT, int CPS>
+template <int D, bool DROP, bool PSMEM, int KT, int CPS, int ABL = 0>
 static int launch_fwd_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse, int B, int T, int H, float scale,
                          const AttnDropKey& key, cudaStream_t s) {
     using C = TcfCfg<D, PSMEM, KT, CPS>;
@@ -398,7 +420,7 @@ static int launch_fwd_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* ls
     if (rc) return rc;
     rc = make_tmap_bf16_sw(&tm_kv, qkv, 3 * E, static_cast<uint64_t>(B) * T, 3 * E, D, C::KT, C::RB);
     if (rc) return rc;
-    auto kernel = attn_fwd_tc_kernel<D, DROP, PSMEM, KT, CPS>;
+    auto kernel = attn_fwd_tc_kernel<D, DROP, PSMEM, KT, CPS, ABL>;
     static bool configured = false;
     if (!configured) {
         CB200_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -412,7 +434,7 @@ static int launch_fwd_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* ls
     long long grid = static_cast<long long>(per_sm) * device_sm_count();
     if (grid > items) grid = items;
     kernel<<<static_cast<int>(grid), TCF_THREADS, smem, s>>>(tm_q, tm_kv, out, lse, T, H, B * H, nq,
-                                                              scale * 1.4426950408889634f, key);
+                                                              scale * 1.4426950408889634f, key, attention_get_trace());
     CB200_CUDA_OK(cudaGetLastError());
     note_launch(1);
     return 0;
@@ -438,6 +460,17 @@ int attention_fwd_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse, i
         case 16:
             if (variant == 3) return launch_fwd_tc_d<16, 64, 3>(qkv, out, lse, B, T, H, scale, key, false, s);
             if (variant == 4) return launch_fwd_tc_d<16, 64, 4>(qkv, out, lse, B, T, H, scale, key, false, s);
+            if (variant >= 100) {   // timing-only ablations of the default shape, dropout off
+                switch (variant - 100) {
+                    case 1: return launch_fwd_tc<16, false, false, 128, 2, 1>(qkv, out, lse, B, T, H, scale, key, s);
+                    case 2: return launch_fwd_tc<16, false, false, 128, 2, 2>(qkv, out, lse, B, T, H, scale, key, s);
+                    case 3: return launch_fwd_tc<16, false, false, 128, 2, 3>(qkv, out, lse, B, T, H, scale, key, s);
+                    case 4: return launch_fwd_tc<16, false, false, 128, 2, 4>(qkv, out, lse, B, T, H, scale, key, s);
+                    case 8: return launch_fwd_tc<16, false, false, 128, 2, 8>(qkv, out, lse, B, T, H, scale, key, s);
+                    case 15: return launch_fwd_tc<16, false, false, 128, 2, 15>(qkv, out, lse, B, T, H, scale, key, s);
+                    default: break;
+                }
+            }
             return launch_fwd_tc_d<16, 128, 2>(qkv, out, lse, B, T, H, scale, key, psmem, s);
         case 32: return launch_fwd_tc_d<32, 64, 2>(qkv, out, lse, B, T, H, scale, key, psmem, s);
         case 64: return launch_fwd_tc_d<64, 64, 2>(qkv, out, lse, B, T, H, scale, key, psmem, s);

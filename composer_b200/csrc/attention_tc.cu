@@ -26,6 +26,7 @@ namespace cb200 {
 
 static long long* g_attention_trace = nullptr;   // device buffer of 12 x 512 words, see the kernel
 void attention_set_trace(long long* buffer) { g_attention_trace = buffer; }
+long long* attention_get_trace() { return g_attention_trace; }
 
 constexpr int TCB_SM_WARPS = 8;                        // softmax warps: 4 row bands x 2 column slices of a 64-key half
 constexpr int TCB_THREADS = (TCB_SM_WARPS + 4) * 32;   // + one warpgroup of issuing warps: loads + S/dP, dV (+ TMEM alloc), dK, dQ
