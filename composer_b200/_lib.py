@@ -58,6 +58,9 @@ _SIGNATURES = {
     'cb200_decode_workspace_bytes': (c_i64, [c_ptr, c_int]),
     'cb200_generate': (c_int, [c_ptr, c_ptr, c_int, c_ptr, c_i64, c_ptr, c_int, c_int, c_int, c_f32, c_u64, c_i64,
                                c_ptr, c_ptr, c_ptr, c_ptr]),
+    'cb200_prefill': (c_int, [c_ptr, c_ptr, c_int, c_int, c_ptr, c_int, c_ptr, c_ptr]),
+    'cb200_decode_step': (c_int, [c_ptr, c_ptr, c_int, c_ptr, c_i64, c_ptr, c_int, c_int, c_ptr, c_ptr]),
+    'cb200_set_decode_prefill': (c_int, [c_int]),
     'cb200_gemm': (c_int, [c_int, c_int, c_int, c_int, c_ptr, c_int, c_ptr, c_int, c_ptr, c_ptr, c_int, c_ptr, c_int,
                            c_ptr, c_int, c_ptr, c_int, c_f32, c_u64, c_u32, c_u32, c_u32, c_ptr]),
     'cb200_logits_ce': (c_int, [c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_f32, c_ptr, c_ptr, c_ptr,

@@ -173,6 +173,38 @@ decode_embed_kernel(const int32_t* __restrict__ cur, const float* __restrict__ w
     }
 }
 
+// ---- batched prefill: k, v of T prompt tokens from the c_attn output into the per-step cache layout ----
+// qkv: [B * T, 3E] (q | k | v thirds, head h at columns h D); kcache / vcache: [B, H, t_max, D] of one layer
+// (transformer.py:419-426: split_heads of key and value, i.e. the reference's `present` for positions 0 .. T-1).
+// One thread per 16-byte piece.
+__global__ void __launch_bounds__(256)
+kv_export_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ kcache,
+                 __nv_bfloat16* __restrict__ vcache, int B, int T, int H, int D, int t_max) {
+    const int pieces = D / 8, E = H * D;
+    const size_t n = static_cast<size_t>(B) * T * H * pieces * 2;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        size_t r = i;
+        const int c = static_cast<int>(r % pieces); r /= pieces;
+        const int h = static_cast<int>(r % H); r /= H;
+        const int kv = static_cast<int>(r & 1); r >>= 1;
+        const int t = static_cast<int>(r % T);
+        const int b = static_cast<int>(r / T);
+        const uint4 val = *reinterpret_cast<const uint4*>(qkv + (static_cast<size_t>(b) * T + t) * 3 * E + (1 + kv) * E + h * D + c * 8);
+        __nv_bfloat16* dst = (kv ? vcache : kcache) + ((static_cast<size_t>(b) * H + h) * t_max + t) * D + c * 8;
+        *reinterpret_cast<uint4*>(dst) = val;
+    }
+}
+
+int kv_export(const __nv_bfloat16* qkv, __nv_bfloat16* kcache, __nv_bfloat16* vcache, int B, int T, int H, int D,
+              int t_max, cudaStream_t s) {
+    const size_t n = static_cast<size_t>(B) * T * H * (D / 8) * 2;
+    const int blocks = static_cast<int>(n / 256 + 1 < 148 * 8 ? n / 256 + 1 : 148 * 8);
+    kv_export_kernel<<<blocks, 256, 0, s>>>(qkv, kcache, vcache, B, T, H, D, t_max);
+    CB200_CUDA_OK(cudaGetLastError());
+    note_launch(1);
+    return 0;
+}
+
 int decode_embed(const int32_t* cur, const float* wte, const float* wpe, __nv_bfloat16* out, const int* pos_ptr, int B,
                  int E, int vocab, cudaStream_t s) {
     if (B == 0) return 0;

@@ -9,6 +9,9 @@ namespace cb200 {
 // out: [B, E] bf16; *pos_ptr = position of the new token (device memory).
 int decode_attention(const __nv_bfloat16* qkv, __nv_bfloat16* kcache, __nv_bfloat16* vcache, __nv_bfloat16* out,
                      const int* pos_ptr, int B, int H, int D, int t_max, float scale, cudaStream_t s);
+// Batched prefill: k, v rows of T tokens per sequence from a c_attn output [B * T, 3E] into one layer of the cache.
+int kv_export(const __nv_bfloat16* qkv, __nv_bfloat16* kcache, __nv_bfloat16* vcache, int B, int T, int H, int D,
+              int t_max, cudaStream_t s);
 int decode_embed(const int32_t* cur, const float* wte, const float* wpe, __nv_bfloat16* out, const int* pos_ptr, int B,
                  int E, int vocab, cudaStream_t s);
 // pos_ptr[0] = position, pos_ptr[1] = ticket scratch (must be 0); step_ptr = output column.
@@ -44,6 +47,7 @@ struct MegaArgs {
     long long* prof;               // 24 cycle counters (phase profile of cluster 0: 15 phases, then ring waits per phase), or null
     long long layer_stride;        // elements per layer of the cache
     int B, E, H, F, V, L, t_max, steps, use_ln, greedy, seq_base;
+    int step0;                     // first step to run: positions 0 .. step0-1 are already in the cache (batched prefill)
     int kv_split_log2;             // a pair's KV chunks go to up to 1 << this warps when the CTA has few pairs (set by decode_mega)
     int kv_prefetch;               // KV chunks per warp and attention phase requested into L2 during the GEMM phases (set by decode_mega)
     int l2_hints;                  // 1: cache reads evict-first, weight stream evict-last (set by decode_mega)
@@ -59,6 +63,9 @@ int decode_mega_capacity(int E, int H, int V, int D, int L, int cluster_size);
 // cluster_size: 0 = automatic, 4 or 8 CTAs per cluster.
 // stream_ws: device scratch of decode_mega_stream_bytes() bytes for the packed weight stream.
 int64_t decode_mega_stream_bytes(int E, int H, int D, int V, int L);
+// Batched prefill for the cluster kernel's cache layout ([B, H, t_max, 2, D] per layer, swizzled 16-byte pieces).
+int kv_export_mega(const __nv_bfloat16* qkv, __nv_bfloat16* cache_layer, int B, int T, int H, int D, int t_max,
+                   cudaStream_t s);
 int decode_mega(MegaArgs args, int D, int max_clusters, int cluster_size, uint8_t* stream_ws, int64_t stream_ws_bytes,
                 cudaStream_t s);
 

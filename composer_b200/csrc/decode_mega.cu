@@ -615,7 +615,7 @@ decode_mega_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ M
     jr.base = ring + first_stage * MG_STAGE;
     jr.bars = bars + first_stage;
     jr.stage = 0; jr.phase = 0; jr.nst = NST + (warp < sm.nst_extra ? 1 : 0);
-    jr.cur = JobCursor{0, 0, 0, 0, 0, nullptr};
+    jr.cur = JobCursor{a.step0, 0, 0, 0, 0, nullptr};
     jr.wait_prof = nullptr;
     const bool wait_profiling = a.prof != nullptr && blockIdx.x == 0 && tid == 0;
 #define MG_WAIT_SLOT(k) if (wait_profiling) jr.wait_prof = prof_acc + 16 + (k);
@@ -640,7 +640,7 @@ decode_mega_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ M
     LnFrag lnf;
     if (use_ln) ln_prefetch(lnf, P + a.layers[0].ln1_g, P + a.layers[0].ln1_b, E, lane);
 
-    for (int step = 0; step < a.steps; ++step) {
+    for (int step = a.step0; step < a.steps; ++step) {
         const int pos = step;
         // ---- token + positional embedding: warp = row ----
         if (warp < G) {
@@ -1136,6 +1136,43 @@ int decode_mega_capacity(int E, int H, int V, int D, int L, int CL) {
     if (!mega_shape_ok(E, H, D, V, L, CL)) return 0;
     const MegaSmem sm = mega_smem_fit(E, V, D, CL, L);
     return CB200_MEGA_DISPATCH(mega_capacity, sm);
+}
+
+// ---- batched prefill: the k|v records of T prompt tokens in this kernel's cache layout ----
+// One thread per 16-byte piece of a record (pieces 0 .. D/8-1 = k, the rest = v), written where the attention phase's
+// append would have put it (kv_piece_off: the swizzle inside the CT-token chunk).
+template <int D>
+__global__ void __launch_bounds__(256)
+kv_export_mega_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ cache_l, int B, int T, int H, int t_max) {
+    constexpr int CT = MG_CT(D), REC = 4 * D, CH = D / 8;
+    const int E = H * D;
+    const size_t n = static_cast<size_t>(B) * T * H * 2 * CH;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        size_t r = i;
+        const int piece = static_cast<int>(r % (2 * CH)); r /= 2 * CH;
+        const int h = static_cast<int>(r % H); r /= H;
+        const int t = static_cast<int>(r % T);
+        const int b = static_cast<int>(r / T);
+        const int part = piece % CH, kv = piece / CH;
+        const uint4 val = *reinterpret_cast<const uint4*>(qkv + (static_cast<size_t>(b) * T + t) * 3 * E + (1 + kv) * E + h * D + part * 8);
+        const size_t rec = ((static_cast<size_t>(b) * H + h) * t_max + t) * (2 * D);
+        *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(cache_l + rec) + kv_piece_off<D>(t % CT, piece) - (t % CT) * REC) = val;
+    }
+}
+
+int kv_export_mega(const __nv_bfloat16* qkv, __nv_bfloat16* cache_layer, int B, int T, int H, int D, int t_max,
+                   cudaStream_t s) {
+    const size_t n = static_cast<size_t>(B) * T * H * (D / 4);
+    const int blocks = static_cast<int>(n / 256 + 1 < 148 * 8 ? n / 256 + 1 : 148 * 8);
+    switch (D) {
+        case 16: kv_export_mega_kernel<16><<<blocks, 256, 0, s>>>(qkv, cache_layer, B, T, H, t_max); break;
+        case 32: kv_export_mega_kernel<32><<<blocks, 256, 0, s>>>(qkv, cache_layer, B, T, H, t_max); break;
+        case 64: kv_export_mega_kernel<64><<<blocks, 256, 0, s>>>(qkv, cache_layer, B, T, H, t_max); break;
+        default: set_error("head size %d is not supported", D); return -1;
+    }
+    CB200_CUDA_OK(cudaGetLastError());
+    note_launch(1);
+    return 0;
 }
 
 // cluster_size 0 = automatic: 8-CTA clusters (each weight is read by fewer CTAs) when the batch fits one wave of

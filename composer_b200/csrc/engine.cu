@@ -228,8 +228,18 @@ static int refresh_shadows(Engine& e, cudaStream_t s) {
 // ---------------------------------------------------------------------------
 // Forward (+ loss)
 // ---------------------------------------------------------------------------
+// Where the k, v rows of a forward pass go when it doubles as the prefill of a KV cache (transformer.py:419-432: the
+// `presents` of a call without `past`).  layout 0: [L, 2, B, H, t_max, d_h] (the reference's present per layer, with
+// room for t_max positions; per-step kernels); 1: the cluster kernel's [L, B, H, t_max, 2, d_h], swizzled pieces.
+struct KvExport {
+    bf16* cache;
+    int t_max, layout;
+    bool skip_head;     // the caller does not need logits: stop after the last block
+};
+
 static int forward(Engine& e, const int32_t* ids, const int32_t* labels, int B, int T, int training, uint64_t seed,
-                   uint32_t step, float grad_scale, float* loss_sum, int32_t* correct, float* logits, cudaStream_t s) {
+                   uint32_t step, float grad_scale, float* loss_sum, int32_t* correct, float* logits, cudaStream_t s,
+                   const KvExport* kx = nullptr) {
     CB200_REQUIRE(e.params != nullptr && e.ws != nullptr, "engine is not bound");
     CB200_REQUIRE(B >= 1 && T >= 1 && static_cast<int64_t>(B) * T <= static_cast<int64_t>(e.max_B) * e.max_T,
                   "batch %d x %d exceeds the bound workspace (%d x %d)", B, T, e.max_B, e.max_T);
@@ -259,6 +269,13 @@ static int forward(Engine& e, const int32_t* ids, const int32_t* labels, int B, 
             d.bias = P + o.attn_b; d.out0 = x.qkv; d.ld_out0 = 3 * E;
             if ((rc = gemm_launch(d, s))) return rc;
         }
+        if (kx != nullptr) {
+            const int64_t layer_stride = 2ll * B * e.H * kx->t_max * e.D;
+            bf16* cl = kx->cache + l * layer_stride;
+            if (kx->layout == 1) rc = kv_export_mega(x.qkv, cl, B, T, e.H, e.D, kx->t_max, s);
+            else rc = kv_export(x.qkv, cl, cl + layer_stride / 2, B, T, e.H, e.D, kx->t_max, s);
+            if (rc) return rc;
+        }
         if ((rc = attention_fwd(x.qkv, x.att, x.lse, B, T, e.H, e.D, att_scale, drop_attn, layer, s))) return rc;
         {   // attn c_proj + dropout + residual (transformer.py:443-444, 587)
             GemmDesc d = gemm_desc(GEMM_BIAS_DROP_RES, M, E, E, x.att, E, S + e.shT_proj[l], E);
@@ -284,6 +301,7 @@ static int forward(Engine& e, const int32_t* ids, const int32_t* labels, int B, 
         }
         x_in = x.x3;
     }
+    if (kx != nullptr && kx->skip_head) return 0;
     // ln_f (transformer.py:811) and the tied logits (:818) fused with the loss (:888, 918)
     if ((rc = layernorm_fwd(x_in, P + e.lay.lnf_g, P + e.lay.lnf_b, e.hf, e.lnf_stats, M, E, e.cfg.layer_normalization_epsilon, s))) return rc;
     {
@@ -475,8 +493,10 @@ static long long* g_decode_prof = nullptr;   // device buffer of 16 counters for
 static int g_decode_cluster_size = 0;    // 0 = automatic, 4 or 8 CTAs per cluster
 static int g_decode_max_clusters = 0;   // > 0 caps the clusters of the persistent kernel (tests)
 
+static int g_decode_prefill = 1;        // 1: prompts go through one batched forward pass (KV export), 0: teacher-forced token by token
+
 struct DecodeBuffers {
-    int32_t *cur, *state, *all_ids, *forced;
+    int32_t *cur, *state, *all_ids, *forced, *prefix;
     float *logits, *uniforms;
     bf16 *x, *x1, *qkv, *att, *x2, *mln, *u, *gl, *y;
     float* stats;
@@ -491,6 +511,7 @@ static int64_t carve_decode(const Engine& e, uint8_t* base, int B, int steps, De
     d.cur = b.take<int32_t>(B);
     d.all_ids = b.take<int32_t>(static_cast<int64_t>(B) * steps);
     d.forced = b.take<int32_t>(static_cast<int64_t>(B) * steps);
+    d.prefix = b.take<int32_t>(static_cast<int64_t>(B) * steps);
     d.uniforms = b.take<float>(static_cast<int64_t>(B) * steps);
     d.logits = b.take<float>(static_cast<int64_t>(B) * e.V);
     d.stats = b.take<float>(2 * B);
@@ -508,11 +529,13 @@ static int64_t carve_decode(const Engine& e, uint8_t* base, int B, int steps, De
     return (b.off + 255) & ~int64_t(255);
 }
 
-__global__ void decode_init_kernel(const int32_t* prompt, int B, int P, int steps, int32_t* cur, int32_t* forced,
-                                   int32_t* state) {
+// step0: the first step the decode loop runs (0, or prompt_len - 1 after a batched prefill of the tokens before it)
+__global__ void decode_init_kernel(const int32_t* prompt, int B, int P, int steps, int step0, int32_t* cur,
+                                   int32_t* forced, int32_t* prefix, int32_t* state) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < 8) state[i] = 0;
-    if (i < B) cur[i] = prompt[static_cast<size_t>(i) * P];
+    if (i < 8) state[i] = (i == 0 || i == 2) ? step0 : 0;      // [0] position, [1] ticket, [2] output column
+    if (i < B) cur[i] = prompt[static_cast<size_t>(i) * P + step0];
+    if (step0 > 0 && i < B * step0) prefix[i] = prompt[static_cast<size_t>(i / step0) * P + i % step0];
     if (i < B * steps) {
         const int b = i / steps, s = i % steps;
         forced[i] = (s + 1 < P) ? prompt[static_cast<size_t>(b) * P + s + 1] : -1;
@@ -568,13 +591,26 @@ static int generate_on(Engine& e, bf16* cache, int t_max, uint8_t* ws, int64_t w
     const int64_t need = carve_decode(e, nullptr, B, steps, d);
     CB200_REQUIRE(ws_bytes >= need, "decode workspace too small: %lld < %lld", (long long)ws_bytes, (long long)need);
     carve_decode(e, ws, B, steps, d);
+    // Prompt tokens 0 .. P-2 only feed the cache: one batched forward pass (the training kernels, inference mode)
+    // writes their k, v rows, and the decode loop starts at the last prompt token (transformer.py:735-770: a call
+    // without `past` returns the presents of the whole prompt).  Needs an engine workspace bound for B x (P - 1).
+    const bool prefill = g_decode_prefill != 0 && P > 1 && e.ws != nullptr &&
+                         static_cast<int64_t>(B) * (P - 1) <= static_cast<int64_t>(e.max_B) * e.max_T;
+    const int step0 = prefill ? P - 1 : 0;
     const int n_init = B * steps > 8 ? B * steps : 8;
-    decode_init_kernel<<<(n_init + 255) / 256, 256, 0, s>>>(prompt, B, P, steps, d.cur, d.forced, d.state);
+    decode_init_kernel<<<(n_init + 255) / 256, 256, 0, s>>>(prompt, B, P, steps, step0, d.cur, d.forced, d.prefix, d.state);
     CB200_CUDA_OK(cudaGetLastError());
     note_launch(1);
     int rc;
     // (the cluster kernel copies whole 64-token chunks of the cache: t_max must be a multiple of the chunk)
     const bool mega = g_decode_impl == 0 && t_max % 64 == 0 && decode_mega_supported(e.E, e.H, e.D, e.V, e.L);
+    if (mega)   // chunks are copied whole: positions that are not cached yet must read as zeros (V rows enter an MMA)
+        CB200_CUDA_OK(cudaMemsetAsync(cache, 0, sizeof(bf16) * 2ull * B * e.H * t_max * e.D * e.L, s));
+    if (prefill) {
+        if (uniforms_out) CB200_CUDA_OK(cudaMemsetAsync(d.uniforms, 0, sizeof(float) * B * steps, s));
+        const KvExport kx{cache, t_max, mega ? 1 : 0, true};
+        if ((rc = forward(e, d.prefix, nullptr, B, P - 1, 0, 0, 0, 0.f, nullptr, nullptr, nullptr, s, &kx))) return rc;
+    }
     if (mega) {
         // the whole generation (all steps, all layers) is one persistent cluster kernel
         MegaArgs m{};
@@ -583,6 +619,7 @@ static int generate_on(Engine& e, bf16* cache, int t_max, uint8_t* ws, int64_t w
         m.prof = g_decode_prof;
         m.layer_stride = 2ll * B * e.H * t_max * e.D;
         m.B = B; m.E = e.E; m.H = e.H; m.F = e.F; m.V = e.V; m.L = e.L; m.t_max = t_max; m.steps = steps;
+        m.step0 = step0;
         m.use_ln = e.cfg.use_layer_normalization ? 1 : 0;
         m.greedy = temperature <= 0.f ? 1 : 0;
         m.seq_base = static_cast<int>(seq_base);
@@ -603,25 +640,23 @@ static int generate_on(Engine& e, bf16* cache, int t_max, uint8_t* ws, int64_t w
             w.attn_w = static_cast<uint32_t>(e.shT_attn[l]); w.proj_w = static_cast<uint32_t>(e.shT_proj[l]);
             w.fc_w = static_cast<uint32_t>(e.shT_fc[l]); w.proj2_w = static_cast<uint32_t>(e.shT_proj2[l]);
         }
-        // chunks are copied whole: positions that are not cached yet must read as zeros (V rows enter an MMA)
-        CB200_CUDA_OK(cudaMemsetAsync(cache, 0, sizeof(bf16) * static_cast<size_t>(m.layer_stride) * e.L, s));
         if ((rc = decode_mega(m, e.D, g_decode_max_clusters, g_decode_cluster_size, d.mega_stream, d.mega_stream_bytes, s))) return rc;
     } else {
     // step 0 runs eagerly (also configures kernel attributes outside of capture); the rest replays a graph
     if ((rc = decode_step(e, d, cache, t_max, B, steps, temperature, seed, seq_base, s))) return rc;
-    if (steps > 1) {
+    if (steps - step0 > 1) {
         cudaGraph_t graph = nullptr;
         cudaGraphExec_t exec = nullptr;
         CB200_CUDA_OK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
         const long long before = g_launches.load();
         rc = decode_step(e, d, cache, t_max, B, steps, temperature, seed, seq_base, s);
         const long long per_step = g_launches.load() - before;
-        note_launch(per_step * (steps - 2));   // the captured step itself is replayed steps-1 times
+        note_launch(per_step * (steps - step0 - 2));   // the captured step itself is replayed steps-step0-1 times
         cudaError_t ce = cudaStreamEndCapture(s, &graph);
         if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
         CB200_CUDA_OK(ce);
         CB200_CUDA_OK(cudaGraphInstantiate(&exec, graph, 0));
-        for (int i = 1; i < steps; ++i) {
+        for (int i = step0 + 1; i < steps; ++i) {
             cudaError_t le = cudaGraphLaunch(exec, s);
             if (le != cudaSuccess) {
                 cudaGraphExecDestroy(exec); cudaGraphDestroy(graph);
@@ -662,6 +697,42 @@ static int generate(Engine& e, bf16* cache, int t_max, uint8_t* ws, int64_t ws_b
         CB200_CUDA_OK(cudaStreamCreateWithFlags(&e.decode_stream, cudaStreamNonBlocking));
     return generate_on(e, cache, t_max, ws, ws_bytes, prompt, B, P, n_new, temperature, seed, seq_base, out_ids,
                        uniforms_out, step_logits, e.decode_stream);
+}
+
+// `Transformer.call(inputs, past=None)` for a KV cache the caller keeps: logits of every position (optional) and the
+// presents of the prompt written into `cache` ([L, 2, B, H, t_max, d_h]: layer l's slice [2, B, H, :T, d_h] is the
+// reference's `present`, transformer.py:430-432).
+static int prefill(Engine& e, const int32_t* ids, int B, int T, bf16* cache, int t_max, float* logits, cudaStream_t s) {
+    CB200_REQUIRE(T <= t_max, "KV cache too small: %d positions, t_max %d", T, t_max);
+    const KvExport kx{cache, t_max, 0, logits == nullptr};
+    return forward(e, ids, nullptr, B, T, 0, 0, 0, 0.f, nullptr, nullptr, logits, s, &kx);
+}
+
+__global__ void decode_step_init_kernel(const int32_t* ids, int B, int pos, int32_t* cur, int32_t* forced, int32_t* state) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 8) state[i] = (i == 0) ? pos : 0;
+    if (i < B) { cur[i] = ids[i]; forced[i] = -1; }
+}
+
+// `Transformer.call(inputs[:, -1:], past=presents)` (transformer.py:735-737, 423-426): one token per sequence at
+// position `pos` = the past length, k, v appended to the cache in place, logits [B, V] of that position.
+static int decode_one(Engine& e, bf16* cache, int t_max, uint8_t* ws, int64_t ws_bytes, const int32_t* ids, int B,
+                      int pos, float* logits_out, cudaStream_t s) {
+    CB200_REQUIRE(e.params != nullptr, "engine is not bound");
+    CB200_REQUIRE(pos >= 0 && pos < t_max, "position %d outside the KV cache (t_max %d)", pos, t_max);
+    CB200_REQUIRE(pos < e.W, "position %d exceeds window_size %d (wpe has only window_size rows)", pos, e.W);
+    DecodeBuffers d;
+    const int64_t need = carve_decode(e, nullptr, B, 1, d);
+    CB200_REQUIRE(ws_bytes >= need, "decode workspace too small: %lld < %lld", (long long)ws_bytes, (long long)need);
+    carve_decode(e, ws, B, 1, d);
+    decode_step_init_kernel<<<(B + 255) / 256 > 0 ? (B + 255) / 256 : 1, 256, 0, s>>>(ids, B, pos, d.cur, d.forced, d.state);
+    CB200_CUDA_OK(cudaGetLastError());
+    note_launch(1);
+    int rc = decode_step(e, d, cache, t_max, B, 1, 0.f, 0, 0, s);
+    if (rc) return rc;
+    if (logits_out)
+        CB200_CUDA_OK(cudaMemcpyAsync(logits_out, d.logits, sizeof(float) * B * e.V, cudaMemcpyDeviceToDevice, s));
+    return 0;
 }
 
 }  // namespace cb200
@@ -832,6 +903,24 @@ int cb200_generate(void* engine, void* cache, int t_max, void* workspace, int64_
     return generate(*static_cast<Engine*>(engine), static_cast<bf16*>(cache), t_max, static_cast<uint8_t*>(workspace),
                     workspace_bytes, prompt, B, prompt_len, n_new, temperature, seed, seq_index_base, out_ids,
                     uniforms_out, step_logits, static_cast<cudaStream_t>(stream));
+}
+
+int cb200_prefill(void* engine, const int32_t* ids, int B, int T, void* cache, int t_max, float* logits, void* stream) {
+    CB200_REQUIRE(engine && ids && cache, "null argument");
+    return prefill(*static_cast<Engine*>(engine), ids, B, T, static_cast<bf16*>(cache), t_max, logits,
+                   static_cast<cudaStream_t>(stream));
+}
+
+int cb200_decode_step(void* engine, void* cache, int t_max, void* workspace, int64_t workspace_bytes, const int32_t* ids,
+                      int B, int pos, float* logits, void* stream) {
+    CB200_REQUIRE(engine && cache && workspace && ids, "null argument");
+    return decode_one(*static_cast<Engine*>(engine), static_cast<bf16*>(cache), t_max, static_cast<uint8_t*>(workspace),
+                      workspace_bytes, ids, B, pos, logits, static_cast<cudaStream_t>(stream));
+}
+
+int cb200_set_decode_prefill(int enabled) {
+    g_decode_prefill = enabled ? 1 : 0;
+    return 0;
 }
 
 // ---- single kernels ---------------------------------------------------------

@@ -38,6 +38,57 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+class Presents:
+    '''
+    The ``presents`` / ``past`` of the model call (transformer.py:423-432, 800-809): behaves like the reference's tuple
+    of ``decoder_layers_count`` tensors ``[2, batch, heads, t, d_h]`` (index it, iterate it, ``len``), and is one
+    bf16 CUDA tensor ``[layers, 2, batch, heads, capacity, d_h]`` underneath, so that a decode step appends the new
+    key / value rows in place instead of re-concatenating the whole cache.
+    '''
+
+    def __init__(self, owner, storage, length):
+        self.owner, self.storage, self.length = owner, storage, int(length)
+
+    @property
+    def capacity(self):
+        return self.storage.shape[4]
+
+    @property
+    def batch(self):
+        return self.storage.shape[2]
+
+    @classmethod
+    def allocate(cls, model, batch, length):
+        # room for 64 .. 127 more positions (a step that finds the cache full moves it to a larger one), never more
+        # than wpe can address
+        capacity = max(min(model.window_size, (length + 127) // 64 * 64), length)
+        heads = model.attention_head_count
+        storage = torch.empty((model.decoder_layers_count, 2, batch, heads, capacity, model.embedding_size // heads),
+                              dtype=torch.bfloat16, device=model.device)
+        return cls(model, storage, length)
+
+    @classmethod
+    def from_tensors(cls, model, past):
+        layers = [torch.as_tensor(p) for p in past]
+        if len(layers) != model.decoder_layers_count:
+            raise ValueError('past has %d layers, the model %d' % (len(layers), model.decoder_layers_count))
+        length = layers[0].shape[-2]
+        presents = cls.allocate(model, layers[0].shape[1], length + 1)
+        for index, layer in enumerate(layers):
+            presents.storage[index, :, :, :, :length] = layer.to(device=model.device, dtype=torch.bfloat16)
+        presents.length = length
+        return presents
+
+    def __len__(self):
+        return self.storage.shape[0]
+
+    def __getitem__(self, layer):
+        return self.storage[layer, :, :, :, :self.length]
+
+    def __iter__(self):
+        return (self[layer] for layer in range(len(self)))
+
+
 class Transformer(BaseModel):
     '''
     A Transformer-decoder model that generates music as a sequence of MIDI-like
@@ -105,6 +156,7 @@ class Transformer(BaseModel):
         self._loss_dev = torch.zeros(1, dtype=torch.float32, device=self.device)
         self._correct_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._decode_state = None
+        self._step_ws = None
         self.set_weights(self.initial_weights(self.seed))
 
     def __del__(self):
@@ -265,21 +317,61 @@ class Transformer(BaseModel):
     def __call__(self, inputs, past=None, training=False, use_cache=True):
         '''
         ``Transformer.call`` (transformer.py:696-833) for integer ``inputs``
-        [batch, sequence].  Returns ``(logits, presents)``: logits is a float32
-        CUDA tensor [batch, sequence, vocab]; ``presents`` is ``None`` (the KV
-        cache lives inside :meth:`generate`, which is what the CLI loop uses).
+        [batch, sequence].  Returns ``(logits, presents)`` like the reference
+        (``(logits,)`` with ``use_cache=False``): logits is a float32 CUDA
+        tensor [batch, sequence, vocab] and ``presents`` a :class:`Presents`,
+        a sequence of ``decoder_layers_count`` tensors [2, batch, heads, t, d_h]
+        (transformer.py:430-432) that can be handed back as ``past``.
+
+        With ``past`` only the last token of ``inputs`` is used (:735-737); it
+        is embedded at position ``t`` = the length of the past (:765-770), its
+        key / value rows are appended and the logits have shape [batch, 1, vocab].
+        A :class:`Presents` returned by this model is extended IN PLACE (the
+        reference re-concatenates the whole cache every step, :423-426): the
+        object passed in and the one returned share storage, and stepping from
+        the same past twice overwrites position ``t``.  Any other sequence of
+        [2, batch, heads, t, d_h] tensors is copied into a fresh cache first.
         '''
 
-        if past is not None:
-            raise NotImplementedError('use generate() for cached decoding')
         ids = self._as_ids(inputs)
-        batch, sequence = ids.shape
-        self._bind(batch, sequence, training=False)
-        logits = torch.empty((batch, sequence, self.vocab_size), dtype=torch.float32, device=self.device)
+        if past is None:
+            batch, sequence = ids.shape
+            self._bind(batch, sequence, training=False)
+            logits = torch.empty((batch, sequence, self.vocab_size), dtype=torch.float32, device=self.device)
+            with torch.cuda.device(self.device):
+                if not use_cache:
+                    _lib.call('cb200_forward', self._engine, _ptr(ids), None, batch, sequence, 0, self.seed, 0, 0.0,
+                              None, None, _ptr(logits), _stream())
+                    return (logits,)
+                presents = Presents.allocate(self, batch, sequence)
+                _lib.call('cb200_prefill', self._engine, _ptr(ids), batch, sequence, _ptr(presents.storage),
+                          presents.capacity, _ptr(logits), _stream())
+            return logits, presents
+
+        ids = ids[:, -1].contiguous()                                       # transformer.py:735-737
+        batch = ids.shape[0]
+        if not (isinstance(past, Presents) and past.owner is self and past.length < past.capacity):
+            past = Presents.from_tensors(self, past)
+        if past.batch != batch:
+            raise ValueError('past holds %d sequences, inputs %d' % (past.batch, batch))
+        if past.length >= self.window_size:
+            # TF-CPU's gather raises on an index outside wpe (window_size rows, transformer.py:675-679, 770)
+            raise IndexError('position %d is outside wpe (window_size=%d)' % (past.length, self.window_size))
+        if self._bound is None:
+            self._bind(1, min(self.window_size, 64), training=False)
+        logits = torch.empty((batch, 1, self.vocab_size), dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
-            _lib.call('cb200_forward', self._engine, _ptr(ids), None, batch, sequence, 0, self.seed, 0, 0.0, None,
-                      None, _ptr(logits), _stream())
-        return logits, None
+            workspace = self._step_workspace(batch)
+            _lib.call('cb200_decode_step', self._engine, _ptr(past.storage), past.capacity, _ptr(workspace),
+                      workspace.numel(), _ptr(ids), batch, past.length, _ptr(logits), _stream())
+        past.length += 1
+        return (logits, past) if use_cache else (logits,)
+
+    def _step_workspace(self, batch):
+        if self._step_ws is None or self._step_ws[0] < batch:
+            need = _lib.call('cb200_decode_workspace_bytes', self._engine, batch)
+            self._step_ws = (batch, torch.empty(need, dtype=torch.uint8, device=self.device))
+        return self._step_ws[1]
 
     def forward_loss(self, x, y, training=False, step=0, return_logits=False):
         '''Forward + summed loss + correct count on the device; returns (loss_sum, correct[, logits]) tensors.'''
@@ -456,6 +548,11 @@ class Transformer(BaseModel):
 
         batch, prompt_length = prompt.shape
         steps = prompt_length - 1 + length
+        if prompt_length > 1:
+            # the prompt's k, v rows come from one batched forward pass: its workspace has to hold batch x (prompt - 1) tokens
+            bound = self._bound
+            if bound is None or bound[0] * bound[1] < batch * (prompt_length - 1):
+                self._bind(batch, prompt_length - 1, training=False)
         if self._bound is None:
             self._bind(1, min(self.window_size, 64), training=False)
         with torch.cuda.device(self.device):

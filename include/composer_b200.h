@@ -127,6 +127,24 @@ int cb200_generate(void* engine, void* cache, int t_max, void* workspace, int64_
                    const int32_t* prompt, int B, int prompt_len, int n_new, float temperature, uint64_t seed,
                    int64_t seq_index_base, int32_t* out_ids, float* uniforms_out, float* step_logits, void* stream);
 
+/* ---- the model call with a KV cache the CALLER keeps (composer/models/transformer.py:696-833: `past` / `presents`) ----
+ * cache: device bf16 [L, 2, B, H, t_max, d_h]; layer l's slice [2, B, H, :t, d_h] is exactly the reference's
+ * `present` of that layer for a context of t tokens (transformer.py:419-432: split_heads(key), split_heads(value),
+ * stacked), with room for t_max positions so that a step appends in place instead of re-concatenating (:423-426).
+ *
+ * cb200_prefill      = Transformer.call(inputs [B, T], past=None): one batched pass over the whole prompt (the training
+ *                      forward kernels in inference mode); writes the presents of positions 0 .. T-1 and, when `logits`
+ *                      is not NULL, the fp32 logits [B, T, vocab].  Needs cb200_engine_bind for >= B x T tokens.
+ * cb200_decode_step  = Transformer.call(inputs[:, -1:], past=presents) (:735-737): ids [B] (device int32) are the
+ *                      tokens at position `pos` = the length of the past; appends their k, v rows at `pos` and writes
+ *                      the fp32 logits [B, vocab] of that position.  workspace: cb200_decode_workspace_bytes(engine, B).
+ * cb200_generate (above) uses the same prefill for prompts longer than one token (its cache layout stays private);
+ * cb200_set_decode_prefill(0) restores the token-by-token teacher forcing of round 1 (A/B and tests). */
+int cb200_prefill(void* engine, const int32_t* ids, int B, int T, void* cache, int t_max, float* logits, void* stream);
+int cb200_decode_step(void* engine, void* cache, int t_max, void* workspace, int64_t workspace_bytes, const int32_t* ids,
+                      int B, int pos, float* logits, void* stream);
+int cb200_set_decode_prefill(int enabled);
+
 /* ---- single kernels (unit parity tests, ncu isolation) ---------------------- */
 /* D[M,N] = A[M,K] B[N,K]^T (+ bias).  kind: 0 bias, 1 bias+gelu (out1 = gelu), 2 bias+dropout+residual(aux),
  * 3 acc * gelu'(aux), 4 weight gradient outf += A^T B with A [K,M], B [K,N], 6 bias with B stored [K,N]. */

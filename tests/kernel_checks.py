@@ -787,3 +787,95 @@ GROUPS['configs'] = [
     # the default model through the persistent decode kernel: 16 prompts x 256 steps as well
     lambda: check_greedy_sweep(layers=8, embedding=256, heads=16, prompts=16, prompt_len=4, length=256, window=320),
 ]
+
+
+def check_model_call_with_past(B=3, T=37, steps=6, layers=3, embedding=256, heads=16, window=64):
+    '''
+    The model call of the reference (transformer.py:696-833) through its `past` / `presents` interface:
+    ``logits, presents = model(x)`` (batched prefill, cb200_prefill), then ``model(next, past=presents)`` one token
+    at a time (cb200_decode_step), against ``oracle.transformer_call`` with the same past.
+    '''
+    import numpy as np
+    from oracle import transformer_oracle as oracle
+
+    model, cfg, weights = _small_model(layers, embedding, heads, window=window)
+    params = oracle.to_torch(weights, torch.float64)
+    rng = np.random.default_rng(31)
+    x = rng.integers(0, cfg.vocab_size, size=(B, T))
+    results = []
+    logits, presents = model(x)
+    with torch.no_grad():
+        ref_logits, ref_presents = oracle.transformer_call(params, x, cfg)
+    results.append(_stats('prefill logits [B, T, V]', logits.double().cpu().reshape(B * T, -1), ref_logits.reshape(B * T, -1), 2e-2))
+    results.append({'name': 'presents: %d layers of [2, B, H, T, d_h]' % len(presents), 'rel': 0.0, 'tol': 0.0, 'nan': False,
+                    'ok': len(presents) == layers and tuple(presents[0].shape) == (2, B, heads, T, embedding // heads)})
+    for layer in (0, layers - 1):
+        ref = torch.stack([ref_presents[layer][0], ref_presents[layer][1]]) if isinstance(ref_presents[layer], (tuple, list)) \
+            else ref_presents[layer]
+        results.append(_stats('presents[%d] vs oracle' % layer, presents[layer].double().cpu().reshape(-1, embedding // heads),
+                              ref.reshape(-1, embedding // heads), 1e-2))
+    # plain tensors handed back as `past` (copied into a fresh cache) and the in-place path must agree
+    as_tuple = tuple(p.clone() for p in presents)
+    nxt = rng.integers(0, cfg.vocab_size, size=(B, 1))
+    via_tuple, _ = model(nxt, past=as_tuple)
+    past_ref = ref_presents
+    for step in range(steps):
+        step_logits, presents = model(nxt, past=presents)
+        with torch.no_grad():
+            ref_step, past_ref = oracle.transformer_call(params, nxt, cfg, past=past_ref)
+        if step == 0:
+            results.append(_stats('step 0: past given as a tuple of tensors == in-place cache', via_tuple.cpu().reshape(B, -1),
+                                  step_logits.cpu().reshape(B, -1), 1e-6))
+        if step in (0, steps - 1):
+            results.append(_stats('step %d logits [B, 1, V] with past of %d tokens' % (step, T + step),
+                                  step_logits.double().cpu().reshape(B, -1), ref_step.reshape(B, -1), 2e-2))
+        nxt = rng.integers(0, cfg.vocab_size, size=(B, 1))
+    results.append({'name': 'presents grew to %d positions' % presents.length, 'rel': 0.0, 'tol': 0.0, 'nan': False,
+                    'ok': presents.length == T + steps and tuple(presents[1].shape)[3] == T + steps})
+    # inputs longer than one token with a past: only the last one is used (transformer.py:735-737)
+    longer = np.concatenate([rng.integers(0, cfg.vocab_size, size=(B, 4)), nxt], axis=1)
+    a, presents = model(longer, past=presents)
+    with torch.no_grad():
+        b, _ = oracle.transformer_call(params, longer, cfg, past=past_ref)
+    results.append(_stats('inputs[:, -1:] is what a call with past uses', a.double().cpu().reshape(B, -1), b.reshape(B, -1), 2e-2))
+    return _finish(results)
+
+
+def check_prefill_equals_teacher_forcing(B=5, prompt_len=23, length=12, embedding=256, heads=16, window=64):
+    '''The batched prompt prefill of cb200_generate against feeding the prompt token by token (both decode paths).'''
+    import numpy as np
+
+    model, cfg, _ = _small_model(3, embedding, heads, window=window)
+    rng = np.random.default_rng(41)
+    prompt = rng.integers(0, cfg.vocab_size, size=(B, prompt_len))
+    results = []
+    for impl in (0, 1):
+        outs = {}
+        for prefill in (1, 0):
+            _lib.call('cb200_set_decode_impl', impl, 0, 0)
+            _lib.call('cb200_set_decode_prefill', prefill)
+            try:
+                ids, uniforms, last = model.generate(prompt, length, temperature=1.0, seed=5, return_uniforms=True,
+                                                     return_last_logits=True)
+                outs[prefill] = (ids.cpu().numpy(), uniforms.cpu().numpy(), last.float().cpu())
+            finally:
+                _lib.call('cb200_set_decode_impl', 0, 0, 0)
+                _lib.call('cb200_set_decode_prefill', 1)
+        same = float((outs[1][0] == outs[0][0]).mean())
+        results.append({'name': 'impl %d: sampled tokens, prefill vs teacher forcing, equal %.3f' % (impl, same),
+                        'rel': 1 - same, 'tol': 0.1, 'nan': False, 'ok': same >= 0.9})
+        results.append({'name': 'impl %d: same uniforms at the sampled steps' % impl, 'rel': 0.0, 'tol': 0.0, 'nan': False,
+                        'ok': bool(np.array_equal(outs[1][1][:, prompt_len - 1:], outs[0][1][:, prompt_len - 1:]))})
+        rows = (outs[1][0] == outs[0][0]).all(axis=1)
+        if rows.any():
+            results.append(_stats('impl %d: last-step logits (%d identical rows)' % (impl, int(rows.sum())),
+                                  outs[1][2][torch.from_numpy(rows)], outs[0][2][torch.from_numpy(rows)], 8e-3))
+    return _finish(results)
+
+
+GROUPS['past'] = [
+    check_model_call_with_past,
+    lambda: check_model_call_with_past(B=2, T=64, steps=3, layers=2, embedding=512, heads=8, window=128),
+    check_prefill_equals_teacher_forcing,
+    lambda: check_prefill_equals_teacher_forcing(B=33, prompt_len=2, length=20),
+]
