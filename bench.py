@@ -16,7 +16,11 @@ already resident in HBM; `e2e` is the same metric through the public
 `Transformer.train_step` call with host (pinned) batches, host->device copies
 and the loss read-back inside the timed region.  `--impl reference` times the
 CPU restatement of the reference (oracle/; TensorFlow is not installable in
-this image, so the reference's own code cannot run) on the host cores.
+this image, so the reference's own code cannot run) on the host cores: same
+`config`, dropout on, one sequence of the batch per step (`config_delta`).
+Also on the line: `roofline` (attention backward, against the tensor peak and
+the MUFU.EX2 rate), `generate` (configs[2], ids copied to the host inside the
+timed region, its own `cpu_baseline`), `other_configs` (configs[0], [3], [4]).
 '''
 
 import argparse
@@ -118,8 +122,39 @@ class ClockSampler:
 # CPU baseline: the oracle (a restatement of the reference's TensorFlow model)
 # ---------------------------------------------------------------------------
 
-def cpu_reference_step(batch, seq_len, steps, warmup):
-    '''Times the oracle's training step (forward, loss, autograd, Adam) in fp32 on all host cores.'''
+def gpu_config(world, batch):
+    '''The `config` object of both arms (the reference arm times a bounded sample of the same workload).'''
+
+    return {'workload': 'BASELINE.json configs[1]: Transformer training step bf16, seq len 2048 '
+                        '(default_config.yml hyperparameters, window_size 2048, dropout 0.1)',
+            'global_batch': world * batch, 'per_gpu_batch': batch, 'seq_len': SEQ_LEN, 'vocab': VOCAB,
+            'parallelism': 'dp%d' % world,
+            'l2_policy': 'inputs larger than L2: each step streams >4 GB of activations'}
+
+
+def oracle_dropout_masks(cfg, batch, seq_len, generator):
+    '''Keep masks for every dropout site of the reference model (transformer.py:361, 444, 506, 794), drawn on the host.'''
+
+    import torch
+
+    def keep(shape, rate):
+        return (torch.rand(shape, generator=generator) >= rate).to(torch.float32)
+
+    heads, E = cfg.attention_head_count, cfg.embedding_size
+    masks = {'embd': keep((batch, seq_len, E), cfg.residual_dropout_rate)}
+    for layer in range(1, cfg.decoder_layers_count + 1):
+        masks[(layer, 'attn_w')] = keep((batch, heads, seq_len, seq_len), cfg.attention_dropout_rate)
+        masks[(layer, 'attn_resid')] = keep((batch, seq_len, E), cfg.residual_dropout_rate)
+        masks[(layer, 'mlp')] = keep((batch, seq_len, E), cfg.residual_dropout_rate)
+    return masks
+
+
+def cpu_reference_step(batch, seq_len, steps, warmup, budget_seconds=120.0):
+    '''
+    Times the oracle's training step (forward with dropout 0.1 at every site, loss, autograd, Keras Adam) in fp32 on
+    all host cores.  Mask generation is inside the timed region, as it is inside the reference's step.  At most
+    `steps` timed steps, fewer when `budget_seconds` of CPU work are used up first (the mean is over what ran).
+    '''
 
     import numpy as np
     import torch
@@ -130,17 +165,20 @@ def cpu_reference_step(batch, seq_len, steps, warmup):
     cfg = oracle.OracleConfig(vocab_size=VOCAB, embedding_size=MODEL['embedding_size'], window_size=seq_len,
                               decoder_layers_count=MODEL['decoder_layers_count'],
                               attention_head_count=MODEL['attention_head_count'],
-                              attention_dropout_rate=0.0, residual_dropout_rate=0.0)
+                              attention_dropout_rate=MODEL['attention_dropout_rate'],
+                              residual_dropout_rate=MODEL['residual_dropout_rate'])
     weights = oracle.init_parameters(cfg, seed=0)
     params = oracle.to_torch(weights, torch.float32, requires_grad=True)
     optimizer_state = {name: (torch.zeros_like(p), torch.zeros_like(p)) for name, p in params.items()}
     rng = np.random.default_rng(1234)
+    generator = torch.Generator().manual_seed(1234)
     times = []
     for step in range(warmup + steps):
         draw = rng.integers(0, VOCAB, size=(batch, seq_len + 1))
         x, y = draw[:, :-1], draw[:, 1:]
         start = time.perf_counter()
-        logits, _ = oracle.transformer_call(params, x, cfg)
+        masks = oracle_dropout_masks(cfg, batch, seq_len, generator)
+        logits, _ = oracle.transformer_call(params, x, cfg, dropout_masks=masks)
         loss = oracle.sparse_categorical_crossentropy(y, logits)
         loss.backward()
         t = step + 1
@@ -155,27 +193,63 @@ def cpu_reference_step(batch, seq_len, steps, warmup):
         elapsed = time.perf_counter() - start
         if step >= warmup:
             times.append(elapsed)
+            if sum(times) > budget_seconds:
+                break
     mean = sum(times) / len(times)
     return batch * seq_len / mean, threads, mean
+
+
+def cpu_reference_generate(sequences, length):
+    '''Times the oracle's KV-cache decode (transformer.py:735-770 `past=`) on the host cores: events/s.'''
+
+    import numpy as np
+    import torch
+    from oracle import transformer_oracle as oracle
+
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    cfg = oracle.OracleConfig(vocab_size=VOCAB, embedding_size=MODEL['embedding_size'], window_size=1024,
+                              decoder_layers_count=MODEL['decoder_layers_count'],
+                              attention_head_count=MODEL['attention_head_count'],
+                              attention_dropout_rate=0.0, residual_dropout_rate=0.0)
+    weights = oracle.init_parameters(cfg, seed=0)
+    rng = np.random.default_rng(99)
+    prompt = rng.integers(0, VOCAB, size=(sequences, 1))
+    uniforms = rng.random((sequences, length))
+    start = time.perf_counter()
+    oracle.generate(weights, prompt, length, cfg, temperature=1.0, dtype=torch.float32, uniforms=uniforms)
+    seconds = time.perf_counter() - start
+    return sequences * length / seconds, threads, seconds
 
 
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
+    world = int(os.environ.get('WORLD_SIZE', '1'))
     batch = 1
     value, threads, seconds = cpu_reference_step(batch, SEQ_LEN, max(1, args.steps), max(0, min(args.warmup, 1)))
-    sample = ('oracle/transformer_oracle.py (CPU restatement of composer/models/transformer.py; TensorFlow is not '
-              'installable here) training step, fp32, B=%d x T=%d per step, dropout off' % (batch, SEQ_LEN))
+    sample = ('oracle/transformer_oracle.py (CPU restatement of composer/models/transformer.py, pinned to the '
+              'reference\'s own model code under a TensorFlow stand-in; TensorFlow itself is not installable here) '
+              'training step, fp32, dropout 0.1 at every site, 1 of the %d sequences x T=%d per step, up to %d timed steps '
+              '(120 s budget) of %.1f s' % (args.batch, SEQ_LEN, max(1, args.steps), seconds))
+    gen_value, _, gen_seconds = cpu_reference_generate(4, 256)
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': seconds * 1e3, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'BASELINE.json configs[1]: training step, default_config.yml hyperparameters, '
-                               'window_size 2048', 'global_batch': batch, 'seq_len': SEQ_LEN,
-                   'parallelism': 'cpu x%d threads' % threads},
+        'config': gpu_config(world, args.batch),
+        'config_delta': {'per_step_batch': batch, 'why': 'bounded sample: a 32 x 2048 step of the fp32 CPU model needs '
+                                                         '>100 GB of attention matrices and ~1 minute; tokens/s is '
+                                                         'per token and does not depend on the batch',
+                         'dtype': 'f32 (the reference computes in fp32)', 'host_threads': threads},
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'generate': {'metric': 'generated events/s (KV-cache decode, temperature 1.0)', 'value': gen_value,
+                     'unit': 'events/s',
+                     'cpu_baseline': {'value': gen_value, 'unit': 'events/s', 'cores': threads, 'kind': 'port',
+                                      'sample': 'oracle cached decode (past=), fp32, 4 sequences x 256 events, '
+                                                '%.1f s' % gen_seconds}},
         'gpu_launches': 0,
     }
     print(json.dumps(line), flush=True)
@@ -273,30 +347,36 @@ def run_gpu(args):
     peaks, peak_kind = load_peaks()
     roofline, kernel_breakdown = None, None
     if rank == 0:
-        roofline, kernel_breakdown = dominant_kernel_roofline(model, B, T, peaks, peak_kind, seconds / K)
+        roofline, kernel_breakdown = dominant_kernel_roofline(model, B, T, peaks, peak_kind, seconds / K, clocks)
 
     # ---- generation (configs[2]): reported beside the headline, same run ----
     generate = None
     if args.generate:
-        generate = generation_benchmark(model, world, rank, device, dist if world > 1 else None)
+        generate = generation_benchmark(model, world, rank, device, dist if world > 1 else None,
+                                        cpu_baseline=not args.no_cpu_baseline)
+
+    # ---- the other single-GPU configurations of BASELINE.json, short runs (N = 1 only) ----
+    other = None
+    if world == 1 and args.other_configs:
+        del model
+        torch.cuda.empty_cache()
+        other = other_configs(peaks)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_value, threads, cpu_seconds = cpu_reference_step(1, T, 1, 1)
+        cpu_steps = 6
+        cpu_value, threads, cpu_seconds = cpu_reference_step(1, T, cpu_steps, 1)
         cpu = {'value': cpu_value, 'unit': UNIT, 'cores': threads, 'kind': 'port',
-               'sample': 'oracle training step (fp32 torch-CPU restatement of the reference; TensorFlow not '
-                         'installable), B=1 x T=%d, 1 warm-up + 1 timed step (%.1f s)' % (T, cpu_seconds)}
+               'sample': 'oracle training step (fp32 torch-CPU restatement of the reference, dropout 0.1; TensorFlow '
+                         'not installable), 1 of the %d sequences x T=%d per step, 1 warm-up + %d timed steps of %.1f s'
+                         % (B, T, cpu_steps, cpu_seconds)}
 
     if rank == 0:
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
             'ms_per_step': seconds / K * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'bf16', 'data': 'synthetic',
-            'config': {'workload': 'BASELINE.json configs[1]: Transformer training step bf16, seq len 2048 '
-                                   '(default_config.yml hyperparameters, window_size 2048, dropout 0.1)',
-                       'global_batch': world * B, 'per_gpu_batch': B, 'seq_len': T, 'vocab': VOCAB,
-                       'parallelism': 'dp%d' % world,
-                       'l2_policy': 'inputs larger than L2: each step streams >4 GB of activations'},
+            'config': gpu_config(world, B),
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': 2 * B * T * 4,
                     'd2h_bytes_per_step': 4, 'ms_per_step': e2e_seconds / K * 1e3},
@@ -307,6 +387,7 @@ def run_gpu(args):
             'kernels': kernel_breakdown,
             'cpu_baseline': cpu,
             'generate': generate,
+            'other_configs': other,
             'last_loss': losses[-1] / (B * T) if losses else None,
         }
         print(json.dumps(line), flush=True)
@@ -314,7 +395,7 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
-def dominant_kernel_roofline(model, B, T, peaks, peak_kind, step_seconds):
+def dominant_kernel_roofline(model, B, T, peaks, peak_kind, step_seconds, clocks=None):
     '''
     Times the kernels of one decoder block alone (CUDA events on the launch
     stream) and returns the roofline entry of the one that dominates the step,
@@ -364,30 +445,87 @@ def dominant_kernel_roofline(model, B, T, peaks, peak_kind, step_seconds):
                                      ptr(dq_acc), ptr(dqkv), B, T, H, D, scale, rate, 1, 1, 1, stream))
     pairs = B * H * T * (T + 1) / 2.0
     fwd_flops = 4.0 * D * pairs
-    bwd_flops = 2.5 * fwd_flops
-    traffic = None
+    # backward = 2 x forward FLOPs, the recomputation of S = Q K^T inside the kernel is not
+    # counted (`achieved`); `achieved_with_recompute` counts the 5 MMAs the kernel really issues (2.5 x forward).
+    bwd_flops = 2.0 * fwd_flops
+    traffic, traffic_note = None, 'no ncu capture of this source tree under profiles/'
     summary_path = os.path.join(ROOT, 'profiles', 'ncu_summary.json')
     if os.path.exists(summary_path):
+        from composer_b200 import build as native_build
         with open(summary_path) as handle:
             summary = json.load(handle)
         for name, entry in summary.items():
-            if name.startswith('attn_bwd_tc_kernel'):
+            if name.startswith('attn_bwd_tc_kernel') and entry.get('source_hash') == native_build.source_hash():
                 traffic = entry.get('dram_bytes_per_launch')
+                traffic_note = 'ncu --set full capture %s of this source tree (hash %s)' % (
+                    entry.get('capture', '?'), entry['source_hash'][:12])
     achieved = bwd_flops / t_bwd / 1e12
+    sm_mhz = (clocks or {}).get('sm_mhz') or 1965.0
+    exp_peak = 16 * 148 * sm_mhz * 1e6          # MUFU.EX2: 16 per clock per SM
     roofline = {
         'kernel': 'attn_bwd_tc_kernel<%d,1> (tcgen05 / TMEM; + delta and dq-store helpers), one decoder block' % D,
         'bound': 'tensor', 'achieved': achieved, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
-        'frac': achieved / peaks['bf16_tflops'], 'traffic': traffic, 'peak_source': peak_kind + ' (burst)',
-        'note': 'at d_h = 16 the kernel is bound by MUFU.EX2 / issue slots, not the tensor pipe: %.2f T '
-                'exponentials/s of ~4.5 T/s (16/clk/SM x 148 SMs x 1.9 GHz)' % (pairs / t_bwd / 1e12),
+        'frac': achieved / peaks['bf16_tflops'], 'traffic': traffic, 'traffic_source': traffic_note,
+        'peak_source': peak_kind + ' (burst)',
+        'flop_convention': 'SURVEY 8(d): 2 x forward, recompute not counted',
+        'achieved_with_recompute': 2.5 * fwd_flops / t_bwd / 1e12,
+        'exp_per_s': pairs / t_bwd, 'exp_peak_per_s': exp_peak, 'exp_frac': pairs / t_bwd / exp_peak,
+        'note': 'at d_h = 16 a score element costs one exponential and ~6 other instructions against 80 MMA FLOPs: '
+                'the kernel is measured against the MUFU.EX2 rate (16 / clk / SM x 148 SMs x the SM clock sampled '
+                'during the run) as well as the tensor peak',
         'share_of_step': L * t_bwd / step_seconds,
     }
     breakdown = {
         'attention_fwd_ms_per_block': t_fwd * 1e3, 'attention_bwd_ms_per_block': t_bwd * 1e3,
         'attention_share_of_step': L * (t_fwd + t_bwd) / step_seconds,
         'attention_fwd_tflops': fwd_flops / t_fwd / 1e12, 'attention_bwd_tflops': achieved,
+        'attention_fwd_exp_frac': pairs / t_fwd / exp_peak,
     }
     return roofline, breakdown
+
+
+def other_configs(peaks):
+    '''
+    configs[0], [3] and [4] of BASELINE.json on this GPU, short runs (3 warm-up + 3 timed steps each), so that the
+    numbers DESIGN.md quotes for them are driver-visible.  configs[1] is the headline above, configs[2] is `generate`.
+    '''
+
+    import numpy as np
+    import torch
+
+    from composer_b200.models.transformer import Transformer
+
+    def run(name, layers, embedding, heads, T, B, train):
+        model = Transformer(VOCAB, embedding, T, layers, heads, False, 0.0, 0.02, 0.1, 0.1, 1e-5, True, True, seed=0)
+        model.compile(1e-3)
+        rng = np.random.default_rng(0)
+        draw = torch.from_numpy(rng.integers(0, VOCAB, size=(B, T + 1)).astype(np.int32)).cuda()
+        x, y = draw[:, :-1].contiguous(), draw[:, 1:].contiguous()
+        fn = (lambda: model.train_step(x, y)) if train else (lambda: model.forward_loss(x, y, training=False))
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        for _ in range(3):
+            fn()
+        end.record()
+        torch.cuda.synchronize()
+        seconds = start.elapsed_time(end) * 1e-3 / 3
+        flops = step_flops_per_token(layers, embedding, VOCAB, T) / (1 if train else 3)
+        tokens_per_s = B * T / seconds
+        del model
+        torch.cuda.empty_cache()
+        return {'config': name, 'layers': layers, 'embedding_size': embedding, 'heads': heads, 'seq_len': T,
+                'per_gpu_batch': B, 'phase': 'train step' if train else 'forward + loss', 'dropout': 0.1 if train else 0.0,
+                'tokens_per_s': tokens_per_s, 'ms_per_step': seconds * 1e3,
+                'algorithmic_tflops': tokens_per_s * flops / 1e12,
+                'frac_of_sustained_bf16_peak': tokens_per_s * flops / 1e12 / peaks['bf16_tflops_sustained']}
+
+    return [run('configs[0] forward + loss, default hyperparameters, B 4 x T 1024', 8, 256, 16, 1024, 4, False),
+            run('configs[3] long-context training step, T 4096, B 16', 8, 256, 16, 4096, 16, True),
+            run('configs[4] scaled Transformer (12 layers, d_model 1024) training step, T 1024, B 16', 12, 1024, 16,
+                1024, 16, True)]
 
 
 def decode_implementation(model, batch):
@@ -408,7 +546,7 @@ def decode_implementation(model, batch):
             'clusters': clusters, 'co_resident_clusters': cap, 'launches_per_generation': 3}
 
 
-def generation_benchmark(model, world, rank, device, dist):
+def generation_benchmark(model, world, rank, device, dist, cpu_baseline=True):
     '''configs[2]: 256 sequences sharded over the GPUs, prompt 1, 1024 events, temperature 1.0, KV cache.'''
 
     import numpy as np
@@ -437,7 +575,7 @@ def generation_benchmark(model, world, rank, device, dist):
         torch.cuda.synchronize()
         start = time.perf_counter()
         out = gen_model.generate(prompt, length, temperature=1.0, seed=7, sequence_index_base=rank * per_rank)
-        torch.cuda.synchronize()
+        host_ids = out.cpu()                        # the ids leave the device inside the timed region
         elapsed = torch.tensor([time.perf_counter() - start], device=device, dtype=torch.float64)
         if dist is not None:
             dist.all_reduce(elapsed, op=dist.ReduceOp.MAX)
@@ -455,17 +593,25 @@ def generation_benchmark(model, world, rank, device, dist):
     if world == 1 and os.path.exists(summary_path):
         with open(summary_path) as handle:
             entry = json.load(handle).get('decode_mega_kernel<16, 4>')
-        if entry and 'prompt 1, 1,024 events' in entry.get('capture', ''):
+        from composer_b200 import build as native_build
+        if entry and 'prompt 1, 1,024 events' in entry.get('capture', '') \
+                and entry.get('source_hash') == native_build.source_hash():
             traffic = entry.get('dram_bytes_per_launch')
+    cpu = None
+    if rank == 0 and world == 1 and cpu_baseline:
+        cpu_value, threads, cpu_seconds = cpu_reference_generate(4, 256)
+        cpu = {'value': cpu_value, 'unit': 'events/s', 'cores': threads, 'kind': 'port',
+               'sample': 'oracle cached decode (past=), fp32, 4 sequences x 256 events (%.1f s)' % cpu_seconds}
     return {'metric': 'generated events/s (256 sequences x 1024 events, temperature 1.0, KV-cache decode)',
             'value': total * length / seconds, 'unit': 'events/s', 'seconds': seconds, 'seconds_of_each_run': runs,
+            'd2h_bytes_per_generation': int(host_ids.numel() * host_ids.element_size()), 'cpu_baseline': cpu,
             'sequences_per_gpu': per_rank,
             'us_per_step': seconds / length * 1e6,
             'roofline': {'bound': 'hbm', 'achieved': bytes_per_gpu / seconds / 1e9, 'peak': peaks['hbm_gbs'],
                          'unit': 'GB/s', 'frac': bytes_per_gpu / seconds / 1e9 / peaks['hbm_gbs'], 'traffic': traffic,
                          'algorithmic_bytes': bytes_per_gpu,
                          'peak_source': kind},
-            'sample_ids': out[0, :8].tolist(),
+            'sample_ids': host_ids[0, :8].tolist(),
             'implementation': decode_implementation(gen_model, per_rank)}
 
 
@@ -478,6 +624,7 @@ def main():
     parser.add_argument('--batch', type=int, default=BATCH_PER_GPU, help='sequences per GPU')
     parser.add_argument('--no-generate', dest='generate', action='store_false')
     parser.add_argument('--no-cpu-baseline', action='store_true')
+    parser.add_argument('--no-other-configs', dest='other_configs', action='store_false')
     args = parser.parse_args()
     if args.impl == 'reference':
         run_reference(args)
