@@ -357,7 +357,7 @@ attn_dq_store_kernel(float* __restrict__ dq_acc, __nv_bfloat16* __restrict__ dqk
 // ---------------------------------------------------------------------------
 // Host launchers
 // ---------------------------------------------------------------------------
-static int g_attention_fwd_impl = 0;   // 0: tcgen05, P in TMEM (TS MMA); 1: round-1 mma.sync kernel; 2: tcgen05, P through smem; 3, 4: tile-shape variants of 0
+static int g_attention_fwd_impl = 0;   // 0: tcgen05, P in TMEM (TS MMA); 1: round-1 mma.sync kernel; 2: tcgen05, P through smem; 3, 4: tile-shape variants of 0; 7: 0 with two threads per score row
 void attention_set_fwd_impl(int impl) { g_attention_fwd_impl = impl; }
 
 static const float kLog2e = 1.4426950408889634f;

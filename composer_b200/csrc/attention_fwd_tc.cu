@@ -27,28 +27,35 @@
 
 namespace cb200 {
 
-constexpr int TCF_THREADS = 256;
+constexpr int TCF_THREADS = 256;          // row split 1; (4 RS + 4) * 32 in general
 
 // KT: keys per tile = the part of a score row a thread holds in registers.  CPS: CTAs per SM.  Four softmax warps
 // per CTA means CPS softmax warps per scheduler: KT 128 needs ~180 registers per softmax thread (2 CTAs per SM), KT 64
 // about 110 (3 or 4 per SM: more warps to hide the MUFU / TMEM / barrier latencies, twice the per-tile hand-offs).
-template <int D, bool PSMEM, int KT_, int CPS_>
+// RS: threads per score row.  With RS = 2 a row's KT keys are split between two warps of the same TMEM lane quadrant
+// (8 softmax warps per CTA, 4 per scheduler with two CTAs per SM): one warp alone reaches ~70 % of the MUFU rate
+// (tools/cuda/pipe_bench.cu), so the exponentials only run at full rate while two warps of a scheduler are in their
+// arithmetic phase at the same time, which two softmax warps per scheduler rarely are.
+template <int D, bool PSMEM, int KT_, int CPS_, int RS_ = 1>
 struct TcfCfg {
-    static constexpr int KT = KT_, CPS = CPS_;
+    static constexpr int KT = KT_, CPS = CPS_, RS = RS_;
+    static constexpr int THREADS = (4 * RS_ + 4) * 32;
     static constexpr int RB = 2 * D;                        // bytes per row of a Q / K / V tile
     static constexpr int QTILE = 128 * RB;
     static constexpr int KTILE = KT * RB;
     static constexpr int NKV = (D == 64) ? 3 : 4;           // K / V ring stages
     static constexpr int PBYTES = (KT / 64) * 128 * 128;    // P in shared memory: 64-key halves of [128 rows][128 B]
-    static constexpr size_t SMEM = 2 * QTILE + NKV * 2 * KTILE + (PSMEM ? 2 * PBYTES : 0) + 256 + 1024;
+    static constexpr int XBYTES = (RS_ > 1) ? 3 * RS_ * 128 * 4 : 0;     // row maxima (2 slots, by tile parity) / sums (1 slot) exchanged between the RS threads of a row
+    static constexpr size_t SMEM = 2 * QTILE + NKV * 2 * KTILE + (PSMEM ? 2 * PBYTES : 0) + XBYTES + 256 + 1024;
     // TMEM: two buffers; a buffer holds S (KT fp32 columns), later P (KT/2 columns of bf16 pairs) and O~ (D columns)
     static constexpr int COL_O = KT / 2;
     static constexpr int BUF_COLS = (KT / 2 + D <= 64 && KT <= 64) ? 64 : 128;
     static constexpr int TMEM_COLS = 2 * BUF_COLS;
     // registers after setmaxnreg: 128 * (SOFTMAX + CONTROL) = the CTA's share of the register file
-    static constexpr int LAUNCH_REGS = (65536 / (CPS * TCF_THREADS)) / 8 * 8;
-    static constexpr int CONTROL_REGS = (CPS == 2) ? 56 : 24;
-    static constexpr int SOFTMAX_REGS = 2 * LAUNCH_REGS - CONTROL_REGS;
+    static constexpr int LAUNCH_REGS = (65536 / (CPS * THREADS)) / 8 * 8;
+    static constexpr int CONTROL_REGS = (RS_ > 1) ? 32 : (CPS == 2) ? 56 : 24;
+    // what the control warpgroup releases is shared by the 4 RS softmax warps
+    static constexpr int SOFTMAX_REGS = (LAUNCH_REGS + (LAUNCH_REGS - CONTROL_REGS) / RS_) / 8 * 8;
     static_assert(COL_O + D <= BUF_COLS && KT <= BUF_COLS, "TMEM buffer layout");
     static_assert(CPS * TMEM_COLS <= 512, "TMEM budget");
 };
@@ -64,13 +71,16 @@ struct TcfCursor {
 };
 
 // ABL: timing-only ablations (results wrong): 1 no max pass, 2 no MUFU (multiply instead), 4 no P store, 8 no O~ load
-template <int D, bool DROP, bool PSMEM, int KT_, int CPS_, int ABL = 0>
-__global__ void __launch_bounds__(TCF_THREADS, CPS_)
+template <int D, bool DROP, bool PSMEM, int KT_, int CPS_, int ABL = 0, int RS = 1>
+__global__ void __launch_bounds__((4 * RS + 4) * 32, CPS_)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                    __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int T, int H, int BH, int nq,
                    float scale_log2, AttnDropKey drop, long long* __restrict__ trace) {
-    using C = TcfCfg<D, PSMEM, KT_, CPS_>;
-    constexpr int KT = C::KT, RB = C::RB, QTILE = C::QTILE, KTILE = C::KTILE, NKV = C::NKV, NCH = KT / 32;
+    using C = TcfCfg<D, PSMEM, KT_, CPS_, RS>;
+    static_assert(RS == 1 || (RS == 2 && !PSMEM && KT_ == 128), "row split: two threads per row of a 128-key tile, P in TMEM");
+    constexpr int KT = C::KT, RB = C::RB, QTILE = C::QTILE, KTILE = C::KTILE, NKV = C::NKV, NCH = KT / 32 / RS;
+    constexpr int KW = KT / RS;                                 // keys per thread and tile
+    constexpr int SW = 4 * RS;                                  // softmax warps; then: S issuer, TMA producer, TMEM allocation, P V issuer
     constexpr uint32_t LT = umma_layout_for_row_bytes(RB);
     constexpr uint32_t COL_O = C::COL_O, BUFC = C::BUF_COLS;
 
@@ -81,7 +91,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     const uint32_t sK = sQ + 2 * QTILE;                     // [NKV][KTILE]
     const uint32_t sV = sK + NKV * KTILE;                   // [NKV][KTILE]
     const uint32_t sP = sV + NKV * KTILE;                   // [2][PBYTES] (PSMEM only)
-    const uint32_t bars = sP + (PSMEM ? 2 * C::PBYTES : 0);
+    const uint32_t sX = sP + (PSMEM ? 2 * C::PBYTES : 0);   // [3][RS][128] floats (row split only)
+    const uint32_t bars = sX + C::XBYTES;
     const uint32_t bar_q_full = bars;                       // [2] Q tile landed
     const uint32_t bar_q_free = bars + 16;                  // [2] the item's last S MMA has read it
     const uint32_t bar_kv_full = bars + 32;                 // [NKV]
@@ -105,16 +116,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     };
     TR(1);
 
-    if (warp == 4 && lane == 0) {
+    if (warp == SW && lane == 0) {
         tma_prefetch_desc(&tm_q);
         tma_prefetch_desc(&tm_kv);
         for (int i = 0; i < 2; ++i) {
             mbar_init_a(bar_q_full + 8 * i, 1);
             mbar_init_a(bar_q_free + 8 * i, 1);
             mbar_init_a(bar_s_full + 8 * i, 1);
-            mbar_init_a(bar_p_full + 8 * i, 128);
+            mbar_init_a(bar_p_full + 8 * i, 128 * RS);
             mbar_init_a(bar_o_full + 8 * i, 1);
-            mbar_init_a(bar_buf_free + 8 * i, 128);
+            mbar_init_a(bar_buf_free + 8 * i, 128 * RS);
         }
         for (int i = 0; i < NKV; ++i) {
             mbar_init_a(bar_kv_full + 8 * i, 1);
@@ -122,7 +133,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         }
         mbar_fence_init();
     }
-    if (warp == 6) {
+    if (warp == SW + 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(C::TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -147,9 +158,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         }
     };
 
-    if (warp >= 4) {
+    if (warp >= SW) {
         setmaxnreg_dec<C::CONTROL_REGS>();
-        if (warp == 5) {
+        if (warp == SW + 1) {
             // ===================== TMA producer =====================
             if (elect_one()) {
                 TcfCursor c{static_cast<int>(blockIdx.x), 0, 0, 0, 0, 0, 0};
@@ -171,7 +182,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                     advance(c);
                 }
             }
-        } else if (warp == 4) {
+        } else if (warp == SW) {
             // ===================== S issuer (runs one tile ahead of the softmax) =====================
             // Two issuing threads (S here, P V in warp 7): an issuing thread runs alone at one instruction every few
             // cycles, and with 9 small MMAs per tile that instruction stream is a large part of a tile's critical path.
@@ -199,7 +210,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                     advance(c);
                 }
             }
-        } else if (warp == 7) {
+        } else if (warp == SW + 3) {
             // ===================== P V issuer =====================
             if (elect_one()) {
                 constexpr uint32_t IDESC_O = umma_idesc_bf16(128, D, 0, 1);      // P V (V is MN-major)
@@ -232,24 +243,37 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
             }
         }
     } else {
-        // ===================== softmax warps: thread = query row =====================
+        // ===================== softmax warps: thread = query row (RS = 2: half of one) =====================
         setmaxnreg_inc<C::SOFTMAX_REGS>();
-        const int r = warp * 32 + lane;
-        const uint32_t t_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+        const int quad = warp & 3;                          // TMEM lane quadrant = 32-row band of the tile
+        const int part = warp >> 2;                         // which KW-key part of a row this thread owns
+        const int r = quad * 32 + lane;
+        const uint32_t t_lane = tmem + (static_cast<uint32_t>(quad * 32) << 16);
         const float thr = __uint_as_float(drop.thr_bits);
         const float ks_scale = DROP ? drop.keep_scale : 1.0f;
         const uint64_t c2 = f2_pack(scale_log2, scale_log2);
+        constexpr int DW = D / RS;                          // output columns folded and stored by this thread
+        // exchange between the RS threads of a row: a named barrier per lane quadrant, values through shared memory
+        auto exchange = [&](int slot, float mine) -> float {
+            if (RS == 1) return mine;
+            const uint32_t base = sX + static_cast<uint32_t>(slot * RS * 128 * 4);
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(base + (part * 128 + r) * 4), "f"(mine) : "memory");
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "n"(32 * RS) : "memory");
+            float other;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(other) : "r"(base + ((part ^ 1) * 128 + r) * 4) : "memory");
+            return other;
+        };
         int g = 0;
         for (int item = blockIdx.x; item < items; item += gridDim.x) {
             const int qi = nq - 1 - item / BH, bh = item % BH;
             const int b = bh / H, h = bh % H;
             const int n = (qi + 1) * (128 / KT);
             const int row_g = qi * 128 + r;                 // query row inside the sequence
-            const int rmin = qi * 128 + warp * 32, rmax = rmin + 31;
+            const int rmin = qi * 128 + quad * 32, rmax = rmin + 31;
             const uint32_t dbase = DROP ? attn_drop_base(drop, bh) : 0u;
-            float o_acc[D];
+            float o_acc[DW];
 #pragma unroll
-            for (int d = 0; d < D; ++d) o_acc[d] = 0.f;
+            for (int d = 0; d < DW; ++d) o_acc[d] = 0.f;
             float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
 
             auto fold_o = [&](int gp) {                     // o = o * alpha + O~ of tile gp, then release its buffer
@@ -257,14 +281,18 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                 mbar_wait_a(bar_o_full + 8 * pb, (gp >> 1) & 1);
                 tc_fence_after();
                 TR(35);
+                uint32_t op[DW];
+                if (!(ABL & 8)) {
+                    if (DW == 8) tmem_ld8(t_lane + pb * BUFC + COL_O + part * DW, *reinterpret_cast<uint32_t(*)[8]>(&op[0]));
+                    else {
 #pragma unroll
-                for (int d0 = 0; d0 < D; d0 += 16) {
-                    uint32_t op[16];
-                    if (!(ABL & 8)) tmem_ld16(t_lane + pb * BUFC + COL_O + d0, op);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int d = 0; d < 16; ++d) o_acc[d0 + d] = fmaf(o_acc[d0 + d], alpha_prev, __uint_as_float(op[d]));
+                        for (int d0 = 0; d0 < DW; d0 += 16)
+                            tmem_ld16(t_lane + pb * BUFC + COL_O + part * DW + d0, *reinterpret_cast<uint32_t(*)[16]>(&op[d0 % DW]));
+                    }
                 }
+                tmem_ld_wait();
+#pragma unroll
+                for (int d = 0; d < DW; ++d) o_acc[d] = fmaf(o_acc[d], alpha_prev, __uint_as_float(op[d]));
                 tc_fence_before();
                 mbar_arrive_a(bar_buf_free + 8 * pb);
             };
@@ -275,19 +303,19 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                 mbar_wait_a(bar_s_full + 8 * buf, (g >> 1) & 1);
                 tc_fence_after();
                 TR(30);
-                uint32_t s[KT];
+                uint32_t s[KW];
 #pragma unroll
-                for (int c = 0; c < NCH; ++c) tmem_ld32(tbuf + 32 * c, *reinterpret_cast<uint32_t(*)[32]>(&s[32 * c]));
+                for (int c = 0; c < NCH; ++c) tmem_ld32(tbuf + part * KW + 32 * c, *reinterpret_cast<uint32_t(*)[32]>(&s[32 * c]));
                 if (j > 0) fold_o(g - 1);                   // (its tcgen05.wait::ld also covers the S loads above)
                 else tmem_ld_wait();
                 TR(31);
 
-                const int key0 = j * KT;
-                const bool diag = key0 + KT - 1 > qi * 128;  // some key of the tile lies above some row of the q tile
+                const int key0 = j * KT + part * KW;        // first key of this thread's part
+                const bool diag = j * KT + KT - 1 > qi * 128;   // some key of the tile lies above some row of the q tile
                 uint32_t x = 0;
                 if (DROP) {
                     x = attn_row_seed(dbase, static_cast<uint32_t>(row_g), static_cast<uint32_t>(key0 >> 7));
-                    if (KT == 64 && (key0 & 64)) x *= mcg_mul_pow(32);
+                    if (key0 & 64) x *= mcg_mul_pow(32);
                 }
                 float alpha = 0.f;
                 uint64_t sum_a = f2_pack(0.f, 0.f), sum_b = sum_a;
@@ -296,7 +324,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                 auto tile_math = [&](auto masked) {
                     constexpr bool MASKED = decltype(masked)::value;
                     // ---- running max ----
-                    float mx0 = m_run, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+                    float mx0 = (RS == 1) ? m_run : -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
                     for (int c = 0; c < ((ABL & 1) ? 0 : NCH); ++c) {
                         const int kmin = key0 + 32 * c;
@@ -315,6 +343,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                         }
                     }
                     float m_new = fmaxf(fmax3f(mx0, mx1, mx2), mx3);
+                    if (RS > 1) m_new = fmax3f(m_run, m_new, exchange(g & 1, m_new));   // the row's other part
                     if (ABL & 1) m_new = 8.f;
                     alpha = fast_exp2((m_run - m_new) * scale_log2);   // first tile: exp2(-inf) = 0
                     m_run = m_new;
@@ -358,7 +387,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                                              "r"(pk[4 * q4 + 1]), "r"(pk[4 * q4 + 2]), "r"(pk[4 * q4 + 3]) : "memory");
                             }
                         } else {
-                            if (!(ABL & 4)) tmem_st16(tbuf + 16 * c, pk);
+                            if (!(ABL & 4)) tmem_st16(tbuf + part * (KW / 2) + 16 * c, pk);
                             else asm volatile("" ::"r"(pk[0] ^ pk[5] ^ pk[10] ^ pk[15]));
                         }
                     }
@@ -368,7 +397,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                 float sa0, sa1, sb0, sb1;
                 f2_unpack(sum_a, sa0, sa1);
                 f2_unpack(sum_b, sb0, sb1);
-                l_run = fmaf(l_run, alpha, (sa0 + sa1) + (sb0 + sb1));
+                l_run = fmaf(l_run, alpha, (sa0 + sa1) + (sb0 + sb1));     // (RS = 2: the sum over this thread's part)
                 if (PSMEM) {
                     fence_proxy_async_smem();
                 } else {
@@ -381,13 +410,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                 alpha_prev = alpha;
             }
             fold_o(g - 1);
+            if (RS > 1) l_run += exchange(2, l_run);
 
             // ---- finalize the row ----
             if (row_g < T) {
                 const float inv = ks_scale / l_run;
-                __nv_bfloat16* dst = out + (static_cast<size_t>(b) * T + row_g) * E + h * D;
+                __nv_bfloat16* dst = out + (static_cast<size_t>(b) * T + row_g) * E + h * D + part * DW;
 #pragma unroll
-                for (int d0 = 0; d0 < D; d0 += 8) {
+                for (int d0 = 0; d0 < DW; d0 += 8) {
                     uint4 v;
                     v.x = pack_bf16(o_acc[d0] * inv, o_acc[d0 + 1] * inv);
                     v.y = pack_bf16(o_acc[d0 + 2] * inv, o_acc[d0 + 3] * inv);
@@ -395,7 +425,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                     v.w = pack_bf16(o_acc[d0 + 6] * inv, o_acc[d0 + 7] * inv);
                     *reinterpret_cast<uint4*>(dst + d0) = v;
                 }
-                if (lse != nullptr) lse[(static_cast<size_t>(b) * H + h) * T + row_g] = fmaf(m_run, scale_log2, log2f(l_run));
+                if (lse != nullptr && part == 0) lse[(static_cast<size_t>(b) * H + h) * T + row_g] = fmaf(m_run, scale_log2, log2f(l_run));
             }
         }
     }
@@ -403,16 +433,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     if (tr != nullptr) tr[0] = tr_n;
     tc_fence_before();
     __syncthreads();
-    if (warp == 6) {
+    if (warp == SW + 2) {
         tc_fence_after();
         tmem_dealloc<C::TMEM_COLS>(tmem);
     }
 }
 
-template <int D, bool DROP, bool PSMEM, int KT, int CPS, int ABL = 0>
+template <int D, bool DROP, bool PSMEM, int KT, int CPS, int ABL = 0, int RS = 1>
 static int launch_fwd_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse, int B, int T, int H, float scale,
                          const AttnDropKey& key, cudaStream_t s) {
-    using C = TcfCfg<D, PSMEM, KT, CPS>;
+    using C = TcfCfg<D, PSMEM, KT, CPS, RS>;
     constexpr size_t smem = C::SMEM;
     const int E = H * D;
     CUtensorMap tm_q, tm_kv;
@@ -420,7 +450,7 @@ static int launch_fwd_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* ls
     if (rc) return rc;
     rc = make_tmap_bf16_sw(&tm_kv, qkv, 3 * E, static_cast<uint64_t>(B) * T, 3 * E, D, C::KT, C::RB);
     if (rc) return rc;
-    auto kernel = attn_fwd_tc_kernel<D, DROP, PSMEM, KT, CPS, ABL>;
+    auto kernel = attn_fwd_tc_kernel<D, DROP, PSMEM, KT, CPS, ABL, RS>;
     static bool configured = false;
     if (!configured) {
         CB200_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -433,7 +463,7 @@ static int launch_fwd_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* ls
     const long long items = static_cast<long long>(nq) * B * H;
     long long grid = static_cast<long long>(per_sm) * device_sm_count();
     if (grid > items) grid = items;
-    kernel<<<static_cast<int>(grid), TCF_THREADS, smem, s>>>(tm_q, tm_kv, out, lse, T, H, B * H, nq,
+    kernel<<<static_cast<int>(grid), C::THREADS, smem, s>>>(tm_q, tm_kv, out, lse, T, H, B * H, nq,
                                                               scale * 1.4426950408889634f, key, attention_get_trace());
     CB200_CUDA_OK(cudaGetLastError());
     note_launch(1);
@@ -460,6 +490,9 @@ int attention_fwd_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse, i
         case 16:
             if (variant == 3) return launch_fwd_tc_d<16, 64, 3>(qkv, out, lse, B, T, H, scale, key, false, s);
             if (variant == 4) return launch_fwd_tc_d<16, 64, 4>(qkv, out, lse, B, T, H, scale, key, false, s);
+            if (variant == 7)       // two threads per row: 8 softmax warps per CTA
+                return key.thr_bits != 0 ? launch_fwd_tc<16, true, false, 128, 2, 0, 2>(qkv, out, lse, B, T, H, scale, key, s)
+                                         : launch_fwd_tc<16, false, false, 128, 2, 0, 2>(qkv, out, lse, B, T, H, scale, key, s);
             if (variant >= 100) {   // timing-only ablations of the default shape, dropout off
                 switch (variant - 100) {
                     case 1: return launch_fwd_tc<16, false, false, 128, 2, 1>(qkv, out, lse, B, T, H, scale, key, s);

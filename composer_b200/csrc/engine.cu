@@ -1015,7 +1015,7 @@ int cb200_set_decode_profile(void* counters) {
 }
 
 int cb200_set_attention_fwd_impl(int impl) {
-    CB200_REQUIRE((impl >= 0 && impl <= 4) || (impl >= 100 && impl < 200),
+    CB200_REQUIRE((impl >= 0 && impl <= 4) || impl == 7 || (impl >= 100 && impl < 200),
                   "attention forward implementation must be 0 (tcgen05, P in TMEM), 1 (mma.sync), 2 (tcgen05, P in smem) "
                   "or 3 / 4 (tile-shape variants of 0)");
     attention_set_fwd_impl(impl);

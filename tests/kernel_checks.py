@@ -301,20 +301,23 @@ def _attention_reference(qkv, B, T, H, D, scale, keep=None, rate=0.0):
     return out
 
 
-def check_attention(B=2, T=200, H=16, D=16, rate=0.0, backward=True, fwd_impl=0):
+def check_attention(B=2, T=200, H=16, D=16, rate=0.0, backward=True, fwd_impl=0, sharp=1.0):
     '''fwd_impl: 0 = tcgen05 with P in TMEM (default), 1 = round-1 mma.sync kernel, 2 = tcgen05 with P through smem,
-    3 / 4 = tile-shape variants of 0 (d_h 16).'''
+    3 / 4 = tile-shape variants of 0 (d_h 16), 7 = 0 with two threads per score row.  ``sharp`` scales the scores
+    (their standard deviation, in nats).'''
     _lib.call('cb200_set_attention_fwd_impl', fwd_impl)
     try:
-        return _check_attention(B, T, H, D, rate, backward)
+        return _check_attention(B, T, H, D, rate, backward, sharp)
     finally:
         _lib.call('cb200_set_attention_fwd_impl', 0)
 
 
-def _check_attention(B, T, H, D, rate, backward):
+def _check_attention(B, T, H, D, rate, backward, sharp=1.0):
     E = H * D
     scale = 1.0 / math.sqrt(D)
     qkv = _randn(B, T, 3 * E, scale=1.0, seed=61)
+    if sharp != 1.0:
+        qkv[..., :2 * E] = (qkv[..., :2 * E].float() * math.sqrt(sharp)).to(torch.bfloat16)
     out = torch.full((B, T, E), float('nan'), dtype=torch.bfloat16, device=DEV)
     lse = torch.empty((B, H, T), dtype=torch.float32, device=DEV)
     _lib.call('cb200_attention_fwd', ptr(qkv), ptr(out), ptr(lse), B, T, H, D, scale, rate, 123, 7, 3, stream())
@@ -411,6 +414,17 @@ GROUPS = {
                       # more work items than resident CTAs (persistent loop, Q / K / V rings wrap, both S buffers)
                       lambda: check_attention(6, 1024, 16, 16, rate=0.1, backward=False),
                       lambda: check_attention(2, 640, 16, 64, rate=0.1, backward=False),
+                      # sharp attention: the lazy softmax reference has to rescale the accumulator (slow path)
+                      lambda: check_attention(2, 1024, 4, 16, rate=0.1, backward=False, sharp=24.0),
+                      lambda: check_attention(1, 512, 2, 64, backward=False, sharp=12.0),
+                      # two threads per score row (8 softmax warps per CTA)
+                      lambda: check_attention(2, 200, 16, 16, rate=0.1, backward=False, fwd_impl=7),
+                      lambda: check_attention(6, 1024, 16, 16, rate=0.1, backward=False, fwd_impl=7),
+                      lambda: check_attention(2, 1024, 4, 16, backward=False, sharp=24.0, fwd_impl=7),
+                      # the first tcgen05 kernel (O~ folded per tile)
+                      lambda: check_attention(2, 200, 16, 16, rate=0.1, backward=False, fwd_impl=6),
+                      lambda: check_attention(6, 1024, 16, 16, rate=0.1, backward=False, fwd_impl=6),
+                      lambda: check_attention(2, 384, 4, 64, rate=0.1, backward=False, fwd_impl=6),
                       # the other two forward implementations: P staged through shared memory, round-1 mma.sync kernel
                       lambda: check_attention(2, 200, 16, 16, rate=0.1, backward=False, fwd_impl=2),
                       lambda: check_attention(6, 1024, 16, 16, backward=False, fwd_impl=2),

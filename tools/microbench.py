@@ -102,9 +102,9 @@ def main():
     out = torch.empty(B, T, E, device=dev, dtype=bf)
     lse = torch.empty(B, H, T, device=dev)
     att_flops = 4.0 * B * H * T * (T + 1) / 2 * D
-    impl_names = {0: 'tcgen05, P in TMEM', 3: 'tcgen05 TS, KT 64, 3 CTA/SM', 4: 'tcgen05 TS, KT 64, 4 CTA/SM', 2: 'tcgen05, P via smem',
+    impl_names = {0: 'tcgen05, P in TMEM', 7: 'tcgen05, two threads per row', 3: 'tcgen05 TS, KT 64, 3 CTA/SM', 4: 'tcgen05 TS, KT 64, 4 CTA/SM', 2: 'tcgen05, P via smem',
                   1: 'mma.sync (round 1)'}
-    for impl in (0, 3, 4, 2, 1):
+    for impl in (0, 7, 1):
         _lib.call('cb200_set_attention_fwd_impl', impl)
         for rate in (0.0, 0.1):
             try:

@@ -9,6 +9,8 @@ dev = 'cuda'
 ptr = lambda t: ctypes.c_void_p(t.data_ptr())
 stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 rate = float(sys.argv[1]) if len(sys.argv) > 1 else 0.0
+if len(sys.argv) > 2:
+    _lib.call('cb200_set_attention_fwd_impl', int(sys.argv[2]))
 qkv = torch.randn(B, T, 3 * E, device=dev).to(torch.bfloat16)
 out = torch.empty(B, T, E, device=dev, dtype=torch.bfloat16)
 lse = torch.empty(B, H, T, device=dev)
