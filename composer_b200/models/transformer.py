@@ -24,7 +24,7 @@ from pathlib import Path
 import numpy as np
 import torch
 
-from composer_b200 import ModelSaveFrequencyMode, _lib, parallel
+from composer_b200 import ModelSaveFrequencyMode, _lib, parallel, tf_checkpoint
 from composer_b200.models.base import BaseModel
 
 CHECKPOINT_INDEX = 'checkpoint.json'
@@ -613,13 +613,62 @@ class Transformer(BaseModel):
 
     @staticmethod
     def latest_checkpoint(restoredir):
+        '''
+        The newest checkpoint of ``restoredir``: this package's ``ckpt-N.npz`` (via ``checkpoint.json``) or, in a
+        log directory written by the reference itself, the TensorFlow checkpoint prefix its ``checkpoint`` state file
+        names (``tf.train.latest_checkpoint``, models/__init__.py:79).
+        '''
+
         index_path = Path(restoredir) / CHECKPOINT_INDEX
-        if not index_path.exists():
-            return None
-        latest = json.loads(index_path.read_text()).get('latest')
-        return str(Path(restoredir) / latest) if latest else None
+        if index_path.exists():
+            latest = json.loads(index_path.read_text()).get('latest')
+            return str(Path(restoredir) / latest) if latest else None
+        return tf_checkpoint.latest_checkpoint(str(restoredir))
+
+    def _restore_tf(self, prefix, with_optimizer):
+        '''A checkpoint the reference wrote (``tf.train.Checkpoint(step, epoch, optimizer, model)``, transformer.py:890).'''
+
+        bundle = tf_checkpoint.read_bundle(prefix)
+        shapes = {name: self._shape_of(name) for name in self._layout}
+        weights, adam_m, adam_v, counters = tf_checkpoint.to_arrays(bundle, list(self._layout), shapes)
+        self.set_weights(weights)
+        self._global_step = counters.get('step', 1)
+        self._epoch = counters.get('epoch', 1)
+        if with_optimizer and len(adam_m) == len(self._layout) and len(adam_v) == len(self._layout):
+            self._bind(1, min(self.window_size, 64), training=True)
+            for slots, arena in ((adam_m, self._adam_m), (adam_v, self._adam_v)):
+                host = np.zeros(arena.numel(), dtype=np.float32)
+                for name, (offset, rows, cols) in self._layout.items():
+                    host[offset:offset + rows * cols] = slots[name].reshape(-1)
+                arena.copy_(torch.from_numpy(host))
+            self._adam_t = counters.get('iterations', 0)
+
+    def export_tf_checkpoint(self, logdir, number=1):
+        '''
+        Writes the variables (and Adam slots / counters when they exist) as ``<logdir>/ckpt-<number>`` in
+        TensorFlow's checkpoint format under the reference's object-graph names, plus the ``checkpoint`` state
+        file, so that a name-based restore on the reference side (``tf.train.load_checkpoint`` /
+        ``load_variable``) finds every tensor where its own ``CheckpointManager.save`` puts it.
+        '''
+
+        logdir = Path(logdir)
+        logdir.mkdir(parents=True, exist_ok=True)
+        weights = self.get_weights()
+        adam_m = adam_v = None
+        if self._adam_m is not None:
+            m_host, v_host = self._adam_m.detach().cpu().numpy(), self._adam_v.detach().cpu().numpy()
+            adam_m = {n: m_host[o:o + r * c].reshape(self._shape_of(n)) for n, (o, r, c) in self._layout.items()}
+            adam_v = {n: v_host[o:o + r * c].reshape(self._shape_of(n)) for n, (o, r, c) in self._layout.items()}
+        counters = {'step': self._global_step, 'epoch': self._epoch, 'iterations': self._adam_t}
+        prefix = str(logdir / ('ckpt-%d' % number))
+        tf_checkpoint.write_bundle(prefix, tf_checkpoint.from_arrays(weights, adam_m, adam_v, counters))
+        (logdir / 'checkpoint').write_text('model_checkpoint_path: "ckpt-%d"\nall_model_checkpoint_paths: "ckpt-%d"\n'
+                                           % (number, number))
+        return prefix
 
     def _restore(self, path, with_optimizer):
+        if not str(path).endswith('.npz'):
+            return self._restore_tf(str(path), with_optimizer)
         data = np.load(path)
         self.set_weights({name: data['variables/' + name] for name in self._layout})
         self._global_step = int(data['step'])

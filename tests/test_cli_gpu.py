@@ -112,3 +112,44 @@ def test_scaled_configuration_matches_oracle():
 def test_head_size_32_matches_oracle():
     import kernel_checks
     kernel_checks.check_engine_forward_backward(B=2, T=80, layers=1, embedding=512, heads=16)
+
+
+def test_tensorflow_checkpoint_restores_into_the_engine(tmp_path):
+    '''
+    A log directory in the reference's checkpoint format (tensor bundle + ``checkpoint`` state file, object-graph
+    names ``model/decoder_blocks/<i>/...``; here written by ``export_tf_checkpoint``) restores through the same
+    ``load_from_checkpoint`` / ``train(restoredir=...)`` entry points as this package's own files: variables,
+    Adam slots and counters.
+    '''
+    import torch
+    from composer_b200.models.transformer import Transformer
+
+    def make(seed):
+        return Transformer(390, 256, 64, 2, 16, False, 0.0, 0.02, 0.0, 0.0, 1e-5, True, True, seed=seed)
+
+    rng = np.random.default_rng(0)
+    draw = rng.integers(0, 390, size=(2, 33))
+    source = make(1)
+    source.compile(1e-3)
+    for _ in range(2):
+        source.train_step(draw[:, :-1], draw[:, 1:])
+    source._global_step, source._epoch = 3, 2
+    source.export_tf_checkpoint(tmp_path / 'logs')
+    assert (tmp_path / 'logs' / 'ckpt-1.index').exists() and (tmp_path / 'logs' / 'checkpoint').exists()
+
+    weights_only = make(2)
+    weights_only.load_from_checkpoint(tmp_path / 'logs')
+    for name, value in source.get_weights().items():
+        np.testing.assert_array_equal(weights_only.get_weights()[name], value)
+    a, _ = source(draw[:, :-1])
+    b, _ = weights_only(draw[:, :-1])
+    assert torch.equal(a, b)
+
+    resumed = make(3)
+    resumed._restore(Transformer.latest_checkpoint(tmp_path / 'logs'), with_optimizer=True)
+    assert (resumed._global_step, resumed._epoch, resumed._adam_t) == (3, 2, 2)
+    assert torch.equal(resumed._adam_m, source._adam_m) and torch.equal(resumed._adam_v, source._adam_v)
+    source.train_step(draw[:, :-1], draw[:, 1:])
+    resumed.compile(1e-3)
+    resumed.train_step(draw[:, :-1], draw[:, 1:])
+    assert torch.equal(resumed._params, source._params)
