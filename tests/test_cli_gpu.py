@@ -152,4 +152,5 @@ def test_tensorflow_checkpoint_restores_into_the_engine(tmp_path):
     source.train_step(draw[:, :-1], draw[:, 1:])
     resumed.compile(1e-3)
     resumed.train_step(draw[:, :-1], draw[:, 1:])
-    assert torch.equal(resumed._params, source._params)
+    # (weight gradients are summed with fp32 atomics: the order, hence the last bit, varies from run to run)
+    assert float((resumed._params - source._params).abs().max()) < 1e-6
