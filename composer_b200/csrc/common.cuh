@@ -300,22 +300,9 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 
 // Spin on a phase parity.  A bounded spin turns a protocol bug into a trap
-// (reported by the runtime as an error) instead of a hung GPU box.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t addr = smem_u32(bar);
-    uint32_t done = 0;
-    for (uint32_t spins = 0; !done; ++spins) {
-        // the suspend-time hint parks the thread instead of re-issuing the poll at full rate
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-            "selp.b32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(addr), "r"(parity), "r"(100000u)
-            : "memory");
-        if (spins > (1u << 16)) __trap();   // ~6 s at the 0.1 ms suspend hint
-    }
-}
+// (reported by the runtime as an error) instead of a hung GPU box.  (Loop: see mbar_wait_a below.)
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity);
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { mbar_wait_a(smem_u32(bar), parity); }
 
 // The same operations on 32-bit shared-space addresses.  A kernel that converts its barrier / buffer pointers once
 // (smem_u32) and keeps the addresses in registers avoids a generic -> shared conversion (4-6 uniform-datapath
@@ -329,18 +316,31 @@ __device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// The wait loop is part of every hand-off of the warp-specialised kernels, and their waiting warps share the
+// schedulers with the working ones: in the attention backward kernel a third of all executed instructions were wait
+// loops (ncu source view: SYNCS + BRA + uniform-datapath bookkeeping).  So the loop is kept minimal, in PTX: a poll
+// that succeeds costs two instructions, a failed one five (the hardware parks the thread inside try_wait for a
+// system-dependent time), and the spin counter that turns a protocol bug into a trap instead of a hung GPU is only
+// touched on the failure path.
 __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
-    uint32_t done = 0;
-    for (uint32_t spins = 0; !done; ++spins) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-            "selp.b32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity), "r"(100000u)
-            : "memory");
-        if (spins > (1u << 16)) __trap();
-    }
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .u32 spins;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra MBAR_DONE;\n\t"
+        "mov.u32 spins, 0;\n"
+        "MBAR_RETRY:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra MBAR_DONE;\n\t"
+        "add.u32 spins, spins, 1;\n\t"
+        "setp.gt.u32 p, spins, 0x1000000;\n\t"
+        "@p trap;\n\t"
+        "bra MBAR_RETRY;\n"
+        "MBAR_DONE:\n\t"
+        "}"
+        ::"r"(bar), "r"(parity)
+        : "memory");
 }
 __device__ __forceinline__ void tma_load_2d_a(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar, int x, int y) {
     asm volatile(

@@ -584,9 +584,9 @@ def check_generate_impls_agree(B=19, prompt_len=3, length=50, embedding=256, hea
         same_g = float((got[0] == ref[0]).mean())
         same_s = float((got[1][:, :8] == ref[1][:, :8]).mean())
         results.append({'name': 'cluster kernel (clusters %d) greedy tokens equal %.3f' % (key[1], same_g), 'rel': 1 - same_g,
-                        'tol': 0.1, 'nan': False, 'ok': same_g >= 0.9})
+                        'tol': 0.02, 'nan': False, 'ok': same_g >= 0.98})    # measured 1.000 in every variant (profiles/parity_margins_r2.txt)
         results.append({'name': 'cluster kernel (clusters %d) first 8 sampled tokens equal %.3f' % (key[1], same_s),
-                        'rel': 1 - same_s, 'tol': 0.15, 'nan': False, 'ok': same_s >= 0.85})
+                        'rel': 1 - same_s, 'tol': 0.12, 'nan': False, 'ok': same_s >= 0.88})    # measured 0.905 .. 1.000: a draw at a CDF edge may fall either side
         rows = (got[0] == ref[0]).all(axis=1)
         if rows.any():
             results.append(_stats('final logits vs per-step kernels (%d identical rows)' % int(rows.sum()),
@@ -594,8 +594,8 @@ def check_generate_impls_agree(B=19, prompt_len=3, length=50, embedding=256, hea
     a, b = outs[(0, 0)], outs[(0, 2)]
     # the two runs differ in cluster size, hence in the K split of the mlp c_proj: a near-tie may flip a token
     same = float(min((a[1][:, :8] == b[1][:, :8]).mean(), (a[0] == b[0]).mean()))
-    results.append({'name': 'tokens independent of the cluster layout %.3f' % same, 'rel': 1 - same, 'tol': 0.05,
-                    'nan': False, 'ok': same >= 0.95})
+    results.append({'name': 'tokens independent of the cluster layout %.3f' % same, 'rel': 1 - same, 'tol': 0.02,
+                    'nan': False, 'ok': same >= 0.98})
     return _finish(results)
 
 

@@ -1,0 +1,13 @@
+#!/bin/bash
+# Round-2 GPU session M: whole GPU suite, parity margins, launch lists, ncu --set full of every kernel of the step.
+set -u
+mkdir -p gpurun_out
+timeout -s KILL 1400 python -m pytest tests -q -m gpu --timeout 900 -p no:cacheprovider > gpurun_out/r2m_gpu_tests.log 2>&1
+tail -4 gpurun_out/r2m_gpu_tests.log | cut -c1-300
+timeout -s KILL 900 python tools/parity_margins.py > gpurun_out/parity_margins_r2.txt 2>&1
+tail -3 gpurun_out/parity_margins_r2.txt | cut -c1-200
+timeout -s KILL 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_train_r2.csv python bench.py --steps 2 --warmup 3 --no-generate --no-cpu-baseline --no-other-configs > gpurun_out/launches_train_r2.log 2>&1
+timeout -s KILL 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 1700 -c 580 --csv --log-file gpurun_out/launches_scaled_r2.csv python tools/bench_configs.py 4 > gpurun_out/launches_scaled_r2.log 2>&1
+timeout -s KILL 900 ncu --set full --clock-control none --import-source on -k regex:"gemm_sm100|attn_|layernorm|bias_grad" -f -o gpurun_out/prof_step_r2 python tools/microbench.py --once > gpurun_out/r2m_ncu_step.log 2>&1
+tail -2 gpurun_out/r2m_ncu_step.log
+ls -la gpurun_out/*.ncu-rep | tail -3

@@ -26,7 +26,16 @@ def stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+ONCE = '--once' in sys.argv      # one launch per kernel, no timing: for `ncu --set full` over every kernel of the step
+if ONCE:
+    sys.argv.remove('--once')
+
+
 def timeit(fn, iters=10, warmup=3):
+    if ONCE:
+        fn()
+        torch.cuda.synchronize()
+        return 1.0
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize()

@@ -3,9 +3,15 @@ Turns ncu output brought back in gpurun_out/ into the small text / JSON
 summaries committed under profiles/:
 
     python tools/ncu_summary.py launches <launches.csv> <out.txt>
-    python tools/ncu_summary.py kernels <report.ncu-rep> <out.json>
+    python tools/ncu_summary.py kernels <report.ncu-rep> <out.json> [capture label]
+
+`kernels` merges into an existing <out.json>: one entry per kernel name (template arguments included), the first
+launch of each, tagged with the capture label and the hash of the sources the library was built from
+(composer_b200/build.py source_hash), which is what bench.py checks before it quotes `traffic` from an entry.
 '''
-import collections, csv, json, re, subprocess, sys
+import collections, csv, json, os, re, subprocess, sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
 def launches(path, out):
@@ -30,7 +36,9 @@ def launches(path, out):
     print(open(out).read())
 
 
-def kernels(path, out):
+def kernels(path, out, capture=None):
+    from composer_b200 import build as native_build
+    source_hash = native_build.source_hash()
     raw = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr = rows[0]
@@ -47,7 +55,8 @@ def kernels(path, out):
     result = {}
     units = rows[1]
     for r in rows[2:]:
-        name = re.sub(r'\(.*', '', r[hdr.index('Kernel Name')]).replace('void ', '').replace('cb200::', '')
+        name = re.sub(r'\((int|bool|unsigned int)\)', '', r[hdr.index('Kernel Name')])
+        name = re.sub(r'\(.*', '', name).replace('void ', '').replace('cb200::', '')
         entry = {}
         for metric, key in want.items():
             if metric in hdr:
@@ -60,10 +69,17 @@ def kernels(path, out):
             entry['dram_bytes_per_launch'] = float(rd) * scale[ru] + float(wr) * scale[wu]
         except Exception:
             pass
+        name = re.sub(r'\((int|bool|unsigned int)\)', '', name)
+        entry['capture'] = capture or os.path.basename(path)
+        entry['source_hash'] = source_hash
         result.setdefault(name, entry)
+    if os.path.exists(out):
+        merged = json.load(open(out))
+        merged.update(result)
+        result = merged
     json.dump(result, open(out, 'w'), indent=1)
     print(json.dumps(result, indent=1))
 
 
 if __name__ == '__main__':
-    {'launches': launches, 'kernels': kernels}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {'launches': launches, 'kernels': kernels}[sys.argv[1]](*sys.argv[2:])
