@@ -115,12 +115,16 @@ def load():
             'libcomposer_b200.so is not built (%s). Run `python -m composer_b200.build`; there is no '
             'fallback path.' % LIBRARY_PATH)
 
-    # a binary built from other sources than the ones in the tree must not pass for the product
+    # a binary built from other sources than the ones in the tree must not pass for the product: when the hash of
+    # csrc/ + include/ differs from the one recorded at build time (or none was recorded), rebuild before loading
     from composer_b200 import build as native_build
     if not native_build.is_current() and os.environ.get('CB200_ALLOW_STALE_LIBRARY') != '1':
-        raise ImportError(
-            'libcomposer_b200.so does not match the sources in csrc/ and include/ (source hash differs from %s). '
-            'Run `python -m composer_b200.build`.' % native_build.STAMP)
+        try:
+            native_build.build()
+        except Exception as error:
+            raise ImportError(
+                'libcomposer_b200.so does not match the sources in csrc/ and include/ (source hash differs from %s) '
+                'and rebuilding it failed: %s' % (native_build.STAMP, error))
 
     library = ctypes.CDLL(LIBRARY_PATH, mode=ctypes.RTLD_GLOBAL)
     for name, (restype, argtypes) in _SIGNATURES.items():
