@@ -17,6 +17,8 @@
 //
 // Q, K, V, dO tiles are rows of d_h bf16 (32 / 64 / 128 bytes) loaded by TMA with the swizzle whose span is one
 // row, consumed K-major (S, dP) and MN-major (dV, dK, dQ right operands).  Reference semantics: attention_fwd_tc.cu.
+#include <cstdlib>
+
 #include "attention.h"
 #include "gemm.h"
 
@@ -62,7 +64,7 @@ __global__ void __launch_bounds__(TCB_THREADS, TcbCfg<D>::CPS)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                    const float* __restrict__ lse, const float* __restrict__ delta, float* __restrict__ dq_acc,
                    __nv_bfloat16* __restrict__ dqkv, int T, int H, float scale, float scale_log2, AttnDropKey drop,
-                   long long* __restrict__ trace) {
+                   long long* __restrict__ trace, int ablate) {
     using C = TcbCfg<D>;
     constexpr int RB = C::RB, TILE = C::TILE, PBYTES = C::PBYTES, NBUF_Q = C::NBUF_Q, NBUF_P = C::NBUF_P;
     constexpr uint32_t LT = umma_layout_for_row_bytes(RB); // swizzle mode of the Q/K/V/dO tiles
@@ -219,7 +221,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
                 tc_fence_after();
                 TR(21);
                 const uint32_t pb = (it % NBUF_P) * (PBYTES >> 4);
-                if (chain < 2) {
+                if (ablate & (1 << chain)) {
+                    // timing-only ablation (CB200_BWD_ABLATE: bit 0 dV, 1 dK, 2 dQ): the chain's MMAs are not issued
+                } else if (chain < 2) {
                     const uint32_t tb = b_lo + buf * (TILE >> 4);
                     const uint32_t acc = it > 0 ? 1u : 0u;
 #pragma unroll
@@ -445,6 +449,7 @@ static int launch_bwd_tc(const __nv_bfloat16* qkv, const __nv_bfloat16* dout, co
     rc = make_tmap_bf16_sw(&tm_do, dout, E, static_cast<uint64_t>(B) * T, E, D, TCB_TILE, RB);
     if (rc) return rc;
     auto kernel = attn_bwd_tc_kernel<D, DROP>;
+    static const int ablate = getenv("CB200_BWD_ABLATE") ? atoi(getenv("CB200_BWD_ABLATE")) : 0;   // diagnostic, results wrong
     static bool configured = false;
     if (!configured) {
         CB200_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -453,7 +458,7 @@ static int launch_bwd_tc(const __nv_bfloat16* qkv, const __nv_bfloat16* dout, co
     // longest walks first: x = 0 is the key block with every query tile below it
     dim3 grid((T + TCB_TILE - 1) / TCB_TILE, H, B);
     kernel<<<grid, TCB_THREADS, smem, s>>>(tm_qkv, tm_do, lse, delta, dq_acc, dqkv, T, H, scale,
-                                            scale * 1.4426950408889634f, key, g_attention_trace);
+                                            scale * 1.4426950408889634f, key, g_attention_trace, ablate);
     CB200_CUDA_OK(cudaGetLastError());
     note_launch(1);
     return 0;
