@@ -30,10 +30,9 @@ static long long* g_attention_trace = nullptr;   // device buffer of 12 x 512 wo
 void attention_set_trace(long long* buffer) { g_attention_trace = buffer; }
 long long* attention_get_trace() { return g_attention_trace; }
 
-constexpr int TCB_SM_WARPS = 8;                        // softmax warps: 4 row bands x 2 column slices of a 64-key half
-constexpr int TCB_THREADS = (TCB_SM_WARPS + 4) * 32;   // + one warpgroup of issuing warps: loads + S/dP, dV (+ TMEM alloc), dK, dQ
-constexpr int TCB_SM_THREADS = TCB_SM_WARPS * 32;
-constexpr int TCB_CPT = 32;                            // key columns per softmax thread and half
+// SW softmax warps per CTA: 8 = 4 row bands x 2 column slices of a 64-key half (32 keys per thread and hand-off),
+// 4 = one warp per row band (64 keys per thread and hand-off: half the hand-offs and per-tile bookkeeping per element,
+// half the warps).  Then one warpgroup of issuing warps: loads + S/dP, dV (+ TMEM alloc), dK, dQ.
 constexpr int TCB_TILE = 128;                          // query rows per tile = keys per CTA
 
 template <int D>
@@ -49,7 +48,8 @@ struct TcbCfg {
     // registers (CPS 2): launched with 80 per thread (768 threads per SM); the control warpgroup keeps 32 and what
     // it releases, 128 * 48, lets the 8 softmax warps grow to 104 (setmaxnreg.inc only takes what the CTA's own
     // warps released).  CPS 1: 168 per thread from the start, no redistribution.
-    static constexpr int SOFTMAX_REGS = 104, CONTROL_REGS = 32;
+    static constexpr int SOFTMAX_REGS = 104, CONTROL_REGS = 32;     // SW 8
+    static constexpr int SOFTMAX_REGS4 = 224;                       // SW 4: 256 threads x 128 at launch, 128 * 96 released
     static_assert(CPS * TMEM_COLS <= 512, "TMEM budget");
 };
 
@@ -59,13 +59,16 @@ struct TcbCfg {
 //                    shared memory (bar_p_full).
 //   softmax warps:   wait S/dP(n) -> tcgen05.ld -> release TMEM -> arithmetic -> smem -> bar_p_full;
 //                    dQ(it-1) is drained at the end of tile it, when its MMAs have long finished.
-template <int D, bool DROP>
-__global__ void __launch_bounds__(TCB_THREADS, TcbCfg<D>::CPS)
+template <int D, bool DROP, int SW = 8>
+__global__ void __launch_bounds__((SW + 4) * 32, TcbCfg<D>::CPS)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                    const float* __restrict__ lse, const float* __restrict__ delta, float* __restrict__ dq_acc,
                    __nv_bfloat16* __restrict__ dqkv, int T, int H, float scale, float scale_log2, AttnDropKey drop,
                    long long* __restrict__ trace, int ablate) {
     using C = TcbCfg<D>;
+    constexpr int TCB_SM_WARPS = SW, TCB_SM_THREADS = SW * 32;
+    constexpr int TCB_CPT = 256 / SW;                      // key columns per softmax thread and half (32 or 64)
+    static_assert(SW == 8 || (SW == 4 && C::CPS == 2), "softmax warps per CTA");
     constexpr int RB = C::RB, TILE = C::TILE, PBYTES = C::PBYTES, NBUF_Q = C::NBUF_Q, NBUF_P = C::NBUF_P;
     constexpr uint32_t LT = umma_layout_for_row_bytes(RB); // swizzle mode of the Q/K/V/dO tiles
     // dQ is double buffered (the drain of tile it - 1 runs under the MMAs of tile it)
@@ -242,7 +245,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       }
     } else {
         // ===================== softmax warps =====================
-        if (C::CPS == 2) setmaxnreg_inc<C::SOFTMAX_REGS>();
+        if (C::CPS == 2) setmaxnreg_inc<(SW == 4) ? C::SOFTMAX_REGS4 : C::SOFTMAX_REGS>();
         const int quad = warp & 3;                    // TMEM lane quadrant = 32-row band of the tile
         const int cq = warp >> 2;                     // which 32-column slice of a 64-key half
         const int r = quad * 32 + lane;               // row inside the tile
@@ -261,7 +264,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         const float dq_scale = scale * ks_scale;
 
         auto drain_dq = [&](int t) {                  // tile t's dQ: the two warps of a row band take half the columns each
-            constexpr int DC = D / 2;
+            constexpr int DC = D / (SW / 4);          // columns per thread: the SW / 4 warps of a row band share the row
             const int row_g = (kb + t) * TCB_TILE + r;
             const int buf = t & 1;
             mbar_wait_a(bar_dq_full + 8 * buf, (t >> 1) & 1);
@@ -312,8 +315,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
                 uint32_t sv_all[TCB_CPT], dv_all[TCB_CPT];
                 const bool skip_all = diagonal && col_base > quad * 32 + 31;   // every key of the slice is above the band
                 if (!skip_all) {
-                    tmem_ld32(t_lane + COL_S + cq * TCB_CPT, sv_all);
-                    tmem_ld32(t_lane + COL_DP + cq * TCB_CPT, dv_all);
+#pragma unroll
+                    for (int c32 = 0; c32 < TCB_CPT; c32 += 32) {
+                        tmem_ld32(t_lane + COL_S + cq * TCB_CPT + c32, *reinterpret_cast<uint32_t(*)[32]>(&sv_all[c32]));
+                        tmem_ld32(t_lane + COL_DP + cq * TCB_CPT + c32, *reinterpret_cast<uint32_t(*)[32]>(&dv_all[c32]));
+                    }
                     tmem_ld_wait();
                 }
                 tc_fence_before();
@@ -435,7 +441,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     }
 }
 
-template <int D, bool DROP>
+template <int D, bool DROP, int SW = 8>
 static int launch_bwd_tc(const __nv_bfloat16* qkv, const __nv_bfloat16* dout, const float* lse, const float* delta,
                          float* dq_acc, __nv_bfloat16* dqkv, int B, int T, int H, float scale, const AttnDropKey& key,
                          cudaStream_t s) {
@@ -448,7 +454,7 @@ static int launch_bwd_tc(const __nv_bfloat16* qkv, const __nv_bfloat16* dout, co
     if (rc) return rc;
     rc = make_tmap_bf16_sw(&tm_do, dout, E, static_cast<uint64_t>(B) * T, E, D, TCB_TILE, RB);
     if (rc) return rc;
-    auto kernel = attn_bwd_tc_kernel<D, DROP>;
+    auto kernel = attn_bwd_tc_kernel<D, DROP, SW>;
     static const int ablate = getenv("CB200_BWD_ABLATE") ? atoi(getenv("CB200_BWD_ABLATE")) : 0;   // diagnostic, results wrong
     static bool configured = false;
     if (!configured) {
@@ -457,7 +463,7 @@ static int launch_bwd_tc(const __nv_bfloat16* qkv, const __nv_bfloat16* dout, co
     }
     // longest walks first: x = 0 is the key block with every query tile below it
     dim3 grid((T + TCB_TILE - 1) / TCB_TILE, H, B);
-    kernel<<<grid, TCB_THREADS, smem, s>>>(tm_qkv, tm_do, lse, delta, dq_acc, dqkv, T, H, scale,
+    kernel<<<grid, (SW + 4) * 32, smem, s>>>(tm_qkv, tm_do, lse, delta, dq_acc, dqkv, T, H, scale,
                                             scale * 1.4426950408889634f, key, g_attention_trace, ablate);
     CB200_CUDA_OK(cudaGetLastError());
     note_launch(1);
@@ -469,6 +475,10 @@ int attention_bwd_tc_main(const __nv_bfloat16* qkv, const __nv_bfloat16* dout, c
                           float* dq_acc, __nv_bfloat16* dqkv, int B, int T, int H, int D, float scale,
                           const AttnDropKey& key, cudaStream_t s) {
     const bool dropping = key.thr_bits != 0;
+    static const int sw4 = getenv("CB200_BWD_SW4") ? atoi(getenv("CB200_BWD_SW4")) : 0;   // A/B: 4 softmax warps per CTA (d_h 16)
+    if (D == 16 && sw4)
+        return dropping ? launch_bwd_tc<16, true, 4>(qkv, dout, lse, delta, dq_acc, dqkv, B, T, H, scale, key, s)
+                        : launch_bwd_tc<16, false, 4>(qkv, dout, lse, delta, dq_acc, dqkv, B, T, H, scale, key, s);
     switch (D) {
         case 16: return dropping ? launch_bwd_tc<16, true>(qkv, dout, lse, delta, dq_acc, dqkv, B, T, H, scale, key, s)
                                  : launch_bwd_tc<16, false>(qkv, dout, lse, delta, dq_acc, dqkv, B, T, H, scale, key, s);
