@@ -1,5 +1,7 @@
 #!/bin/bash
-# Round-2 GPU session M: whole GPU suite, parity margins, launch lists, ncu --set full of every kernel of the step.
+# One GPU session that regenerates the evidence under profiles/ (run as: gpurun --timeout 3000 -- 'bash tools/gpu_session.sh'):
+# whole GPU suite, parity margins, launch lists of the training step and the scaled configuration, ncu --set full of
+# every kernel of the step and of the bench.py generation, the bench line.  Summaries: tools/ncu_summary.py.
 set -u
 mkdir -p gpurun_out
 timeout -s KILL 1400 python -m pytest tests -q -m gpu --timeout 900 -p no:cacheprovider > gpurun_out/r2m_gpu_tests.log 2>&1
@@ -10,4 +12,8 @@ timeout -s KILL 600 ncu --metrics gpu__time_duration.sum --clock-control none -c
 timeout -s KILL 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 1700 -c 580 --csv --log-file gpurun_out/launches_scaled_r2.csv python tools/bench_configs.py 4 > gpurun_out/launches_scaled_r2.log 2>&1
 timeout -s KILL 900 ncu --set full --clock-control none --import-source on -k regex:"gemm_sm100|attn_|layernorm|bias_grad" -f -o gpurun_out/prof_step_r2 python tools/microbench.py --once > gpurun_out/r2m_ncu_step.log 2>&1
 tail -2 gpurun_out/r2m_ncu_step.log
+timeout -s KILL 900 ncu --set full --clock-control none -k regex:decode_mega_kernel -f -o gpurun_out/prof_mega_r2 python tools/profile_decode_mega.py 256 1 1024 > gpurun_out/r2m_ncu_mega.log 2>&1
+tail -2 gpurun_out/r2m_ncu_mega.log
 ls -la gpurun_out/*.ncu-rep | tail -3
+timeout -s KILL 600 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_r2_n1.json 2> gpurun_out/bench_r2_n1.err
+tail -c 400 gpurun_out/bench_r2_n1.json
