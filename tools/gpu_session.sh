@@ -12,8 +12,13 @@ timeout -s KILL 600 ncu --metrics gpu__time_duration.sum --clock-control none -c
 timeout -s KILL 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 1700 -c 580 --csv --log-file gpurun_out/launches_scaled_r2.csv python tools/bench_configs.py 4 > gpurun_out/launches_scaled_r2.log 2>&1
 timeout -s KILL 900 ncu --set full --clock-control none --import-source on -k regex:"gemm_sm100|attn_|layernorm|bias_grad" -f -o gpurun_out/prof_step_r2 python tools/microbench.py --once > gpurun_out/r2m_ncu_step.log 2>&1
 tail -2 gpurun_out/r2m_ncu_step.log
+# (gpurun brings back at most 64 MiB: the summary is made here and the 60 MB report stays on the box)
+cp profiles/ncu_summary.json gpurun_out/ncu_summary_r2.json
+python tools/ncu_summary.py kernels gpurun_out/prof_step_r2.ncu-rep gpurun_out/ncu_summary_r2.json "prof_step_r2: tools/microbench.py --once at B 32 T 2048 H 16 d_h 16 (one launch per kernel, ncu --set full --clock-control none)" > /dev/null
+rm -f gpurun_out/prof_step_r2.ncu-rep
 timeout -s KILL 900 ncu --set full --clock-control none -k regex:decode_mega_kernel -f -o gpurun_out/prof_mega_r2 python tools/profile_decode_mega.py 256 1 1024 > gpurun_out/r2m_ncu_mega.log 2>&1
 tail -2 gpurun_out/r2m_ncu_mega.log
-ls -la gpurun_out/*.ncu-rep | tail -3
+python tools/ncu_summary.py kernels gpurun_out/prof_mega_r2.ncu-rep gpurun_out/ncu_summary_r2.json "prof_mega_r2: the bench.py generation exactly (256 sequences, prompt 1, 1,024 events), ncu --set full" > /dev/null
+cp gpurun_out/ncu_summary_r2.json profiles/ncu_summary.json
 timeout -s KILL 600 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_r2_n1.json 2> gpurun_out/bench_r2_n1.err
 tail -c 400 gpurun_out/bench_r2_n1.json
