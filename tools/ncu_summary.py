@@ -62,7 +62,7 @@ def kernels(path, out, capture=None):
             if metric in hdr:
                 i = hdr.index(metric)
                 entry[key] = '%s %s' % (r[i], units[i])
-        scale = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+        scale = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'Tbyte': 1e12}
         try:
             rd, ru = entry['dram_read'].split()
             wr, wu = entry['dram_write'].split()
