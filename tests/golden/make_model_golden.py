@@ -101,11 +101,26 @@ def main():
         out[name + '/step_loss'] = np.array([v for tag, v, _ in shim.SCALARS if tag == 'loss'])
         out[name + '/step_accuracy'] = np.array([v for tag, v, _ in shim.SCALARS if tag == 'accuracy'])
         assert len(out[name + '/step_loss']) == case['train_steps']
+        reduced = case.get('reduced', False)
         for variable_name, grad in first_grads.items():
-            if grad is not None:
+            if grad is None:
+                continue
+            if reduced and grad.size > 4096:         # large tensors: their L2 norm and 64 strided samples
+                out[name + '/grad_norm/' + variable_name] = np.asarray(np.linalg.norm(grad))
+                out[name + '/grad_sample/' + variable_name] = grad.reshape(-1)[::max(1, grad.size // 64)][:64].copy()
+            else:
                 out[name + '/grad/' + variable_name] = grad
         for variable_name, variable in variables.items():
-            out[name + '/trained/' + variable_name] = variable.numpy().copy()
+            value = variable.numpy().copy()
+            if reduced and value.size > 4096:
+                delta = value - np.asarray(weights[variable_name], dtype=np.float64)
+                out[name + '/update_norm/' + variable_name] = np.asarray(np.linalg.norm(delta))
+            else:
+                out[name + '/trained/' + variable_name] = value
+        if reduced:
+            out[name + '/logits'] = out[name + '/logits'].astype(np.float32)
+            out[name + '/decode_logits'] = out[name + '/decode_logits'].astype(np.float32)
+            del out[name + '/presents']
         print(name, 'loss', out[name + '/step_loss'], 'decode', out[name + '/decode_ids'][0, :8])
 
     path = os.path.join(HERE, 'model_golden.npz')

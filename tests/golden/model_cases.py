@@ -17,6 +17,10 @@ CASES = {
     'default_heads': dict(vocab_size=390, embedding_size=32, window_size=24, decoder_layers_count=2,
                           attention_head_count=16, scale=True, use_layer_normalization=True, batch=2, length=20,
                           prompt=4, train_steps=2),
+    # a shape the CUDA engine accepts (embedding a multiple of 256, d_h 16): the GPU tests compare the engine with THIS
+    # case directly, not only with the oracle.  Stored reduced (fp32 logits, norms of the large gradients / updates).
+    'engine': dict(vocab_size=390, embedding_size=256, window_size=64, decoder_layers_count=2, attention_head_count=16,
+                   scale=True, use_layer_normalization=True, batch=2, length=48, prompt=5, train_steps=3, reduced=True),
 }
 
 

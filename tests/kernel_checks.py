@@ -889,3 +889,98 @@ GROUPS['past'] = [
     check_prefill_equals_teacher_forcing,
     lambda: check_prefill_equals_teacher_forcing(B=33, prompt_len=2, length=20),
 ]
+
+
+def check_engine_against_reference_golden():
+    '''
+    The CUDA engine against outputs of the REFERENCE's own ``transformer.py`` (tests/golden/model_golden.npz, case
+    'engine': produced by the unmodified reference model under tests/golden/tf_shim.py), without the oracle in
+    between: ``Transformer.call`` logits, the losses / accuracies its own ``train()`` loop logged over three Adam
+    steps, the norms of its first-step gradients and of its three-step weight updates, greedy ``past=`` decoding.
+    '''
+    import os
+    import sys
+    import numpy as np
+    from oracle import transformer_oracle as oracle      # initialiser recipe of the case's weights only
+    golden_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+    if golden_dir not in sys.path:
+        sys.path.insert(0, golden_dir)
+    import model_cases
+    from composer_b200.models.transformer import Transformer
+
+    name = 'engine'
+    index = list(model_cases.CASES).index(name)
+    case = model_cases.CASES[name]
+    cfg = model_cases.case_config(oracle, case)
+    weights = model_cases.case_weights(oracle, cfg, 10 + index)
+    batches = model_cases.case_batches(case, 10 + index)
+    data = np.load(os.path.join(golden_dir, 'model_golden.npz'))
+    golden = {k[len(name) + 1:]: data[k] for k in data.files if k.startswith(name + '/')}
+
+    model = Transformer(case['vocab_size'], case['embedding_size'], case['window_size'], case['decoder_layers_count'],
+                        case['attention_head_count'], False, 0.0, 0.02, 0.0, 0.0, 1e-5, case['scale'],
+                        case['use_layer_normalization'])
+    model.set_weights(weights)
+    results = []
+    x0 = batches[0][0]
+    B, T = x0.shape
+    logits, presents = model(x0)
+    results.append(_stats('logits vs the reference model', logits.double().cpu().reshape(B * T, -1),
+                          torch.from_numpy(golden['logits']).double().reshape(B * T, -1), 2e-2))
+
+    # greedy decoding through past= : token-identical wherever the reference's top-2 margin exceeds the tolerance
+    steps = golden['decode_ids'].shape[1]
+    out = model.generate(x0[:, :case['prompt']], steps, temperature=0.0).cpu().numpy()
+    ref_logits, ref_ids = golden['decode_logits'], golden['decode_ids']
+    checked = mismatches = 0
+    for b in range(B):
+        for step in range(steps):
+            if step > 0 and out[b, step - 1] != ref_ids[b, step - 1]:
+                break                                    # contexts differ from here on
+            top2 = np.sort(ref_logits[b, step])[-2:]
+            if top2[1] - top2[0] > 2e-2 * np.abs(ref_logits[b, step]).max():
+                checked += 1
+                mismatches += int(out[b, step] != ref_ids[b, step])
+    results.append({'name': 'greedy decode vs the reference model (decisive steps %d)' % checked, 'rel': mismatches, 'tol': 0,
+                    'nan': False, 'ok': mismatches == 0 and checked >= steps // 4})
+
+    # the reference's own training loop: losses and accuracies of three Adam steps, first-step gradients, updates
+    model.compile(1e-3)
+    for step, (x, y) in enumerate(batches):
+        loss_sum, correct = model.forward_loss(x, y, training=True, step=step)
+        loss, accuracy = float(loss_sum) / x.size, float(correct) / x.size
+        results.append({'name': 'train step %d loss %.5f (reference %.5f)' % (step, loss, golden['step_loss'][step]),
+                        'rel': abs(loss - golden['step_loss'][step]), 'tol': 5e-4 * (step + 1), 'nan': loss != loss,
+                        'ok': abs(loss - golden['step_loss'][step]) <= 5e-4 * (step + 1)})   # (bf16 trajectories drift apart)
+        results.append({'name': 'train step %d accuracy' % step, 'rel': abs(accuracy - golden['step_accuracy'][step]),
+                        'tol': 2.0 / x.size, 'nan': False, 'ok': abs(accuracy - golden['step_accuracy'][step]) <= 2.0 / x.size})
+        world = model.backward()
+        if step == 0:
+            grads = model.get_gradients()
+            worst = 0.0
+            for variable, value in grads.items():
+                if 'grad_norm/' + variable in golden:
+                    ref = float(golden['grad_norm/' + variable])
+                    worst = max(worst, abs(float(np.linalg.norm(value)) - ref) / max(ref, 1e-30))
+                elif 'grad/' + variable in golden:
+                    ref = golden['grad/' + variable]
+                    worst = max(worst, float(np.linalg.norm(value.reshape(ref.shape) - ref) / max(np.linalg.norm(ref), 1e-30)))
+            results.append({'name': 'first-step gradients vs the reference (worst tensor, relative L2 / norm)', 'rel': worst,
+                            'tol': 5e-2, 'nan': worst != worst, 'ok': worst <= 5e-2})
+        model.apply_gradients(1e-3, world)
+    trained = model.get_weights()
+    worst = 0.0
+    for variable, value in trained.items():
+        delta = np.linalg.norm(value.astype(np.float64) - weights[variable].astype(np.float64))
+        if 'update_norm/' + variable in golden:
+            ref = float(golden['update_norm/' + variable])
+            worst = max(worst, abs(delta - ref) / max(ref, 1e-30))
+        elif 'trained/' + variable in golden:
+            ref = np.linalg.norm(golden['trained/' + variable].astype(np.float64) - weights[variable].astype(np.float64))
+            worst = max(worst, abs(delta - ref) / max(ref, 1e-30))
+    results.append({'name': 'size of the three-step Adam update per tensor vs the reference (worst)', 'rel': worst, 'tol': 5e-2,
+                    'nan': worst != worst, 'ok': worst <= 5e-2})
+    return _finish(results)
+
+
+GROUPS['golden'] = [check_engine_against_reference_golden]

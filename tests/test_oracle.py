@@ -174,7 +174,7 @@ def _golden_case(name):
 import pytest  # noqa: E402
 
 
-@pytest.mark.parametrize('name', ['small', 'no_layernorm_no_scale', 'default_heads'])
+@pytest.mark.parametrize('name', ['small', 'no_layernorm_no_scale', 'default_heads', 'engine'])
 def test_oracle_matches_reference_transformer(name):
     '''
     ``tests/golden/model_golden.npz`` holds what the reference's own ``Transformer`` (composer/models/transformer.py,
@@ -187,14 +187,16 @@ def test_oracle_matches_reference_transformer(name):
     x0, y0 = batches[0]
     params = oracle.to_torch(weights, torch.float64)
     logits, presents = oracle.transformer_call(params, x0, cfg)
-    np.testing.assert_allclose(logits.numpy(), golden['logits'], rtol=0, atol=1e-11)
+    reduced = case.get('reduced', False)      # the 'engine' case keeps fp32 logits and norms of the large tensors
+    np.testing.assert_allclose(logits.numpy(), golden['logits'], rtol=0, atol=2e-6 if reduced else 1e-11)
     ours = np.stack([np.stack([p[0].numpy(), p[1].numpy()]) if isinstance(p, (tuple, list)) else p.numpy()
                      for p in presents])
-    np.testing.assert_allclose(ours, golden['presents'], rtol=0, atol=1e-6)
+    if 'presents' in golden:
+        np.testing.assert_allclose(ours, golden['presents'], rtol=0, atol=1e-6)
 
     steps = golden['decode_ids'].shape[1]
     ids, step_logits = oracle.generate(weights, x0[:, :case['prompt']], steps, cfg, greedy=True)
-    np.testing.assert_allclose(step_logits, golden['decode_logits'], rtol=0, atol=1e-10)
+    np.testing.assert_allclose(step_logits, golden['decode_logits'], rtol=0, atol=2e-6 if reduced else 1e-10)
     assert (ids == golden['decode_ids']).all()
 
     # the reference's train loop: per-step loss and accuracy, first-step gradients, variables after the last step
@@ -209,10 +211,18 @@ def test_oracle_matches_reference_transformer(name):
                 key = 'grad/' + variable
                 if key in golden:
                     np.testing.assert_allclose(grads[variable], golden[key], rtol=2e-6, atol=1e-9, err_msg=variable)
+                elif 'grad_norm/' + variable in golden:
+                    g = np.asarray(grads[variable])
+                    np.testing.assert_allclose(np.linalg.norm(g), golden['grad_norm/' + variable], rtol=1e-9)
+                    np.testing.assert_allclose(g.reshape(-1)[::max(1, g.size // 64)][:64], golden['grad_sample/' + variable],
+                                               rtol=2e-6, atol=1e-9, err_msg=variable)
                 else:   # never built by the reference (ln_1 / ln_2 without LayerNorm): no gradient here either
                     assert '/ln_' in variable and not np.any(grads[variable])
         current = adam.apply(current, grads)
     for variable in weights:
+        if 'update_norm/' + variable in golden:
+            np.testing.assert_allclose(np.linalg.norm(current[variable] - weights[variable]),
+                                       golden['update_norm/' + variable], rtol=1e-6, err_msg=variable)
         if 'trained/' + variable in golden:
             np.testing.assert_allclose(current[variable], golden['trained/' + variable], rtol=0, atol=2e-7,
                                        err_msg=variable)
