@@ -71,7 +71,9 @@ struct TcfCursor {
 };
 
 // ABL: timing-only ablations (results wrong): 1 no max pass, 2 no MUFU (multiply instead), 4 no P store, 8 no O~ load
-template <int D, bool DROP, bool PSMEM, int KT_, int CPS_, int ABL = 0, int RS = 1>
+// TRACED: the event timeline is compiled in (a separate instantiation: even a never-taken trace branch per event costs
+// the default kernel 3-7 %).
+template <int D, bool DROP, bool PSMEM, int KT_, int CPS_, int ABL = 0, int RS = 1, bool TRACED = false>
 __global__ void __launch_bounds__((4 * RS + 4) * 32, CPS_)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                    __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int T, int H, int BH, int nq,
@@ -109,10 +111,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
 
     // Diagnostic timeline (cb200_set_attention_trace): lane 0 of every warp of CTA 0 appends (event << 40 | clock) words
-    long long* tr = (trace != nullptr && blockIdx.x == 0 && lane == 0) ? trace + warp * 512 : nullptr;
+    long long* tr = (TRACED && trace != nullptr && blockIdx.x == 0 && lane == 0) ? trace + warp * 512 : nullptr;
     int tr_n = 0;
     auto TR = [&](int ev) {
-        if (tr != nullptr && tr_n < 511) tr[++tr_n] = (static_cast<long long>(ev) << 40) | (clock64() & 0xFFFFFFFFFFll);
+        if (TRACED && tr != nullptr && tr_n < 511) tr[++tr_n] = (static_cast<long long>(ev) << 40) | (clock64() & 0xFFFFFFFFFFll);
     };
     TR(1);
 
@@ -430,7 +432,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         }
     }
 
-    if (tr != nullptr) tr[0] = tr_n;
+    if (TRACED && tr != nullptr) tr[0] = tr_n;
     tc_fence_before();
     __syncthreads();
     if (warp == SW + 2) {
@@ -439,7 +441,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     }
 }
 
-template <int D, bool DROP, bool PSMEM, int KT, int CPS, int ABL = 0, int RS = 1>
+template <int D, bool DROP, bool PSMEM, int KT, int CPS, int ABL = 0, int RS = 1, bool TRACED = false>
 static int launch_fwd_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse, int B, int T, int H, float scale,
                          const AttnDropKey& key, cudaStream_t s) {
     using C = TcfCfg<D, PSMEM, KT, CPS, RS>;
@@ -450,7 +452,7 @@ static int launch_fwd_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* ls
     if (rc) return rc;
     rc = make_tmap_bf16_sw(&tm_kv, qkv, 3 * E, static_cast<uint64_t>(B) * T, 3 * E, D, C::KT, C::RB);
     if (rc) return rc;
-    auto kernel = attn_fwd_tc_kernel<D, DROP, PSMEM, KT, CPS, ABL, RS>;
+    auto kernel = attn_fwd_tc_kernel<D, DROP, PSMEM, KT, CPS, ABL, RS, TRACED>;
     static bool configured = false;
     if (!configured) {
         CB200_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -490,6 +492,9 @@ int attention_fwd_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse, i
         case 16:
             if (variant == 3) return launch_fwd_tc_d<16, 64, 3>(qkv, out, lse, B, T, H, scale, key, false, s);
             if (variant == 4) return launch_fwd_tc_d<16, 64, 4>(qkv, out, lse, B, T, H, scale, key, false, s);
+            if (variant == 0 && attention_get_trace() != nullptr)      // diagnostic: the default shape with the event timeline
+                return key.thr_bits != 0 ? launch_fwd_tc<16, true, false, 128, 2, 0, 1, true>(qkv, out, lse, B, T, H, scale, key, s)
+                                         : launch_fwd_tc<16, false, false, 128, 2, 0, 1, true>(qkv, out, lse, B, T, H, scale, key, s);
             if (variant == 7)       // two threads per row: 8 softmax warps per CTA
                 return key.thr_bits != 0 ? launch_fwd_tc<16, true, false, 128, 2, 0, 2>(qkv, out, lse, B, T, H, scale, key, s)
                                          : launch_fwd_tc<16, false, false, 128, 2, 0, 2>(qkv, out, lse, B, T, H, scale, key, s);

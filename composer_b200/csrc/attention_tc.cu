@@ -59,7 +59,8 @@ struct TcbCfg {
 //                    shared memory (bar_p_full).
 //   softmax warps:   wait S/dP(n) -> tcgen05.ld -> release TMEM -> arithmetic -> smem -> bar_p_full;
 //                    dQ(it-1) is drained at the end of tile it, when its MMAs have long finished.
-template <int D, bool DROP, int SW = 8>
+// TRACED: the event timeline is compiled in (a separate instantiation, see attention_fwd_tc.cu).
+template <int D, bool DROP, int SW = 8, bool TRACED = false>
 __global__ void __launch_bounds__((SW + 4) * 32, TcbCfg<D>::CPS)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                    const float* __restrict__ lse, const float* __restrict__ delta, float* __restrict__ dq_acc,
@@ -104,10 +105,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     // Diagnostic timeline (cb200_set_attention_trace): lane 0 of every warp of CTA (0, 0, 0) appends (event << 40 | clock)
     // words to its own 512-entry region; nullptr in normal runs (one predictable branch per event).
-    long long* tr = (trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0) ? trace + warp * 512 : nullptr;
+    long long* tr = (TRACED && trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0) ? trace + warp * 512 : nullptr;
     int tr_n = 0;
     auto TR = [&](int ev) {
-        if (tr != nullptr && tr_n < 511) tr[++tr_n] = (static_cast<long long>(ev) << 40) | (clock64() & 0xFFFFFFFFFFll);
+        if (TRACED && tr != nullptr && tr_n < 511) tr[++tr_n] = (static_cast<long long>(ev) << 40) | (clock64() & 0xFFFFFFFFFFll);
     };
     TR(1);
 
@@ -432,7 +433,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     }
 
     TR(99);
-    if (tr != nullptr) tr[0] = tr_n;
+    if (TRACED && tr != nullptr) tr[0] = tr_n;
     tc_fence_before();
     __syncthreads();
     if (warp == TCB_SM_WARPS + 1) {
@@ -441,7 +442,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     }
 }
 
-template <int D, bool DROP, int SW = 8>
+template <int D, bool DROP, int SW = 8, bool TRACED = false>
 static int launch_bwd_tc(const __nv_bfloat16* qkv, const __nv_bfloat16* dout, const float* lse, const float* delta,
                          float* dq_acc, __nv_bfloat16* dqkv, int B, int T, int H, float scale, const AttnDropKey& key,
                          cudaStream_t s) {
@@ -454,7 +455,7 @@ static int launch_bwd_tc(const __nv_bfloat16* qkv, const __nv_bfloat16* dout, co
     if (rc) return rc;
     rc = make_tmap_bf16_sw(&tm_do, dout, E, static_cast<uint64_t>(B) * T, E, D, TCB_TILE, RB);
     if (rc) return rc;
-    auto kernel = attn_bwd_tc_kernel<D, DROP, SW>;
+    auto kernel = attn_bwd_tc_kernel<D, DROP, SW, TRACED>;
     static const int ablate = getenv("CB200_BWD_ABLATE") ? atoi(getenv("CB200_BWD_ABLATE")) : 0;   // diagnostic, results wrong
     static bool configured = false;
     if (!configured) {
@@ -476,6 +477,9 @@ int attention_bwd_tc_main(const __nv_bfloat16* qkv, const __nv_bfloat16* dout, c
                           const AttnDropKey& key, cudaStream_t s) {
     const bool dropping = key.thr_bits != 0;
     static const int sw4 = getenv("CB200_BWD_SW4") ? atoi(getenv("CB200_BWD_SW4")) : 0;   // A/B: 4 softmax warps per CTA (d_h 16)
+    if (D == 16 && g_attention_trace != nullptr)          // diagnostic: the default shape with the event timeline
+        return dropping ? launch_bwd_tc<16, true, 8, true>(qkv, dout, lse, delta, dq_acc, dqkv, B, T, H, scale, key, s)
+                        : launch_bwd_tc<16, false, 8, true>(qkv, dout, lse, delta, dq_acc, dqkv, B, T, H, scale, key, s);
     if (D == 16 && sw4)
         return dropping ? launch_bwd_tc<16, true, 4>(qkv, dout, lse, delta, dq_acc, dqkv, B, T, H, scale, key, s)
                         : launch_bwd_tc<16, false, 4>(qkv, dout, lse, delta, dq_acc, dqkv, B, T, H, scale, key, s);
