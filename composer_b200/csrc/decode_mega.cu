@@ -273,8 +273,9 @@ __device__ __forceinline__ void kv_prefetch_l2(const JobPlan& p, int layer, int 
 
 // Waits for the warp's next job and returns its stage.  (The stage index and the mbarrier phase are tracked
 // incrementally: an integer division by the runtime stage count costs more than the MMAs of a slot.)
+template <bool PROF>
 __device__ __forceinline__ uint8_t* ring_acquire(const JobRing& r) {
-    if (r.wait_prof != nullptr) {                  // diagnostic: cycles this thread waits for its jobs
+    if (PROF && r.wait_prof != nullptr) {          // diagnostic: cycles this thread waits for its jobs
         const long long t0 = clock64();
         mbar_wait(&r.bars[r.stage], r.phase);
         *r.wait_prof += clock64() - t0;
@@ -318,7 +319,7 @@ __device__ __forceinline__ void slot_mma(float (&acc)[4], const uint8_t* slot, c
 // (col, col + 1) = lo and (col + 8, col + 9) = hi, col relative to this CTA's slice.  All 16 warps must call this
 // (it may contain a __syncthreads).  There is one call site (the phase loop of the kernel): the kernel's code has
 // to stay within the instruction cache, a phase is only a few hundred instructions long.
-template <int D, typename Epi>
+template <int D, bool PROF, typename Epi>
 __device__ __forceinline__ void run_phase(const Phase& ph, const uint8_t* X, int pitch, JobRing& ring, const JobPlan& plan,
                                           float* red, int warp, int lane, Epi epi) {
     const int g = lane >> 2, tig = lane & 3;
@@ -342,7 +343,7 @@ __device__ __forceinline__ void run_phase(const Phase& ph, const uint8_t* X, int
         nt = (ph.ksplit == 1) ? u : ph.nt0;          // (no division here: it would cost as much as the MMAs of a slot)
         const int ks = (ph.ksplit == 1) ? 0 : ph.ks0;
         for (int j = 0; j < ph.sub; ++j) {
-            const uint8_t* slot = ring_acquire(ring);
+            const uint8_t* slot = ring_acquire<PROF>(ring);
             if (j == 0) {
                 bias_lo = *reinterpret_cast<const float*>(slot + MG_SLOT_W + g * 4);
                 bias_hi = *reinterpret_cast<const float*>(slot + MG_SLOT_W + (g + 8) * 4);
@@ -518,7 +519,9 @@ __device__ __forceinline__ int sample_row_smem(float* z, int V, float inv_temper
     return chosen;
 }
 
-template <int D, int CL>
+// PROF: the phase profile (cb200_set_decode_profile) is compiled in; a separate instantiation, because even never-taken
+// diagnostic branches on the job path cost the default kernel issue slots.
+template <int D, int CL, bool PROF = false>
 __global__ void __launch_bounds__(MG_THREADS, 1)
 decode_mega_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ MegaSmem sm) {
     constexpr int CH = D / 8;                     // 16-byte chunks per head row
@@ -617,20 +620,20 @@ decode_mega_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ M
     jr.stage = 0; jr.phase = 0; jr.nst = NST + (warp < sm.nst_extra ? 1 : 0);
     jr.cur = JobCursor{a.step0, 0, 0, 0, 0, nullptr};
     jr.wait_prof = nullptr;
-    const bool wait_profiling = a.prof != nullptr && blockIdx.x == 0 && tid == 0;
-#define MG_WAIT_SLOT(k) if (wait_profiling) jr.wait_prof = prof_acc + 16 + (k);
+    const bool wait_profiling = PROF && a.prof != nullptr && blockIdx.x == 0 && tid == 0;
+#define MG_WAIT_SLOT(k) if (PROF && wait_profiling) jr.wait_prof = prof_acc + 16 + (k);
     for (int st = 0; st < jr.nst; ++st) job_issue<D>(plan, jr.cur, jr.base + st * MG_STAGE, &jr.bars[st], lane);
     cluster_sync_all();                            // every CTA of the cluster is resident before any DSMEM access
 
     // optional phase profile (cluster 0, CTA 0, thread 0): cycles per phase, accumulated in shared memory (a global
     // read-modify-write per sample would cost more than most of the phases it measures) and written out at the end
-    const bool profiling = a.prof != nullptr && blockIdx.x == 0 && tid == 0;
+    const bool profiling = PROF && a.prof != nullptr && blockIdx.x == 0 && tid == 0;
     long long* prof_acc = reinterpret_cast<long long*>(smem + sm.prof);
     if (profiling)
         for (int i = 0; i < 24; ++i) prof_acc[i] = 0;
     long long prof_t = profiling ? clock64() : 0;
 #define MG_PROF(slot)                                                        \
-    if (profiling) {                                                         \
+    if (PROF && profiling) {                                                 \
         const long long now_ = clock64();                                    \
         prof_acc[slot] += now_ - prof_t;                                     \
         prof_t = now_;                                                       \
@@ -695,7 +698,7 @@ decode_mega_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ M
                                       jr.nst + kind * a.kv_prefetch / 3, lane);      // (the first jobs of the phase are fetched by the ring itself)
             }
             MG_WAIT_SLOT(kind == 0 ? 0 : kind + 1)
-            run_phase<D>(ph, src, src_pitch, jr, plan, red, warp, lane, [&](int col, int seq, float2 lo, float2 hi) {
+            run_phase<D, PROF>(ph, src, src_pitch, jr, plan, red, warp, lane, [&](int col, int seq, float2 lo, float2 hi) {
                 if (kind == 0) {                   // q, k, v of this CTA's heads (bf16, local)
                     uint8_t* q = qkvs + (seq * 3 * HS + col) * 2;
                     *reinterpret_cast<uint32_t*>(q) = pack_bf16(lo.x, lo.y);
@@ -788,7 +791,7 @@ decode_mega_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ M
                         }
                         __syncwarp();
                         for (int c = plan.split; c < nchunks; c += 1 << ss) {
-                            uint8_t* st = ring_acquire(jr);
+                            uint8_t* st = ring_acquire<PROF>(jr);
                             const int ntok = min(CT, pos - c * CT);
                             const uint32_t st_a = smem_u32(st);
                             // S^T = K q: s[j][0] = token 16 j + g, s[j][2] = token 16 j + 8 + g (lanes with tig == 0)
@@ -1044,9 +1047,9 @@ static MegaSmem mega_smem_fit(int E, int V, int D, int CL, int L) {
     return sm;
 }
 
-template <int D, int CL>
+template <int D, int CL, bool PROF = false>
 static int mega_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, const MegaSmem& sm) {
-    auto kernel = decode_mega_kernel<D, CL>;
+    auto kernel = decode_mega_kernel<D, CL, PROF>;
     static int configured_smem = 0;
     if (configured_smem < sm.total) {
         CB200_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sm.total));
@@ -1088,15 +1091,16 @@ static int mega_cluster_count(int B, int resident, int max_clusters_hint) {
     return (B + share - 1) / share;
 }
 
-template <int D, int CL>
+template <int D, int CL, bool PROF = false>
 static int launch_mega(const MegaArgs& args, const MegaSmem& sm, int ncl, cudaStream_t s) {
+    if (!PROF && args.prof != nullptr) return launch_mega<D, CL, true>(args, sm, ncl, s);    // diagnostic instantiation
     cudaLaunchConfig_t cfg{};
     cudaLaunchAttribute attr[1];
-    int rc = mega_config<D, CL>(cfg, attr, sm);
+    int rc = mega_config<D, CL, PROF>(cfg, attr, sm);
     if (rc) return rc;
     cfg.stream = s;
     cfg.gridDim = dim3(ncl * CL);
-    CB200_CUDA_OK(cudaLaunchKernelEx(&cfg, decode_mega_kernel<D, CL>, args, sm));
+    CB200_CUDA_OK(cudaLaunchKernelEx(&cfg, decode_mega_kernel<D, CL, PROF>, args, sm));
     note_launch(1);
     return 0;
 }
