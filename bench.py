@@ -591,12 +591,13 @@ def generation_benchmark(model, world, rank, device, dist, cpu_baseline=True):
     traffic = None
     summary_path = os.path.join(ROOT, 'profiles', 'ncu_summary.json')
     if world == 1 and os.path.exists(summary_path):
-        with open(summary_path) as handle:
-            entry = json.load(handle).get('decode_mega_kernel<16, 4>')
         from composer_b200 import build as native_build
-        if entry and 'prompt 1, 1,024 events' in entry.get('capture', '') \
-                and entry.get('source_hash') == native_build.source_hash():
-            traffic = entry.get('dram_bytes_per_launch')
+        with open(summary_path) as handle:
+            summary = json.load(handle)
+        for name, entry in summary.items():      # decode_mega_kernel<d_h, cluster size, profiled>
+            if name.startswith('decode_mega_kernel<16, 4') and 'prompt 1, 1,024 events' in entry.get('capture', '') \
+                    and entry.get('source_hash') == native_build.source_hash():
+                traffic = entry.get('dram_bytes_per_launch')
     cpu = None
     if rank == 0 and world == 1 and cpu_baseline:
         cpu_value, threads, cpu_seconds = cpu_reference_generate(4, 256)
