@@ -104,52 +104,69 @@ int embed_bwd(const int32_t* ids, const __nv_bfloat16* dh, float* dwte, float* d
 // 563, 694): biased variance over the last axis, eps inside the rsqrt.
 // One warp per row; the row stays in registers between the two passes.
 // ---------------------------------------------------------------------------
-template <int VPL>  // 8-element vectors per lane: E = 256 * VPL
+// A warp normalises RPW rows at a time and issues all their loads before the first reduction: with one 512-byte row
+// in flight per warp the kernel was latency-bound at ~3.5 TB/s.
+template <int VPL, int RPW>  // 8-element vectors per lane: E = 256 * VPL; rows per warp
 __global__ void __launch_bounds__(256)
 layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, float* __restrict__ stats,
                      int rows, int E, float eps) {
-    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= rows) return;
+    const int row0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW;
+    if (row0 >= rows) return;
     const int lane = threadIdx.x & 31;
-    float f[VPL][8];
-    float sum = 0.f;
+    float f[RPW][VPL][8];
+    float sum[RPW];
 #pragma unroll
-    for (int v = 0; v < VPL; ++v) {
-        const uint4 raw = *reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * E + (v * 32 + lane) * 8);
-        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+    for (int r = 0; r < RPW; ++r) {
+        sum[r] = 0.f;
+        const int row = row0 + r < rows ? row0 + r : rows - 1;      // (a clamped duplicate keeps the loop uniform)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const float2 p = unpack_bf16(w[e]);
-            f[v][2 * e] = p.x; f[v][2 * e + 1] = p.y;
-            sum += p.x + p.y;
+        for (int v = 0; v < VPL; ++v) {
+            const uint4 raw = *reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * E + (v * 32 + lane) * 8);
+            const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 p = unpack_bf16(w[e]);
+                f[r][v][2 * e] = p.x; f[r][v][2 * e + 1] = p.y;
+                sum[r] += p.x + p.y;
+            }
         }
     }
-    const float mean = warp_sum(sum) / E;
-    float sq = 0.f;
-#pragma unroll
-    for (int v = 0; v < VPL; ++v)
-#pragma unroll
-        for (int e = 0; e < 8; ++e) { const float d = f[v][e] - mean; sq += d * d; }
-    const float rstd = rsqrtf(warp_sum(sq) / E + eps);
-    if (lane == 0 && stats != nullptr) {
-        stats[2 * static_cast<size_t>(row)] = mean;
-        stats[2 * static_cast<size_t>(row) + 1] = rstd;
-    }
+    float g[VPL][8], b[VPL][8];
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
         const int c = (v * 32 + lane) * 8;
         const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
         const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c + 4));
-        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-        const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-        float o[8];
+        g[v][0] = g0.x; g[v][1] = g0.y; g[v][2] = g0.z; g[v][3] = g0.w; g[v][4] = g1.x; g[v][5] = g1.y; g[v][6] = g1.z; g[v][7] = g1.w;
+        b[v][0] = b0.x; b[v][1] = b0.y; b[v][2] = b0.z; b[v][3] = b0.w; b[v][4] = b1.x; b[v][5] = b1.y; b[v][6] = b1.z; b[v][7] = b1.w;
+    }
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = (f[v][e] - mean) * rstd * g[e] + b[e];
-        uint4 out;
-        out.x = pack_bf16(o[0], o[1]); out.y = pack_bf16(o[2], o[3]);
-        out.z = pack_bf16(o[4], o[5]); out.w = pack_bf16(o[6], o[7]);
-        *reinterpret_cast<uint4*>(y + static_cast<size_t>(row) * E + c) = out;
+    for (int r = 0; r < RPW; ++r) {
+        const int row = row0 + r;
+        const float mean = warp_sum(sum[r]) / E;
+        float sq = 0.f;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { const float d = f[r][v][e] - mean; sq += d * d; }
+        const float rstd = rsqrtf(warp_sum(sq) / E + eps);
+        if (row >= rows) continue;
+        if (lane == 0 && stats != nullptr) {
+            stats[2 * static_cast<size_t>(row)] = mean;
+            stats[2 * static_cast<size_t>(row) + 1] = rstd;
+        }
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            const int c = (v * 32 + lane) * 8;
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = (f[r][v][e] - mean) * rstd * g[v][e] + b[v][e];
+            uint4 out;
+            out.x = pack_bf16(o[0], o[1]); out.y = pack_bf16(o[2], o[3]);
+            out.z = pack_bf16(o[4], o[5]); out.w = pack_bf16(o[6], o[7]);
+            *reinterpret_cast<uint4*>(y + static_cast<size_t>(row) * E + c) = out;
+        }
     }
 }
 
@@ -157,13 +174,15 @@ int layernorm_fwd(const __nv_bfloat16* x, const float* gamma, const float* beta,
                   int rows, int E, float eps, cudaStream_t s) {
     CB200_REQUIRE(E % 256 == 0 && E <= 2048, "LayerNorm needs the embedding size to be a multiple of 256 (<= 2048), got %d", E);
     if (rows == 0) return 0;
-    const int grid = (rows + 7) / 8;
+    // rows per warp: 4 at E = 256, 2 at 512, else 1 (the live row values stay within ~64 registers)
+    const int rpw = E == 256 ? 4 : E == 512 ? 2 : 1;
+    const int grid = (rows + 8 * rpw - 1) / (8 * rpw);
     switch (E / 256) {
-        case 1: layernorm_fwd_kernel<1><<<grid, 256, 0, s>>>(x, gamma, beta, y, stats, rows, E, eps); break;
-        case 2: layernorm_fwd_kernel<2><<<grid, 256, 0, s>>>(x, gamma, beta, y, stats, rows, E, eps); break;
-        case 3: layernorm_fwd_kernel<3><<<grid, 256, 0, s>>>(x, gamma, beta, y, stats, rows, E, eps); break;
-        case 4: layernorm_fwd_kernel<4><<<grid, 256, 0, s>>>(x, gamma, beta, y, stats, rows, E, eps); break;
-        case 8: layernorm_fwd_kernel<8><<<grid, 256, 0, s>>>(x, gamma, beta, y, stats, rows, E, eps); break;
+        case 1: layernorm_fwd_kernel<1, 4><<<grid, 256, 0, s>>>(x, gamma, beta, y, stats, rows, E, eps); break;
+        case 2: layernorm_fwd_kernel<2, 2><<<grid, 256, 0, s>>>(x, gamma, beta, y, stats, rows, E, eps); break;
+        case 3: layernorm_fwd_kernel<3, 1><<<grid, 256, 0, s>>>(x, gamma, beta, y, stats, rows, E, eps); break;
+        case 4: layernorm_fwd_kernel<4, 1><<<grid, 256, 0, s>>>(x, gamma, beta, y, stats, rows, E, eps); break;
+        case 8: layernorm_fwd_kernel<8, 1><<<grid, 256, 0, s>>>(x, gamma, beta, y, stats, rows, E, eps); break;
         default: set_error("unsupported embedding size %d for LayerNorm", E); return -1;
     }
     CB200_CUDA_OK(cudaGetLastError());
