@@ -1,18 +1,38 @@
-'''Aggregates an `ncu --page source --csv` dump by SASS opcode: executed warp instructions and stall samples.'''
-import collections, csv, sys
-rows = list(csv.reader(open(sys.argv[1])))
-hdr = rows[1]
-isrc, iex, ismp = hdr.index('Source'), hdr.index('Instructions Executed'), hdr.index('# Samples')
-ops = collections.Counter(); smp = collections.Counter()
-for r in rows[2:]:
-    if len(r) <= iex or not r[iex].isdigit(): continue
-    text = r[isrc].strip()
-    if text.startswith('@'): text = text.split(None, 1)[1]
-    op = text.split()[0].split('.')[0] if text else '?'
-    full = text.split()[0]
-    key = op if op not in ('MUFU', 'LDSM', 'MOVM') else full
-    ops[key] += int(r[iex] or 0); smp[key] += int(r[ismp] or 0)
-total = sum(ops.values()); stotal = sum(smp.values())
-print('total warp instructions %d, samples %d' % (total, stotal))
-for k, v in ops.most_common(28):
-    print('%-22s %12d %5.1f%%   stall samples %5.1f%%' % (k, v, 100.0 * v / total, 100.0 * smp[k] / max(stotal, 1)))
+'''Dynamic instruction mix of a kernel from an `ncu --set full --import-source on` report: warp instructions executed
+per opcode, per score element for the attention kernels.
+
+    python tools/ncu_opmix.py <report.ncu-rep> <kernel substring> [elements]
+'''
+import collections, csv, re, subprocess, sys
+
+def main():
+    path, pattern = sys.argv[1], sys.argv[2]
+    elements = float(sys.argv[3]) if len(sys.argv) > 3 else 32 * 16 * 2048 * 2049 / 2 / 32    # warp-elements, bench shape
+    raw = subprocess.run(['ncu', '-i', path, '--page', 'source', '--csv', '--print-source', 'sass'], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    byop, total, active = collections.Counter(), 0, False
+    for r in rows:
+        if r and r[0] == 'Kernel Name':
+            active = pattern in r[1]
+            hdr = None
+            continue
+        if not active:
+            continue
+        if r and r[0] == 'Address':
+            hdr = r
+            ia, isrc = hdr.index('Instructions Executed'), hdr.index('Source')
+            continue
+        if hdr is None or len(r) <= ia:
+            continue
+        try:
+            n = int(r[ia])
+        except ValueError:
+            continue
+        m = re.match(r'(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_]*)', r[isrc].strip())
+        byop[m.group(1) if m else '?'] += n
+        total += n
+    print('%s: %d warp instructions = %.2f per warp-element' % (pattern, total, total / elements))
+    for op, n in byop.most_common(28):
+        print('  %-10s %12d  %.2f' % (op, n, n / elements))
+
+main()
