@@ -82,6 +82,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     static_assert(RS == 1 || (RS == 2 && !PSMEM && KT_ == 128), "row split: two threads per row of a 128-key tile, P in TMEM");
     constexpr int KT = C::KT, RB = C::RB, QTILE = C::QTILE, KTILE = C::KTILE, NKV = C::NKV, NCH = KT / 32 / RS;
     constexpr int KW = KT / RS;                                 // keys per thread and tile
+    constexpr int FOLD_AT = (NCH >= 4) ? 0 : -1;            // fold O~ of the previous tile after this 32-key chunk (-1: after the maximum pass)
     constexpr int SW = 4 * RS;                                  // softmax warps; then: S issuer, TMA producer, TMEM allocation, P V issuer
     constexpr uint32_t LT = umma_layout_for_row_bytes(RB);
     constexpr uint32_t COL_O = C::COL_O, BUFC = C::BUF_COLS;
@@ -308,8 +309,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                 uint32_t s[KW];
 #pragma unroll
                 for (int c = 0; c < NCH; ++c) tmem_ld32(tbuf + part * KW + 32 * c, *reinterpret_cast<uint32_t(*)[32]>(&s[32 * c]));
-                if (j > 0) fold_o(g - 1);                   // (its tcgen05.wait::ld also covers the S loads above)
-                else tmem_ld_wait();
+                tmem_ld_wait();
                 TR(31);
 
                 const int key0 = j * KT + part * KW;        // first key of this thread's part
@@ -350,6 +350,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                     alpha = fast_exp2((m_run - m_new) * scale_log2);   // first tile: exp2(-inf) = 0
                     m_run = m_new;
                     TR(32);
+                    // O~ of the previous tile is folded here, after the maximum pass: its P V MMAs were triggered at the
+                    // end of the previous tile and need ~600 cycles (wake-up of the issuing thread, 8 MMAs, commit);
+                    // at the top of the tile the softmax warps waited ~300 of them (tools/trace_attention_fwd.py)
+                    if (FOLD_AT < 0 && j > 0) fold_o(g - 1);
                     const float nmc = -m_new * scale_log2;
                     const uint64_t n2 = f2_pack(nmc, nmc);
                     // ---- P = exp2(S c - m c), row sum (before dropout), dropout, bf16 ----
@@ -392,6 +396,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                             if (!(ABL & 4)) tmem_st16(tbuf + part * (KW / 2) + 16 * c, pk);
                             else asm volatile("" ::"r"(pk[0] ^ pk[5] ^ pk[10] ^ pk[15]));
                         }
+                        if (FOLD_AT == c && j > 0) fold_o(g - 1);
                     }
                 };
                 if (diag) tile_math(std::true_type{});
