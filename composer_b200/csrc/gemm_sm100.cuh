@@ -344,7 +344,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         float g[32];
                         if (EPI == EPI_BIAS_GELU) {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) g[j] = gelu_tanh(f[j]);
+                            for (int j = 0; j < 32; j += 2) f2_unpack(gelu_tanh2(f2_pack(f[j], f[j + 1])), g[j], g[j + 1]);
                         }
                         if (EPI == EPI_BIAS_DROP_RES || EPI == EPI_MUL_DGELU) {
                             const bool in_rows = row < args.M;
@@ -370,8 +370,8 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                                         f[j + e] = a2.x + x0;
                                         f[j + e + 1] = a2.y + x1;
                                     } else {
-                                        f[j + e] *= gelu_tanh_grad(a2.x);
-                                        f[j + e + 1] *= gelu_tanh_grad(a2.y);
+                                        f2_unpack(f2_mul(f2_pack(f[j + e], f[j + e + 1]), gelu_tanh_grad2(f2_pack(a2.x, a2.y))),
+                                                  f[j + e], f[j + e + 1]);
                                     }
                                 }
                             }
