@@ -44,12 +44,13 @@ struct MegaArgs {
     int32_t* out_ids;              // [B, steps]
     float* uniforms;               // [B, steps] or null
     float* logits_out;             // [B, V] logits of the last step, or null
-    long long* prof;               // 24 cycle counters (phase profile of cluster 0: 15 phases, then ring waits per phase), or null
+    long long* prof;               // 64 cycle counters (phase profile of cluster 0: 15 phases, ring waits per phase from 16, marks inside the linear phases from 24), or null
     long long layer_stride;        // elements per layer of the cache
     int B, E, H, F, V, L, t_max, steps, use_ln, greedy, seq_base;
     int step0;                     // first step to run: positions 0 .. step0-1 are already in the cache (batched prefill)
     int kv_split_log2;             // a pair's KV chunks go to up to 1 << this warps when the CTA has few pairs (set by decode_mega)
     int kv_prefetch;               // KV chunks per warp and attention phase requested into L2 during the GEMM phases (set by decode_mega)
+    int async_gather;              // 1: all-gathers complete on mbarriers (st.async), 0: at cluster barriers (set by decode_mega)
     int l2_hints;                  // 1: cache reads evict-first, weight stream evict-last (set by decode_mega)
     float eps, scale_log2, inv_temperature;
     uint32_t seed_lo, seed_hi;

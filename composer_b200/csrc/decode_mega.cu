@@ -86,6 +86,17 @@ __device__ __forceinline__ void st_cluster_v2(uint32_t addr, uint32_t x, uint32_
 __device__ __forceinline__ void st_cluster_u32(uint32_t addr, uint32_t v) {
     asm volatile("st.shared::cluster.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
+// A remote store that reports its bytes to an mbarrier of the destination CTA (STAS): the receiver learns that an
+// all-gather is complete by waiting for the byte count on its own mbarrier, and nobody executes a fence.
+// (`barrier.cluster.arrive.release` / `wait.acquire` compile to MEMBAR.ALL.GPU + ERRBAR in front of the arrive and
+// CCTL.IVALL after the wait, in every thread: cluster scope is implemented at GPU scope.  Plain remote stores
+// followed by one `mbarrier.arrive.release.cluster` per sending warp were measured slower than the cluster barrier:
+// the MEMBAR of a single warp costs as much as that of all warps together.)
+__device__ __forceinline__ void st_async_v4(uint32_t addr, const uint4& v, uint32_t bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(addr), "r"(v.x), "r"(v.y),
+                 "r"(v.z), "r"(v.w), "r"(bar)
+                 : "memory");
+}
 // L2 eviction policies of the copies: the KV cache is streamed once per step (evict first), the weight stream is
 // re-read by every cluster every step (evict last), so that 1 GB of cache reads per step does not push the 13 MB of
 // weights out of L2.
@@ -313,22 +324,33 @@ __device__ __forceinline__ void slot_mma(float (&acc)[4], const uint8_t* slot, c
     for (int e = 0; e < 4; ++e) acc[e] += (part[0][e] + part[1][e]) + (part[2][e] + part[3][e]);
 }
 
+// Diagnostic (PROF instantiation only): finer marks inside a linear phase, cycles of one thread since the last mark.
+struct FineProf {
+    long long* acc;        // 6 counters of the current phase kind, or null
+    long long t;
+    __device__ __forceinline__ void mark(int i) {
+        if (acc != nullptr) { const long long now = clock64(); acc[i] += now - t; t = now; }
+    }
+};
+
 // Runs this warp's units of `ph` on the activations X[8, K] (bf16 in shared memory, row pitch `pitch` bytes); the
 // weight slots are the warp's next jobs.  K-split partials meet in `red`.  The warp that owns K part 0 of a tile
 // calls epi(col, seq, lo, hi) once per lane with the complete sums (bias added) of sequence `seq` at output columns
 // (col, col + 1) = lo and (col + 8, col + 9) = hi, col relative to this CTA's slice.  All 16 warps must call this
 // (it may contain a __syncthreads).  There is one call site (the phase loop of the kernel): the kernel's code has
 // to stay within the instruction cache, a phase is only a few hundred instructions long.
-template <int D, bool PROF, typename Epi>
+template <int D, bool PROF, bool DEFER, typename Epi>
 __device__ __forceinline__ void run_phase(const Phase& ph, const uint8_t* X, int pitch, JobRing& ring, const JobPlan& plan,
-                                          float* red, int warp, int lane, Epi epi) {
+                                          float* red, int warp, int lane, FineProf fine, Epi epi) {
     const int g = lane >> 2, tig = lane & 3;
+    if (PROF) fine.mark(0);
     const uint8_t* b0 = X + g * pitch + tig * 16;
     const int nunits = ph.ntiles * ph.ksplit;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     float bias_lo = 0.f, bias_hi = 0.f;
     int nt = 0;
     bool owner = false;                            // this warp holds K part 0 of tile nt in acc
+    bool held = false;                             // the stage of the last slot has not been released yet
     for (int u = warp; u < nunits; u += MG_WARPS) {
         // with several units per warp (then ksplit == 1) the previous tile is finished first
         if (owner) {
@@ -344,18 +366,25 @@ __device__ __forceinline__ void run_phase(const Phase& ph, const uint8_t* X, int
         const int ks = (ph.ksplit == 1) ? 0 : ph.ks0;
         for (int j = 0; j < ph.sub; ++j) {
             const uint8_t* slot = ring_acquire<PROF>(ring);
+            if (PROF) fine.mark(1);
             if (j == 0) {
                 bias_lo = *reinterpret_cast<const float*>(slot + MG_SLOT_W + g * 4);
                 bias_hi = *reinterpret_cast<const float*>(slot + MG_SLOT_W + (g + 8) * 4);
             }
             slot_mma(acc, slot, b0 + (ks * ph.sub + j) * 256, lane);
-            ring_release<D>(ring, plan, lane);
+            if (PROF) fine.mark(2);
+            held = DEFER && (j + 1 == ph.sub) && (u + MG_WARPS >= nunits);
+            if (!held) {
+                ring_release<D>(ring, plan, lane);
+                if (PROF) fine.mark(3);
+            }
         }
         owner = ks == 0;
         if (ks > 0) *reinterpret_cast<float4*>(red + (((ks - 1) * ph.ntiles + nt) * 32 + lane) * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
     }
     if (ph.ksplit > 1) {
         __syncthreads();
+        if (PROF) fine.mark(4);
         if (owner)
             for (int k2 = 1; k2 < ph.ksplit; ++k2) {
                 const float4 p = *reinterpret_cast<const float4*>(red + (((k2 - 1) * ph.ntiles + nt) * 32 + lane) * 4);
@@ -371,6 +400,15 @@ __device__ __forceinline__ void run_phase(const Phase& ph, const uint8_t* X, int
         epi(nt * 16 + (g & ~1), 2 * tig + (odd ? 1 : 0), odd ? make_float2(r0, acc[1]) : make_float2(acc[0], r0),
             odd ? make_float2(r1, acc[3]) : make_float2(acc[2], r1));
     }
+    if (PROF) fine.mark(5);
+    // DEFER (few sequences per cluster, every phase is a latency chain): the stage of the warp's last slot is re-armed
+    // only now; finding and issuing the next job is ~100 scalar instructions, which otherwise sit between the MMAs
+    // and the K-split barrier / the epilogue.  (With 8 sequences per cluster the attention phase is paced by the
+    // ring, and issuing later costs more than it saves: 250 vs 239 us per step at 256 sequences.)
+    if (held) {
+        ring_release<D>(ring, plan, lane);
+        if (PROF) fine.mark(3);
+    }
 }
 
 __device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
@@ -385,6 +423,21 @@ __device__ __forceinline__ void broadcast_u32(const uint8_t* local, uint32_t val
     const uint32_t a = smem_u32(local);
 #pragma unroll
     for (int r = 0; r < CL; ++r) st_cluster_u32(map_to_cta(a, r), val);
+}
+
+// A 16-byte piece of this CTA's copy of an activation to the same place in every CTA of the cluster (this one
+// included: its mbarrier counts those bytes too), each store counted on the mbarrier `bar` (a shared::cta address,
+// the same in every CTA) of its destination.  The window of a CTA in the cluster's shared address space keeps the
+// offsets, so one `mapa` per destination serves the barrier and the data.
+template <int CL>
+__device__ __forceinline__ void broadcast16_async(const uint8_t* local, uint32_t bar) {
+    const uint4 v = *reinterpret_cast<const uint4*>(local);
+    const uint32_t d = smem_u32(local) - bar;
+#pragma unroll
+    for (int r = 0; r < CL; ++r) {
+        const uint32_t rb = map_to_cta(bar, r);
+        st_async_v4(rb + d, v, rb);
+    }
 }
 
 // gamma / beta of one LayerNorm as the lanes of a warp need them (lane = 16-byte chunk of the row, two chunks for
@@ -407,8 +460,8 @@ __device__ __forceinline__ void ln_prefetch(LnFrag& f, const float* gamma, const
 // LayerNorm of the 16 rows of `src` into `dst` (warp = row), both [16, E] bf16 with pitch pe.  Two passes in
 // registers like layernorm_fwd_kernel; the output is rounded to bf16 (what the next GEMM consumes).
 __device__ __forceinline__ void layernorm_rows(const uint8_t* src, uint8_t* dst, int pe, int E, const LnFrag& f, float eps,
-                                               bool enabled, int warp, int lane) {
-    if (warp >= MG_ROWS) return;
+                                               bool enabled, int rows, int warp, int lane) {
+    if (warp >= rows) return;                 // (rows without a sequence keep the zeros of the start: their MMA columns are not used)
     const uint8_t* s = src + warp * pe;
     uint8_t* d = dst + warp * pe;
     const int nchunk = E / 8;                 // 16-byte chunks per row: 32 (E 256) or 64 (E 512)
@@ -444,8 +497,9 @@ __device__ __forceinline__ void layernorm_rows(const uint8_t* src, uint8_t* dst,
         sum += __shfl_xor_sync(0xffffffffu, sum, o);
         sq += __shfl_xor_sync(0xffffffffu, sq, o);
     }
-    const float mean = sum / E;
-    const float rstd = rsqrtf(fmaxf(sq / E - mean * mean, 0.f) + eps);
+    const float inv_e = 1.0f / E;
+    const float mean = sum * inv_e;
+    const float rstd = rsqrtf(fmaxf(sq * inv_e - mean * mean, 0.f) + eps);
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
         const int ch = lane + 32 * i;
@@ -521,7 +575,7 @@ __device__ __forceinline__ int sample_row_smem(float* z, int V, float inv_temper
 
 // PROF: the phase profile (cb200_set_decode_profile) is compiled in; a separate instantiation, because even never-taken
 // diagnostic branches on the job path cost the default kernel issue slots.
-template <int D, int CL, bool PROF = false>
+template <int D, int CL, bool PROF = false, bool AG = true>
 __global__ void __launch_bounds__(MG_THREADS, 1)
 decode_mega_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ MegaSmem sm) {
     constexpr int CH = D / 8;                     // 16-byte chunks per head row
@@ -562,10 +616,21 @@ decode_mega_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ M
 
     // ---- one-time setup ----
     for (int i = tid * 16; i < sm.bars; i += MG_THREADS * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
-    if (tid < MG_WARPS * NST + sm.nst_extra) mbar_init(&bars[tid], 1);
+    if (tid < MG_WARPS * NST + sm.nst_extra + 4) mbar_init(&bars[tid], 1);
     if (tid < MG_ROWS) toks[tid] = (tid < G) ? a.first[s0 + tid] : 0;
     mbar_fence_init();
     __syncthreads();
+    // AG: the four all-gathers of a decoder block (attention output, x2, GELU output, block output) complete on
+    // mbarriers of the receiving CTA: one arrival (thread 0, which states the bytes of the coming gather) plus
+    // the bytes themselves.  A gather can only be sent to a CTA that has passed the previous use of the same barrier
+    // and re-armed it: the sender has by then received that CTA's slices of the three gathers in between.
+    uint64_t* gbar = bars + MG_WARPS * NST + sm.nst_extra;
+    const uint32_t gbar_a = smem_u32(gbar);
+    const uint32_t gbytes[4] = {static_cast<uint32_t>(G * a.E * 2), static_cast<uint32_t>(G * a.E * 2),
+                                static_cast<uint32_t>(G * a.F * 2), static_cast<uint32_t>(G * a.E * 2)};
+    uint32_t gpar = 0;
+    if (AG && tid == 0)
+        for (int k = 0; k < 4; ++k) mbar_expect_tx(&gbar[k], gbytes[k]);
 
     // phases of a decoder block and of the head as this CTA sees them (16-column tiles, K split, slots per unit)
     auto make_phase = [&](int ntiles, int ksplit, int K) {
@@ -630,7 +695,7 @@ decode_mega_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ M
     const bool profiling = PROF && a.prof != nullptr && blockIdx.x == 0 && tid == 0;
     long long* prof_acc = reinterpret_cast<long long*>(smem + sm.prof);
     if (profiling)
-        for (int i = 0; i < 24; ++i) prof_acc[i] = 0;
+        for (int i = 0; i < 64; ++i) prof_acc[i] = 0;
     long long prof_t = profiling ? clock64() : 0;
 #define MG_PROF(slot)                                                        \
     if (PROF && profiling) {                                                 \
@@ -671,7 +736,7 @@ decode_mega_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ M
             const MegaLayer& lw = a.layers[l < a.L ? l : 0];
             // ---- LayerNorm in front of c_attn (ln_1), c_fc (ln_2) and the logits (ln_f) ----
             if (kind == 0 || kind == 2 || kind == 4) {
-                layernorm_rows(X, bufN, pe, E, lnf, a.eps, use_ln, warp, lane);
+                layernorm_rows(X, bufN, pe, E, lnf, a.eps, use_ln, G, warp, lane);
                 if (use_ln && kind != 0) {         // (ln_2's parameters are fetched after the attention)
                     const bool more = kind == 2 && l + 1 < a.L;          // next: ln_1 of the next block, else ln_f / ln_1 of block 0
                     const MegaLayer& nx = a.layers[more ? l + 1 : 0];
@@ -698,7 +763,9 @@ decode_mega_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ M
                                       jr.nst + kind * a.kv_prefetch / 3, lane);      // (the first jobs of the phase are fetched by the ring itself)
             }
             MG_WAIT_SLOT(kind == 0 ? 0 : kind + 1)
-            run_phase<D, PROF>(ph, src, src_pitch, jr, plan, red, warp, lane, [&](int col, int seq, float2 lo, float2 hi) {
+            FineProf fine{nullptr, 0};
+            if (PROF && profiling) { fine.acc = prof_acc + 24 + 6 * kind; fine.t = prof_t; }
+            run_phase<D, PROF, AG>(ph, src, src_pitch, jr, plan, red, warp, lane, fine, [&](int col, int seq, float2 lo, float2 hi) {
                 if (kind == 0) {                   // q, k, v of this CTA's heads (bf16, local)
                     uint8_t* q = qkvs + (seq * 3 * HS + col) * 2;
                     *reinterpret_cast<uint32_t*>(q) = pack_bf16(lo.x, lo.y);
@@ -718,8 +785,21 @@ decode_mega_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ M
                         const float2 r1 = unpack_bf16(*reinterpret_cast<const uint32_t*>(res + off + 16));
                         lo.x += r0.x; lo.y += r0.y; hi.x += r1.x; hi.y += r1.y;
                     }
-                    broadcast_u32<CL>(dst + off, pack_bf16(lo.x, lo.y), seq < G);
-                    broadcast_u32<CL>(dst + off + 16, pack_bf16(hi.x, hi.y), seq < G);
+                    if (AG) {
+                        // the tile (8 sequences x 16 columns) goes into this CTA's copy first; then it leaves as 16-byte
+                        // pieces (lane = sequence and half of the 32-byte row): a quarter of the packets and of the
+                        // byte-count updates of the mbarriers that single words would need
+                        if (seq < G) {
+                            *reinterpret_cast<uint32_t*>(dst + off) = pack_bf16(lo.x, lo.y);
+                            *reinterpret_cast<uint32_t*>(dst + off + 16) = pack_bf16(hi.x, hi.y);
+                        }
+                        __syncwarp();
+                        if (lane < 16 && (lane >> 1) < G)
+                            broadcast16_async<CL>(dst + (lane >> 1) * dst_pitch + (col0 + col - (g & ~1)) * 2 + (lane & 1) * 16, gbar_a + 8 * kind);
+                    } else {
+                        broadcast_u32<CL>(dst + off, pack_bf16(lo.x, lo.y), seq < G);
+                        broadcast_u32<CL>(dst + off + 16, pack_bf16(hi.x, hi.y), seq < G);
+                    }
                 }
             });
             if (kind == 4) break;                  // the step ends with the sampling below
@@ -888,7 +968,28 @@ decode_mega_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ M
                         }
                         const float inv = 4.0f / lsum;                  // lsum counted every token in its 4 tig lanes
                         // every quad holds the same output row: quad g sends it to CTA g of the cluster
-                        if (lead && g < CL) {
+                        if (AG) {
+                            if (lead) {
+                                // lane tig of a quad collects the 16-byte pieces tig, tig + 4 of the head's output row (every
+                                // quad holds the whole row); quad g sends them to CTA g
+                                constexpr int NP = (NT_O + 3) / 4;
+                                uint4 piece[NP] = {};
+    #pragma unroll
+                                for (int dt = 0; dt < NT_O; ++dt) {
+                                    const uint32_t pk = pack_bf16(o[dt][0] * inv, o[dt][1] * inv);
+                                    const uint32_t w0 = __shfl_sync(0xffffffffu, pk, lane & ~3), w1 = __shfl_sync(0xffffffffu, pk, (lane & ~3) + 1);
+                                    const uint32_t w2 = __shfl_sync(0xffffffffu, pk, (lane & ~3) + 2), w3 = __shfl_sync(0xffffffffu, pk, (lane & ~3) + 3);
+                                    if (tig == (dt & 3)) piece[dt >> 2] = make_uint4(w0, w1, w2, w3);
+                                }
+                                if (g < CL) {
+                                    const uint32_t rb = map_to_cta(gbar_a, g);
+                                    const uint32_t dst = rb + (smem_u32(Y + sl * pe + h * D * 2) - gbar_a);
+    #pragma unroll
+                                    for (int i = 0; i < NP; ++i)
+                                        if (4 * i + tig < NT_O) st_async_v4(dst + (4 * i + tig) * 16, piece[i], rb);
+                                }
+                            }
+                        } else if (lead && g < CL) {
                             const uint32_t dst = map_to_cta(smem_u32(Y + sl * pe + (h * D + 2 * tig) * 2), g);
     #pragma unroll
                             for (int dt = 0; dt < NT_O; ++dt) st_cluster_u32(dst + dt * 16, pack_bf16(o[dt][0] * inv, o[dt][1] * inv));
@@ -898,7 +999,17 @@ decode_mega_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ M
                 if (use_ln) ln_prefetch(lnf, P + lw.ln2_g, P + lw.ln2_b, E, lane);
             }
             MG_PROF(kind == 0 ? 3 : 2 * kind + 3)
-            cluster_sync_all();                    // the all-gathered activation is complete in every CTA
+            if (AG) {                              // every slice of the all-gathered activation has arrived in this CTA
+                // (one warp polls the mbarrier, the others sleep at the CTA barrier)
+                if (warp == 0) {
+                    mbar_wait(&gbar[kind], gpar);
+                    if (lane == 0) mbar_expect_tx(&gbar[kind], gbytes[kind]);
+                }
+                __syncthreads();
+                if (kind == 3) gpar ^= 1u;
+            } else {
+                cluster_sync_all();                // the all-gathered activation is complete in every CTA
+            }
             MG_PROF(2 * kind + 4)
             if (kind == 3) { uint8_t* t = X; X = Y; Y = t; }        // the block output becomes the next block's input
         }
@@ -929,7 +1040,7 @@ decode_mega_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ M
         MG_PROF(14)
     }
     if (profiling)
-        for (int i = 0; i < 24; ++i) a.prof[i] = prof_acc[i];
+        for (int i = 0; i < 64; ++i) a.prof[i] = prof_acc[i];
 #undef MG_PROF
 #undef MG_WAIT_SLOT
 }
@@ -1020,9 +1131,9 @@ static MegaSmem mega_smem_layout(int E, int F, int V, int D, int CL, int nst, in
     if (MG_ROWS * s.zp * 4 <= MG_ROWS * s.pf) s.zbuf = s.bufg;
     else s.zbuf = take(MG_ROWS * s.zp * 4);
     s.ring = take((MG_WARPS * nst + nst_extra) * MG_STAGE);
-    s.bars = take((MG_WARPS * nst + nst_extra) * 8);
+    s.bars = take((MG_WARPS * nst + nst_extra + 4) * 8);      // ring stages, then the four all-gather barriers
     s.toks = take(MG_ROWS * 4);
-    s.prof = take(24 * 8);
+    s.prof = take(64 * 8);
     s.total = off;
     return s;
 }
@@ -1047,9 +1158,9 @@ static MegaSmem mega_smem_fit(int E, int V, int D, int CL, int L) {
     return sm;
 }
 
-template <int D, int CL, bool PROF = false>
+template <int D, int CL, bool PROF = false, bool AG = true>
 static int mega_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, const MegaSmem& sm) {
-    auto kernel = decode_mega_kernel<D, CL, PROF>;
+    auto kernel = decode_mega_kernel<D, CL, PROF, AG>;
     static int configured_smem = 0;
     if (configured_smem < sm.total) {
         CB200_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sm.total));
@@ -1091,16 +1202,17 @@ static int mega_cluster_count(int B, int resident, int max_clusters_hint) {
     return (B + share - 1) / share;
 }
 
-template <int D, int CL, bool PROF = false>
+template <int D, int CL, bool PROF = false, bool AG = true>
 static int launch_mega(const MegaArgs& args, const MegaSmem& sm, int ncl, cudaStream_t s) {
-    if (!PROF && args.prof != nullptr) return launch_mega<D, CL, true>(args, sm, ncl, s);    // diagnostic instantiation
+    if (!PROF && args.prof != nullptr) return launch_mega<D, CL, true, AG>(args, sm, ncl, s);    // diagnostic instantiation
+    if (AG && !args.async_gather) return launch_mega<D, CL, PROF, false>(args, sm, ncl, s);      // cluster barriers
     cudaLaunchConfig_t cfg{};
     cudaLaunchAttribute attr[1];
-    int rc = mega_config<D, CL, PROF>(cfg, attr, sm);
+    int rc = mega_config<D, CL, PROF, AG>(cfg, attr, sm);
     if (rc) return rc;
     cfg.stream = s;
     cfg.gridDim = dim3(ncl * CL);
-    CB200_CUDA_OK(cudaLaunchKernelEx(&cfg, decode_mega_kernel<D, CL, PROF>, args, sm));
+    CB200_CUDA_OK(cudaLaunchKernelEx(&cfg, decode_mega_kernel<D, CL, PROF, AG>, args, sm));
     note_launch(1);
     return 0;
 }
@@ -1236,11 +1348,18 @@ int decode_mega(MegaArgs args, int D, int max_clusters, int cluster_size, uint8_
     if (const char* env = getenv("CB200_DECODE_KV_SPLIT")) args.kv_split_log2 = std::min(3, std::max(0, atoi(env)));      // tuning knob
     args.l2_hints = 1;
     if (const char* env = getenv("CB200_DECODE_L2_HINTS")) args.l2_hints = atoi(env) != 0;
+    // All-gathers through st.async + mbarriers unless the clusters are full: measured on one B200 (us per step,
+    // st.async vs cluster barriers) 101.7 / 108.6 at 16 sequences, 107.8 / 114.6 at 32, 123.4 / 130.1 at 64,
+    // 134.1 / 139.8 at 96 (8-CTA clusters), 156.6 / 157.4 at 128, 202.5 / 203.5 at 192, 245.1 / 242.6 at 256 (4-CTA
+    // clusters of 4, 6, 8 sequences): each 16-byte st.async costs its destination ~2 cycles, which at 8 sequences per
+    // cluster outweighs the four cluster barriers per block.
+    args.async_gather = CL == 8 || (args.B + ncl - 1) / ncl <= 6;
+    if (const char* env = getenv("CB200_DECODE_ASYNC_GATHER")) args.async_gather = atoi(env) != 0;      // tuning knob
     // L2 prefetch budget of an attention phase, dealt evenly to the warps of all CTAs as whole 4 KB chunks
     int prefetch_mb = 0;          // (measured: a net loss, the prefetch traffic slows the GEMM phases by more than its hits save)
     if (const char* env = getenv("CB200_DECODE_KV_PREFETCH_MB")) prefetch_mb = std::max(0, atoi(env));                  // tuning knob
     args.kv_prefetch = static_cast<int>(std::min<long long>(30, (static_cast<long long>(prefetch_mb) << 20) / (static_cast<long long>(ncl) * CL * MG_WARPS * MG_STAGE)));
-    if (args.prof != nullptr) CB200_CUDA_OK(cudaMemsetAsync(args.prof, 0, 24 * sizeof(long long), s));
+    if (args.prof != nullptr) CB200_CUDA_OK(cudaMemsetAsync(args.prof, 0, 64 * sizeof(long long), s));
     return CB200_MEGA_DISPATCH(launch_mega, args, sm, ncl, s);
 }
 

@@ -197,7 +197,7 @@ int layernorm_fwd(const __nv_bfloat16* x, const float* gamma, const float* beta,
 // Persistent blocks: each warp walks rows with a grid stride and keeps its
 // dgamma/dbeta partials in registers; one smem reduction + atomics at the end.
 // ---------------------------------------------------------------------------
-template <int VPL>
+template <int VPL, int RPI>
 __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy_a, const __nv_bfloat16* __restrict__ dy_b,
                      const __nv_bfloat16* __restrict__ x, const float* __restrict__ stats,
@@ -222,67 +222,90 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy_a, const __nv_bfloat16
 #pragma unroll
         for (int e = 0; e < 8; ++e) { pg[v][e] = 0.f; pb[v][e] = 0.f; }
     }
-    for (int row = blockIdx.x * (blockDim.x >> 5) + warp; row < rows; row += warps_total) {
-        const float mean = stats[2 * static_cast<size_t>(row)], rstd = stats[2 * static_cast<size_t>(row) + 1];
-        float dyv[VPL][8], xh[VPL][8];
-        float s1 = 0.f, s2 = 0.f;
+    // RPI rows per warp and iteration, all their loads issued before the first use: one row per warp (2 KB) left
+    // 32 KB per SM in flight, short of what the HBM latency needs at 6.5 TB/s
+    for (int row0 = blockIdx.x * (blockDim.x >> 5) + warp; row0 < rows; row0 += RPI * warps_total) {
+        uint4 ra[RPI][VPL], rx[RPI][VPL], rb[RPI][VPL], rr[RPI][VPL];
+        float mean[RPI], rstd[RPI];
 #pragma unroll
-        for (int v = 0; v < VPL; ++v) {
-            const size_t off = static_cast<size_t>(row) * E + (v * 32 + lane) * 8;
-            const uint4 ra = *reinterpret_cast<const uint4*>(dy_a + off);
-            const uint4 rx = *reinterpret_cast<const uint4*>(x + off);
-            uint4 rb = make_uint4(0, 0, 0, 0);
-            if (dy_b != nullptr) rb = *reinterpret_cast<const uint4*>(dy_b + off);
-            const uint32_t wa[4] = {ra.x, ra.y, ra.z, ra.w}, wx[4] = {rx.x, rx.y, rx.z, rx.w}, wb[4] = {rb.x, rb.y, rb.z, rb.w};
+        for (int r = 0; r < RPI; ++r) {
+            const int row = row0 + r * warps_total;
+            const bool live = row < rows;
+            mean[r] = live ? stats[2 * static_cast<size_t>(row)] : 0.f;
+            rstd[r] = live ? stats[2 * static_cast<size_t>(row) + 1] : 0.f;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const float2 a = unpack_bf16(wa[e]), b = unpack_bf16(wb[e]), xx = unpack_bf16(wx[e]);
-                dyv[v][2 * e] = a.x + b.x; dyv[v][2 * e + 1] = a.y + b.y;
-                xh[v][2 * e] = (xx.x - mean) * rstd; xh[v][2 * e + 1] = (xx.y - mean) * rstd;
-            }
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const float g = dyv[v][e] * gam[v][e];
-                s1 += g; s2 += g * xh[v][e];
-                pg[v][e] += dyv[v][e] * xh[v][e];
-                pb[v][e] += dyv[v][e];
+            for (int v = 0; v < VPL; ++v) {
+                const size_t off = static_cast<size_t>(row) * E + (v * 32 + lane) * 8;
+                ra[r][v] = rx[r][v] = rb[r][v] = rr[r][v] = make_uint4(0, 0, 0, 0);
+                if (live) {
+                    ra[r][v] = *reinterpret_cast<const uint4*>(dy_a + off);
+                    rx[r][v] = *reinterpret_cast<const uint4*>(x + off);
+                    if (dy_b != nullptr) rb[r][v] = *reinterpret_cast<const uint4*>(dy_b + off);
+                    if (RPI > 1 && dres != nullptr) rr[r][v] = *reinterpret_cast<const uint4*>(dres + off);
+                }
             }
         }
-        s1 = warp_sum(s1) / E;
-        s2 = warp_sum(s2) / E;
 #pragma unroll
-        for (int v = 0; v < VPL; ++v) {
-            const size_t off = static_cast<size_t>(row) * E + (v * 32 + lane) * 8;
-            float o[8];
+        for (int r = 0; r < RPI; ++r) {
+            const int row = row0 + r * warps_total;
+            if (row >= rows) break;                   // (warp-uniform)
+            float dyv[VPL][8], xh[VPL][8];
+            float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) o[e] = rstd * (dyv[v][e] * gam[v][e] - s1 - xh[v][e] * s2);
-            if (dres != nullptr) {
-                const uint4 rr = *reinterpret_cast<const uint4*>(dres + off);
-                const uint32_t wr[4] = {rr.x, rr.y, rr.z, rr.w};
+            for (int v = 0; v < VPL; ++v) {
+                const uint32_t wa[4] = {ra[r][v].x, ra[r][v].y, ra[r][v].z, ra[r][v].w};
+                const uint32_t wx[4] = {rx[r][v].x, rx[r][v].y, rx[r][v].z, rx[r][v].w};
+                const uint32_t wb[4] = {rb[r][v].x, rb[r][v].y, rb[r][v].z, rb[r][v].w};
 #pragma unroll
-                for (int e = 0; e < 4; ++e) { const float2 r = unpack_bf16(wr[e]); o[2 * e] += r.x; o[2 * e + 1] += r.y; }
-            }
-            uint4 out;
-            out.x = pack_bf16(o[0], o[1]); out.y = pack_bf16(o[2], o[3]);
-            out.z = pack_bf16(o[4], o[5]); out.w = pack_bf16(o[6], o[7]);
-            *reinterpret_cast<uint4*>(dx + off) = out;
-            if (tail.dbias != nullptr) {
-                // what bias_grad would do with dx as its input: the bf16-rounded values, the same keep mask
-                const uint32_t wo[4] = {out.x, out.y, out.z, out.w};
-                float f[8];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) { const float2 p = unpack_bf16(wo[e]); f[2 * e] = p.x; f[2 * e + 1] = p.y; }
-                if (tail.drop.threshold16 != 0) {
-                    const Philox4 r = drop_bits_rowmajor(tail.drop, tail.site, tail.layer, row, v * 32 + lane);
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) f[e] = (drop_u16(r, e) < tail.drop.threshold16) ? 0.f : f[e] * tail.drop.keep_scale;
-                    uint4 g;
-                    g.x = pack_bf16(f[0], f[1]); g.y = pack_bf16(f[2], f[3]);
-                    g.z = pack_bf16(f[4], f[5]); g.w = pack_bf16(f[6], f[7]);
-                    *reinterpret_cast<uint4*>(tail.g_out + off) = g;
+                for (int e = 0; e < 4; ++e) {
+                    const float2 a = unpack_bf16(wa[e]), b = unpack_bf16(wb[e]), xx = unpack_bf16(wx[e]);
+                    dyv[v][2 * e] = a.x + b.x; dyv[v][2 * e + 1] = a.y + b.y;
+                    xh[v][2 * e] = (xx.x - mean[r]) * rstd[r]; xh[v][2 * e + 1] = (xx.y - mean[r]) * rstd[r];
                 }
 #pragma unroll
-                for (int e = 0; e < 8; ++e) pt[v][e] += f[e];
+                for (int e = 0; e < 8; ++e) {
+                    const float g = dyv[v][e] * gam[v][e];
+                    s1 += g; s2 += g * xh[v][e];
+                    pg[v][e] += dyv[v][e] * xh[v][e];
+                    pb[v][e] += dyv[v][e];
+                }
+            }
+            s1 = warp_sum(s1) / E;
+            s2 = warp_sum(s2) / E;
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+                const size_t off = static_cast<size_t>(row) * E + (v * 32 + lane) * 8;
+                float o[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] = rstd[r] * (dyv[v][e] * gam[v][e] - s1 - xh[v][e] * s2);
+                if (dres != nullptr) {
+                    if (RPI == 1) rr[r][v] = *reinterpret_cast<const uint4*>(dres + off);      // (late: fewer live registers)
+                    const uint32_t wr[4] = {rr[r][v].x, rr[r][v].y, rr[r][v].z, rr[r][v].w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) { const float2 q = unpack_bf16(wr[e]); o[2 * e] += q.x; o[2 * e + 1] += q.y; }
+                }
+                uint4 out;
+                out.x = pack_bf16(o[0], o[1]); out.y = pack_bf16(o[2], o[3]);
+                out.z = pack_bf16(o[4], o[5]); out.w = pack_bf16(o[6], o[7]);
+                *reinterpret_cast<uint4*>(dx + off) = out;
+                if (tail.dbias != nullptr) {
+                    // what bias_grad would do with dx as its input: the bf16-rounded values, the same keep mask
+                    const uint32_t wo[4] = {out.x, out.y, out.z, out.w};
+                    float f[8];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) { const float2 q = unpack_bf16(wo[e]); f[2 * e] = q.x; f[2 * e + 1] = q.y; }
+                    if (tail.drop.threshold16 != 0) {
+                        const Philox4 ph = drop_bits_rowmajor(tail.drop, tail.site, tail.layer, row, v * 32 + lane);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) f[e] = (drop_u16(ph, e) < tail.drop.threshold16) ? 0.f : f[e] * tail.drop.keep_scale;
+                        uint4 g;
+                        g.x = pack_bf16(f[0], f[1]); g.y = pack_bf16(f[2], f[3]);
+                        g.z = pack_bf16(f[4], f[5]); g.w = pack_bf16(f[6], f[7]);
+                        *reinterpret_cast<uint4*>(tail.g_out + off) = g;
+                    }
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) pt[v][e] += f[e];
+                }
             }
         }
     }
@@ -442,10 +465,10 @@ int layernorm_bwd_tail(const __nv_bfloat16* dy_a, const __nv_bfloat16* dy_b, con
         return 0;
     }
     switch (E / 256) {
-        case 1: layernorm_bwd_kernel<1><<<grid, 256, smem, s>>>(dy_a, dy_b, x, stats, gamma, dres, dx, dgamma, dbeta, rows, E, tail); break;
-        case 2: layernorm_bwd_kernel<2><<<grid, 256, smem, s>>>(dy_a, dy_b, x, stats, gamma, dres, dx, dgamma, dbeta, rows, E, tail); break;
-        case 3: layernorm_bwd_kernel<3><<<grid, 256, smem, s>>>(dy_a, dy_b, x, stats, gamma, dres, dx, dgamma, dbeta, rows, E, tail); break;
-        case 4: layernorm_bwd_kernel<4><<<grid, 256, smem, s>>>(dy_a, dy_b, x, stats, gamma, dres, dx, dgamma, dbeta, rows, E, tail); break;
+        case 1: layernorm_bwd_kernel<1, 2><<<grid, 256, smem, s>>>(dy_a, dy_b, x, stats, gamma, dres, dx, dgamma, dbeta, rows, E, tail); break;
+        case 2: layernorm_bwd_kernel<2, 1><<<grid, 256, smem, s>>>(dy_a, dy_b, x, stats, gamma, dres, dx, dgamma, dbeta, rows, E, tail); break;
+        case 3: layernorm_bwd_kernel<3, 1><<<grid, 256, smem, s>>>(dy_a, dy_b, x, stats, gamma, dres, dx, dgamma, dbeta, rows, E, tail); break;
+        case 4: layernorm_bwd_kernel<4, 1><<<grid, 256, smem, s>>>(dy_a, dy_b, x, stats, gamma, dres, dx, dgamma, dbeta, rows, E, tail); break;
         default: set_error("unsupported embedding size %d for LayerNorm backward", E); return -1;
     }
     CB200_CUDA_OK(cudaGetLastError());

@@ -181,7 +181,7 @@ int cb200_set_attention_trace(void* buffer);
  * of per-layer kernels per step.  max_clusters > 0 caps the clusters of the persistent kernel (tests);
  * cluster_size 0 = automatic, 4 or 8 = CTAs per cluster. */
 int cb200_set_decode_impl(int impl, int max_clusters, int cluster_size);
-/* Diagnostic: device buffer of 24 int64 that receives the cycles the first CTA of the persistent decode kernel
+/* Diagnostic: device buffer of 64 int64 (15 phases; ring waits from 16; marks inside the linear phases from 24) that receives the cycles the first CTA of the persistent decode kernel
  * spent in each phase (embedding, ln_1, c_attn, attention, barrier, c_proj, barrier, ln_2 + c_fc, barrier,
  * mlp c_proj, barrier, ln_f + logits, barrier, sampling, barrier), summed over the generation.  NULL disables. */
 int cb200_set_decode_profile(void* counters);

@@ -4,7 +4,7 @@
 
 Every positional argument after REPEATS is one setting: a comma-separated list of environment variables read by
 `decode_mega` at each call (CB200_DECODE_KV_PREFETCH_MB, CB200_DECODE_KV_SPLIT, CB200_DECODE_MAX_CLUSTERS,
-CB200_DECODE_L2_HINTS, CB200_DECODE_RING_STAGES); "-" is the default configuration.
+CB200_DECODE_L2_HINTS, CB200_DECODE_RING_STAGES, CB200_DECODE_ASYNC_GATHER); "-" is the default configuration.
 '''
 import os
 import sys
@@ -20,7 +20,7 @@ from composer_b200.models.transformer import Transformer  # noqa: E402
 B, N, R = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
 settings = sys.argv[4:] or ['-']
 KNOBS = ['CB200_DECODE_KV_PREFETCH_MB', 'CB200_DECODE_KV_SPLIT', 'CB200_DECODE_MAX_CLUSTERS', 'CB200_DECODE_L2_HINTS',
-         'CB200_DECODE_RING_STAGES']
+         'CB200_DECODE_RING_STAGES', 'CB200_DECODE_ASYNC_GATHER']
 E, L, H = 256, 8, 16
 model = Transformer(390, E, 1024, L, H, False, 0.0, 0.02, 0.1, 0.1, 1e-5, True, True)
 prompt = np.random.default_rng(99).integers(0, 390, size=(B, 1))

@@ -44,7 +44,7 @@ for size in [v for v in impls if v != 1]:
     import ctypes
     names = ['embed', 'ln_1', 'c_attn', 'attention', 'barrier A', 'c_proj', 'barrier B', 'ln_2 + c_fc', 'barrier C',
              'mlp c_proj', 'barrier D', 'ln_f + logits', 'barrier E', 'sample', 'barrier F']
-    counters = torch.zeros(24, dtype=torch.int64, device='cuda')
+    counters = torch.zeros(64, dtype=torch.int64, device='cuda')
     _lib.call('cb200_set_decode_impl', 0, 0, size if size in (4, 8) else 0)
     _lib.call('cb200_set_decode_profile', ctypes.c_void_p(counters.data_ptr()))
     model.generate(prompt, N, temperature=1.0, seed=7)
@@ -59,3 +59,6 @@ for size in [v for v in impls if v != 1]:
     print('  (ln_2 alone, up to its __syncthreads: %.0f cyc per layer)' % (c[15] / N / L))
     print('  thread 0 waited for its ring jobs (cyc per layer): c_attn %.0f, attention %.0f, c_proj %.0f, c_fc %.0f, mlp c_proj %.0f; logits %.0f per step'
           % tuple([c[16 + k] / N / L for k in range(5)] + [c[21] / N]))
+    print('  inside the linear phases (thread 0, cyc per layer): to run_phase | ring wait | MMAs | ring release | K-split barrier | reduce + epilogue')
+    for k, name in enumerate(['c_attn', 'c_proj', 'c_fc', 'mlp c_proj', 'logits']):
+        print('    %-12s' % name + ' '.join('%7.0f' % (c[24 + 6 * k + i] / N / (L if k < 4 else 1)) for i in range(6)))
