@@ -828,6 +828,8 @@ decode_mega_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ M
                         // is an A-operand register as it stands)
                         v_lane[ks] = kv_piece_off<D>((mr & ~1) + (mi & 1) + (mr & 1) * 8, PR / 2 + ks * 2 + (mi >> 1));
                     }
+                    FineProf afine{nullptr, 0};
+                    if (PROF && profiling) { afine.acc = prof_acc + 54; afine.t = clock64(); }
                     for (int pi = 0; pi < nmine; ++pi) {
                         const int q = (warp + MG_WARPS * pi) >> ss;
                         const int sl = q / HPC, hh = q % HPC;
@@ -870,6 +872,7 @@ decode_mega_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ M
                             asm volatile("fence.proxy.async.global;" ::: "memory");    // read back by TMA in a later job
                         }
                         __syncwarp();
+                        if (PROF) afine.mark(0);
                         for (int c = plan.split; c < nchunks; c += 1 << ss) {
                             uint8_t* st = ring_acquire<PROF>(jr);
                             const int ntok = min(CT, pos - c * CT);
@@ -928,6 +931,7 @@ decode_mega_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ M
                             }
                             ring_release<D>(jr, plan, lane);
                         }
+                        if (PROF) afine.mark(1);
                         lsum += __shfl_xor_sync(0xffffffffu, lsum, 4);
                         lsum += __shfl_xor_sync(0xffffffffu, lsum, 8);
                         lsum += __shfl_xor_sync(0xffffffffu, lsum, 16);
@@ -966,6 +970,7 @@ decode_mega_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ M
                             }
                             asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_n) : "memory");      // the slots are free again
                         }
+                        if (PROF) afine.mark(2);
                         const float inv = 4.0f / lsum;                  // lsum counted every token in its 4 tig lanes
                         // every quad holds the same output row: quad g sends it to CTA g of the cluster
                         if (AG) {
@@ -994,6 +999,7 @@ decode_mega_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ M
     #pragma unroll
                             for (int dt = 0; dt < NT_O; ++dt) st_cluster_u32(dst + dt * 16, pack_bf16(o[dt][0] * inv, o[dt][1] * inv));
                         }
+                        if (PROF) afine.mark(3);
                     }
                 }
                 if (use_ln) ln_prefetch(lnf, P + lw.ln2_g, P + lw.ln2_b, E, lane);

@@ -60,5 +60,7 @@ for size in [v for v in impls if v != 1]:
     print('  thread 0 waited for its ring jobs (cyc per layer): c_attn %.0f, attention %.0f, c_proj %.0f, c_fc %.0f, mlp c_proj %.0f; logits %.0f per step'
           % tuple([c[16 + k] / N / L for k in range(5)] + [c[21] / N]))
     print('  inside the linear phases (thread 0, cyc per layer): to run_phase | ring wait | MMAs | ring release | K-split barrier | reduce + epilogue')
+    print('  inside the attention phase (thread 0, cyc per layer): q, seed, append %.0f | chunk loop %.0f | merge of the split warps %.0f | output %.0f'
+          % tuple(c[54 + i] / N / L for i in range(4)))
     for k, name in enumerate(['c_attn', 'c_proj', 'c_fc', 'mlp c_proj', 'logits']):
         print('    %-12s' % name + ' '.join('%7.0f' % (c[24 + 6 * k + i] / N / (L if k < 4 else 1)) for i in range(6)))
