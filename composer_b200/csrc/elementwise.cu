@@ -114,12 +114,14 @@ layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restric
     const int row0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW;
     if (row0 >= rows) return;
     const int lane = threadIdx.x & 31;
-    float f[RPW][VPL][8];
+    // The arithmetic runs on packed pairs (FADD2 / FMUL2 / FFMA2): at E = 256 the kernel issued 130 instructions per row
+    // and warp at 55 % issue utilisation, as much instruction- as memory-bound.
+    uint64_t f[RPW][VPL][4];
     float sum[RPW];
 #pragma unroll
     for (int r = 0; r < RPW; ++r) {
-        sum[r] = 0.f;
         const int row = row0 + r < rows ? row0 + r : rows - 1;      // (a clamped duplicate keeps the loop uniform)
+        uint64_t acc = f2_pack(0.f, 0.f);
 #pragma unroll
         for (int v = 0; v < VPL; ++v) {
             const uint4 raw = *reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * E + (v * 32 + lane) * 8);
@@ -127,45 +129,55 @@ layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restric
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const float2 p = unpack_bf16(w[e]);
-                f[r][v][2 * e] = p.x; f[r][v][2 * e + 1] = p.y;
-                sum[r] += p.x + p.y;
+                f[r][v][e] = f2_pack(p.x, p.y);
+                acc = f2_add(acc, f[r][v][e]);
             }
         }
+        float lo, hi;
+        f2_unpack(acc, lo, hi);
+        sum[r] = lo + hi;
     }
-    float g[VPL][8], b[VPL][8];
+    uint64_t g[VPL][4], b[VPL][4];
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
         const int c = (v * 32 + lane) * 8;
         const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
         const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c + 4));
-        g[v][0] = g0.x; g[v][1] = g0.y; g[v][2] = g0.z; g[v][3] = g0.w; g[v][4] = g1.x; g[v][5] = g1.y; g[v][6] = g1.z; g[v][7] = g1.w;
-        b[v][0] = b0.x; b[v][1] = b0.y; b[v][2] = b0.z; b[v][3] = b0.w; b[v][4] = b1.x; b[v][5] = b1.y; b[v][6] = b1.z; b[v][7] = b1.w;
+        g[v][0] = f2_pack(g0.x, g0.y); g[v][1] = f2_pack(g0.z, g0.w); g[v][2] = f2_pack(g1.x, g1.y); g[v][3] = f2_pack(g1.z, g1.w);
+        b[v][0] = f2_pack(b0.x, b0.y); b[v][1] = f2_pack(b0.z, b0.w); b[v][2] = f2_pack(b1.x, b1.y); b[v][3] = f2_pack(b1.z, b1.w);
     }
+    const float inv_e = 1.0f / E;
 #pragma unroll
     for (int r = 0; r < RPW; ++r) {
         const int row = row0 + r;
-        const float mean = warp_sum(sum[r]) / E;
-        float sq = 0.f;
+        const float mean = warp_sum(sum[r]) * inv_e;
+        const uint64_t neg_mean = f2_pack(-mean, -mean);
+        uint64_t sq2 = f2_pack(0.f, 0.f);
 #pragma unroll
         for (int v = 0; v < VPL; ++v)
 #pragma unroll
-            for (int e = 0; e < 8; ++e) { const float d = f[r][v][e] - mean; sq += d * d; }
-        const float rstd = rsqrtf(warp_sum(sq) / E + eps);
+            for (int e = 0; e < 4; ++e) { const uint64_t d = f2_add(f[r][v][e], neg_mean); sq2 = f2_fma(d, d, sq2); }
+        float sq_lo, sq_hi;
+        f2_unpack(sq2, sq_lo, sq_hi);
+        const float rstd = rsqrtf(warp_sum(sq_lo + sq_hi) * inv_e + eps);
         if (row >= rows) continue;
         if (lane == 0 && stats != nullptr) {
             stats[2 * static_cast<size_t>(row)] = mean;
             stats[2 * static_cast<size_t>(row) + 1] = rstd;
         }
+        const uint64_t rstd2 = f2_pack(rstd, rstd);
 #pragma unroll
         for (int v = 0; v < VPL; ++v) {
             const int c = (v * 32 + lane) * 8;
-            float o[8];
+            uint32_t o[4];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) o[e] = (f[r][v][e] - mean) * rstd * g[v][e] + b[v][e];
-            uint4 out;
-            out.x = pack_bf16(o[0], o[1]); out.y = pack_bf16(o[2], o[3]);
-            out.z = pack_bf16(o[4], o[5]); out.w = pack_bf16(o[6], o[7]);
-            *reinterpret_cast<uint4*>(y + static_cast<size_t>(row) * E + c) = out;
+            for (int e = 0; e < 4; ++e) {
+                // (x - mean) * rstd * gamma + beta, the rounding points of the scalar expression
+                float lo, hi;
+                f2_unpack(f2_fma(f2_mul(f2_add(f[r][v][e], neg_mean), rstd2), g[v][e], b[v][e]), lo, hi);
+                o[e] = pack_bf16(lo, hi);
+            }
+            *reinterpret_cast<uint4*>(y + static_cast<size_t>(row) * E + c) = make_uint4(o[0], o[1], o[2], o[3]);
         }
     }
 }
@@ -207,24 +219,23 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy_a, const __nv_bfloat16
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int warps_total = gridDim.x * (blockDim.x >> 5);
-    float gam[VPL][8], pg[VPL][8], pb[VPL][8];
-    float pt[VPL][8];      // column sums of the tail's g = dropout_bwd(dx)
-#pragma unroll
-    for (int v = 0; v < VPL; ++v)
-#pragma unroll
-        for (int e = 0; e < 8; ++e) pt[v][e] = 0.f;
+    // The arithmetic runs on packed pairs (FADD2 / FMUL2 / FFMA2; pair e = columns 2 e, 2 e + 1 of the lane's 8): the
+    // scalar version issued 270 instructions per row and warp at 51 % issue utilisation.
+    uint64_t gam[VPL][4], pg[VPL][4], pb[VPL][4];
+    uint64_t pt[VPL][4];   // column sums of the tail's g = dropout_bwd(dx)
+    const uint64_t zero2 = f2_pack(0.f, 0.f);
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
         const int c = (v * 32 + lane) * 8;
         const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
-        gam[v][0] = g0.x; gam[v][1] = g0.y; gam[v][2] = g0.z; gam[v][3] = g0.w;
-        gam[v][4] = g1.x; gam[v][5] = g1.y; gam[v][6] = g1.z; gam[v][7] = g1.w;
+        gam[v][0] = f2_pack(g0.x, g0.y); gam[v][1] = f2_pack(g0.z, g0.w); gam[v][2] = f2_pack(g1.x, g1.y); gam[v][3] = f2_pack(g1.z, g1.w);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) { pg[v][e] = 0.f; pb[v][e] = 0.f; }
+        for (int e = 0; e < 4; ++e) { pg[v][e] = zero2; pb[v][e] = zero2; pt[v][e] = zero2; }
     }
+    const float inv_e = 1.0f / E;
     // RPI rows per warp and iteration, all their loads issued before the first use.  (Measured at E = 256: two rows in
-    // flight per warp, 118 registers, 31.7 us against 30.1 us with one: the kernel is not short of bytes in flight, it
-    // issues 270 instructions per row and warp at 51 % issue utilisation; RPI = 1 everywhere.)
+    // flight per warp, 118 registers, 31.7 us against 30.1 us with one: the kernel is not short of bytes in flight;
+    // RPI = 1 everywhere.)
     for (int row0 = blockIdx.x * (blockDim.x >> 5) + warp; row0 < rows; row0 += RPI * warps_total) {
         uint4 ra[RPI][VPL], rx[RPI][VPL], rb[RPI][VPL], rr[RPI][VPL];
         float mean[RPI], rstd[RPI];
@@ -250,8 +261,9 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy_a, const __nv_bfloat16
         for (int r = 0; r < RPI; ++r) {
             const int row = row0 + r * warps_total;
             if (row >= rows) break;                   // (warp-uniform)
-            float dyv[VPL][8], xh[VPL][8];
-            float s1 = 0.f, s2 = 0.f;
+            uint64_t dyv[VPL][4], xh[VPL][4];
+            uint64_t s1p = zero2, s2p = zero2;
+            const uint64_t neg_mean = f2_pack(-mean[r], -mean[r]), rstd2 = f2_pack(rstd[r], rstd[r]);
 #pragma unroll
             for (int v = 0; v < VPL; ++v) {
                 const uint32_t wa[4] = {ra[r][v].x, ra[r][v].y, ra[r][v].z, ra[r][v].w};
@@ -260,39 +272,40 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy_a, const __nv_bfloat16
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const float2 a = unpack_bf16(wa[e]), b = unpack_bf16(wb[e]), xx = unpack_bf16(wx[e]);
-                    dyv[v][2 * e] = a.x + b.x; dyv[v][2 * e + 1] = a.y + b.y;
-                    xh[v][2 * e] = (xx.x - mean[r]) * rstd[r]; xh[v][2 * e + 1] = (xx.y - mean[r]) * rstd[r];
-                }
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const float g = dyv[v][e] * gam[v][e];
-                    s1 += g; s2 += g * xh[v][e];
-                    pg[v][e] += dyv[v][e] * xh[v][e];
-                    pb[v][e] += dyv[v][e];
+                    dyv[v][e] = f2_add(f2_pack(a.x, a.y), f2_pack(b.x, b.y));
+                    xh[v][e] = f2_mul(f2_add(f2_pack(xx.x, xx.y), neg_mean), rstd2);
+                    const uint64_t g = f2_mul(dyv[v][e], gam[v][e]);
+                    s1p = f2_add(s1p, g);
+                    s2p = f2_fma(g, xh[v][e], s2p);
+                    pg[v][e] = f2_fma(dyv[v][e], xh[v][e], pg[v][e]);
+                    pb[v][e] = f2_add(pb[v][e], dyv[v][e]);
                 }
             }
-            s1 = warp_sum(s1) / E;
-            s2 = warp_sum(s2) / E;
+            float s1lo, s1hi, s2lo, s2hi;
+            f2_unpack(s1p, s1lo, s1hi);
+            f2_unpack(s2p, s2lo, s2hi);
+            const float s1 = warp_sum(s1lo + s1hi) * inv_e;
+            const float s2 = warp_sum(s2lo + s2hi) * inv_e;
+            const uint64_t neg_s1 = f2_pack(-s1, -s1), neg_s2 = f2_pack(-s2, -s2);
 #pragma unroll
             for (int v = 0; v < VPL; ++v) {
                 const size_t off = static_cast<size_t>(row) * E + (v * 32 + lane) * 8;
-                float o[8];
+                if (RPI == 1 && dres != nullptr) rr[r][v] = *reinterpret_cast<const uint4*>(dres + off);      // (late: fewer live registers)
+                const uint32_t wr[4] = {rr[r][v].x, rr[r][v].y, rr[r][v].z, rr[r][v].w};
+                uint32_t wo[4];
+                float f[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) o[e] = rstd[r] * (dyv[v][e] * gam[v][e] - s1 - xh[v][e] * s2);
-                if (dres != nullptr) {
-                    if (RPI == 1) rr[r][v] = *reinterpret_cast<const uint4*>(dres + off);      // (late: fewer live registers)
-                    const uint32_t wr[4] = {rr[r][v].x, rr[r][v].y, rr[r][v].z, rr[r][v].w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) { const float2 q = unpack_bf16(wr[e]); o[2 * e] += q.x; o[2 * e + 1] += q.y; }
+                for (int e = 0; e < 4; ++e) {
+                    // rstd * (dy * gamma - s1 - xhat * s2) (+ dres)
+                    uint64_t o = f2_mul(rstd2, f2_fma(xh[v][e], neg_s2, f2_fma(dyv[v][e], gam[v][e], neg_s1)));
+                    if (dres != nullptr) { const float2 q = unpack_bf16(wr[e]); o = f2_add(o, f2_pack(q.x, q.y)); }
+                    float lo, hi;
+                    f2_unpack(o, lo, hi);
+                    wo[e] = pack_bf16(lo, hi);
                 }
-                uint4 out;
-                out.x = pack_bf16(o[0], o[1]); out.y = pack_bf16(o[2], o[3]);
-                out.z = pack_bf16(o[4], o[5]); out.w = pack_bf16(o[6], o[7]);
-                *reinterpret_cast<uint4*>(dx + off) = out;
+                *reinterpret_cast<uint4*>(dx + off) = make_uint4(wo[0], wo[1], wo[2], wo[3]);
                 if (tail.dbias != nullptr) {
                     // what bias_grad would do with dx as its input: the bf16-rounded values, the same keep mask
-                    const uint32_t wo[4] = {out.x, out.y, out.z, out.w};
-                    float f[8];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) { const float2 q = unpack_bf16(wo[e]); f[2 * e] = q.x; f[2 * e + 1] = q.y; }
                     if (tail.drop.threshold16 != 0) {
@@ -305,7 +318,7 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy_a, const __nv_bfloat16
                         *reinterpret_cast<uint4*>(tail.g_out + off) = g;
                     }
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) pt[v][e] += f[e];
+                    for (int e = 0; e < 4; ++e) pt[v][e] = f2_add(pt[v][e], f2_pack(f[2 * e], f[2 * e + 1]));
                 }
             }
         }
@@ -317,11 +330,17 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy_a, const __nv_bfloat16
 #pragma unroll
     for (int v = 0; v < VPL; ++v)
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const int c = (v * 32 + lane) * 8 + e;
-            atomicAdd(&red[c], pg[v][e]);
-            atomicAdd(&red[E + c], pb[v][e]);
-            if (tail.dbias != nullptr) atomicAdd(&red[2 * E + c], pt[v][e]);
+        for (int e = 0; e < 4; ++e) {
+            const int c = (v * 32 + lane) * 8 + 2 * e;
+            float lo, hi;
+            f2_unpack(pg[v][e], lo, hi);
+            atomicAdd(&red[c], lo); atomicAdd(&red[c + 1], hi);
+            f2_unpack(pb[v][e], lo, hi);
+            atomicAdd(&red[E + c], lo); atomicAdd(&red[E + c + 1], hi);
+            if (tail.dbias != nullptr) {
+                f2_unpack(pt[v][e], lo, hi);
+                atomicAdd(&red[2 * E + c], lo); atomicAdd(&red[2 * E + c + 1], hi);
+            }
         }
     __syncthreads();
     for (int i = threadIdx.x; i < E; i += blockDim.x) {

@@ -599,6 +599,39 @@ def check_generate_impls_agree(B=19, prompt_len=3, length=50, embedding=256, hea
     return _finish(results)
 
 
+def check_generate_gather_modes_agree(B=13, prompt_len=3, length=150, window=192):
+    '''The persistent decode kernel completes its all-gathers either on mbarriers (st.async) or at cluster barriers
+    (full clusters; CB200_DECODE_ASYNC_GATHER overrides the launcher's choice).  The arithmetic is the same, so the
+    tokens, the uniforms and the final logits have to be identical, for both cluster sizes.'''
+    import os
+    import numpy as np
+
+    model, cfg, _ = _small_model(3, 256, 16, window=window)
+    rng = np.random.default_rng(5)
+    prompt = rng.integers(0, cfg.vocab_size, size=(B, prompt_len))
+    results = []
+    saved = os.environ.get('CB200_DECODE_ASYNC_GATHER')
+    try:
+        for size in (8, 4):
+            outs = []
+            for mode in ('0', '1'):
+                os.environ['CB200_DECODE_ASYNC_GATHER'] = mode
+                _lib.call('cb200_set_decode_impl', 0, 0, size)
+                ids, uniforms, logits = model.generate(prompt, length, temperature=1.0, seed=11, return_uniforms=True,
+                                                       return_last_logits=True)
+                outs.append((ids.cpu().numpy(), uniforms.cpu().numpy(), logits.float().cpu().numpy()))
+            same = all(np.array_equal(x, y) for x, y in zip(outs[0], outs[1]))
+            results.append({'name': 'cluster size %d: ids, uniforms, logits identical in both gather modes' % size,
+                            'rel': 0.0 if same else 1.0, 'tol': 0.0, 'nan': False, 'ok': same})
+    finally:
+        _lib.call('cb200_set_decode_impl', 0, 0, 0)
+        if saved is None:
+            os.environ.pop('CB200_DECODE_ASYNC_GATHER', None)
+        else:
+            os.environ['CB200_DECODE_ASYNC_GATHER'] = saved
+    return _finish(results)
+
+
 def _check_generate(B, prompt_len, length, embedding, heads, window=64, sharp=False):
     import numpy as np
     from oracle import transformer_oracle as oracle
@@ -692,6 +725,7 @@ GROUPS['generate'] = [check_generate, lambda: check_generate(impl=1),
                       lambda: check_generate(B=3, prompt_len=70, length=90, window=192),
                       lambda: check_generate(B=10, prompt_len=2, length=140, window=192, cluster_size=4),
                       lambda: check_generate_impls_agree(B=6, prompt_len=2, length=250, window=256),
+                      check_generate_gather_modes_agree,
                       # sharp attention (see check_generate): d_h 16 with 8- and 4-CTA clusters and split pairs, d_h 32,
                       # the per-step kernels, and d_h 64
                       lambda: check_generate(B=3, prompt_len=40, length=150, window=192, sharp=True),
