@@ -19,6 +19,13 @@ rm -f gpurun_out/prof_step_r2.ncu-rep
 timeout -s KILL 900 ncu --set full --clock-control none -k regex:decode_mega_kernel -f -o gpurun_out/prof_mega_r2 python tools/profile_decode_mega.py 256 1 1024 > gpurun_out/r2m_ncu_mega.log 2>&1
 tail -2 gpurun_out/r2m_ncu_mega.log
 python tools/ncu_summary.py kernels gpurun_out/prof_mega_r2.ncu-rep gpurun_out/ncu_summary_r2.json "prof_mega_r2: the bench.py generation exactly (256 sequences, prompt 1, 1,024 events), ncu --set full" > /dev/null
+# the decode kernel at the 8-GPU split of the bench (32 sequences per GPU): ncu capture and phase profile
+timeout -s KILL 600 ncu --set full --clock-control none -k regex:decode_mega_kernel -f -o gpurun_out/prof_mega_b32_r2 python tools/profile_decode_mega.py 32 1 1024 > gpurun_out/r2m_ncu_mega_b32.log 2>&1
+python tools/ncu_summary.py kernels gpurun_out/prof_mega_b32_r2.ncu-rep gpurun_out/ncu_summary_r2.json "prof_mega_b32_r2: generation of 32 sequences (one GPU's share at N = 8), prompt 1, 1,024 events, ncu --set full" > /dev/null
+rm -f gpurun_out/prof_mega_b32_r2.ncu-rep gpurun_out/prof_mega_r2.ncu-rep
+timeout -s KILL 300 python tools/bench_decode.py 32 1024 8 > gpurun_out/decode_b32_r2.txt 2>&1
+timeout -s KILL 300 python tools/bench_decode.py 256 1024 0 > gpurun_out/decode_b256_r2.txt 2>&1
+timeout -s KILL 300 python tools/microbench.py > gpurun_out/microbench_r2.txt 2>&1
 cp gpurun_out/ncu_summary_r2.json profiles/ncu_summary.json
 timeout -s KILL 600 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_r2_n1.json 2> gpurun_out/bench_r2_n1.err
 tail -c 400 gpurun_out/bench_r2_n1.json
