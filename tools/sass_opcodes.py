@@ -13,7 +13,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 WATCH = ['UTCHMMA', 'UTCBAR', 'LDTM', 'STTM', 'UTMALDG', 'UTMASTG', 'UBLKCP', 'HMMA', 'LDSM', 'LDGSTS', 'MUFU',
-         'FFMA2', 'FMUL2', 'FADD2', 'SYNCS', 'REDG', 'RED', 'UCGABAR_ARV']
+         'FFMA2', 'FMUL2', 'FADD2', 'SYNCS', 'REDG', 'RED', 'UCGABAR_ARV', 'STAS', 'MEMBAR', 'CCTL']
 
 
 def main():
